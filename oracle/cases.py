@@ -1,0 +1,51 @@
+"""TEST INFRASTRUCTURE — seeded parity cases shared by oracle/make_golden.py and tests/.
+
+Every case is a pure function of (seed, shape) through seesaw_b200.synth, so fixtures hold only
+reference OUTPUTS and the tests regenerate the inputs."""
+import numpy as np
+
+from seesaw_b200 import synth
+
+CASES = {
+    # name: dict(kind of case + generator parameters)
+    "ms_small": dict(n_images=400, p_lo=3, p_hi=9, dim=512, seed=11, qseed=12),
+    "ms_wide": dict(n_images=1500, p_lo=20, p_hi=60, dim=512, seed=21, qseed=22),
+    "ms_768": dict(n_images=300, p_lo=1, p_hi=5, dim=768, seed=31, qseed=32),
+}
+COARSE = dict(n=10000, dim=512, seed=0, qseed=1, xseed=2, n_excl=300, topk=10)   # BASELINE config 1
+KNN = {
+    "knn_600": dict(n=600, dim=512, seed=41, k=10),
+    "knn_small_n": dict(n=7, dim=512, seed=42, k=10),       # k+1 > N  -> k1 = N (knn_graph.py:172)
+    "knn_dups": dict(n=300, dim=512, seed=43, k=5, dup=True),  # duplicate vectors: self may not rank first
+}
+
+
+def ms_inputs(c):
+    counts = synth.patches_per_image(c["n_images"], c["p_lo"], c["p_hi"], c["seed"])
+    meta = synth.synth_vector_meta(counts, c["seed"] + 1000, dbidx_start=5, dbidx_stride=3)
+    vecs = synth.synth_rows(0, int(counts.sum()), c["dim"], c["seed"], "tri", np.float32)
+    q = synth.unit_queries(4, c["dim"], c["qseed"])
+    return vecs, meta, q
+
+
+def exclude_sets(meta, seed):
+    ids = np.unique(meta.dbidx.values)
+    rng = np.random.default_rng(seed)
+    return {
+        "none": np.zeros(0, np.int64),
+        "some": np.sort(rng.choice(ids, size=min(30, len(ids) // 2), replace=False)),
+        "most": np.sort(rng.choice(ids, size=len(ids) - 7, replace=False)),   # eligible < k
+        "all": ids.copy(),                                                    # k' == 0
+        "foreign": np.concatenate([ids[:5], np.array([10 ** 6, 10 ** 6 + 1])]),  # ids not in the DB
+    }
+
+
+def knn_inputs(c):
+    v = synth.synth_rows(0, c["n"], c["dim"], c["seed"], "tri", np.float32)
+    v = v / np.linalg.norm(v, axis=1, keepdims=True)
+    v = v.astype(np.float16).astype(np.float32)            # fp16-valued, as BASELINE config 4
+    if c.get("dup"):
+        v[1::10] = v[0::10][: len(v[1::10])]                # exact duplicates
+    return v
+
+

@@ -1,0 +1,88 @@
+"""TEST INFRASTRUCTURE — regenerate tests/golden/reference_outputs.npz.
+
+Runs the UNMODIFIED reference (/root/reference, imported through oracle/refstubs.py) on seeded
+synthetic inputs and stores its outputs.  Inputs are not stored: every case is a function of
+(seed, shape) through seesaw_b200.synth, so the fixtures stay small and tests regenerate inputs.
+Only tie-free float data is used here: the reference's np.argsort is unstable, so its output
+on exactly tied scores is not a definition.
+
+    python oracle/make_golden.py            # needs /root/reference; the GPU box never runs this
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+from refstubs import import_reference  # noqa: E402
+from seesaw_b200 import synth  # noqa: E402
+
+from cases import CASES, COARSE, KNN, ms_inputs, exclude_sets, knn_inputs  # noqa: E402
+
+
+def main():
+    ref = import_reference()
+    BitMap = ref.BitMap
+    out = {}
+    for name, c in CASES.items():
+        vecs, meta, qs = ms_inputs(c)
+        idx = ref.multiscale.MultiscaleIndex(embedding=None, vectors=vecs, vector_meta=meta, vec_index=None)
+        for xname, ex in exclude_sets(meta, c["seed"] + 7).items():
+            for qi in range(2):
+                q = qs[qi]
+                r = idx._query_prelim(vector=q, topk_dbidx=50, exclude_dbidx=BitMap(ex))
+                key = f"{name}/prelim/{xname}/{qi}"
+                if isinstance(r, tuple):                   # the reference's "[], [], []" (multiscale_index.py:302)
+                    out[key + "/dbidx"] = np.zeros(0, np.int64)
+                    out[key + "/score"] = np.zeros(0, np.float32)
+                    continue
+                out[key + "/dbidx"] = r["dbidx"].values.astype(np.int64)
+                out[key + "/score"] = r["max_score"].values.astype(np.float32)
+        for agg, topk, use_v2 in (("plain_score", 1, False), ("plain_score", 3, True), ("avg_score", 3, False)):
+            if agg == "avg_score" and name == "ms_wide":
+                continue                                   # slow and adds nothing
+            ex = exclude_sets(meta, c["seed"] + 7)["some"]
+            r = idx.query(vector=qs[2], vector2=qs[3] * 0.25 if use_v2 else None, topk=topk,
+                          shortlist_size=50, exclude=BitMap(ex), agg_method=agg, aug_larger="all",
+                          rescore_method=None)
+            key = f"{name}/query/{agg}/{topk}/{int(use_v2)}"
+            out[key + "/dbidxs"] = np.asarray(r["dbidxs"]).astype(np.int64)
+            out[key + "/act_score"] = np.array([a.score.values[0] for a in r["activations"]], np.float64)
+            out[key + "/act_box"] = np.array([a[["x1", "y1", "x2", "y2"]].values[0] for a in r["activations"]], np.int64)
+
+    c = COARSE
+    v = synth.synth_rows(0, c["n"], c["dim"], c["seed"], "tri", np.float32)
+    import pandas as pd
+    cmeta = pd.DataFrame({"dbidx": np.arange(c["n"], dtype=np.int64)})
+    cidx = ref.coarse.CoarseIndex(embedding=None, vectors=v, vector_meta=cmeta)
+    q = synth.unit_queries(1, c["dim"], c["qseed"])[0]
+    ex = np.sort(np.random.default_rng(c["xseed"]).choice(c["n"], size=c["n_excl"], replace=False))
+    r = cidx.query(topk=c["topk"], vector=q, exclude=BitMap(ex))
+    out["coarse/dbidxs"] = np.asarray(r["dbidxs"]).astype(np.int64)
+    out["coarse/scores"] = np.array([a.score.values[0] for a in r["activations"]], np.float32)
+    out["coarse/nextstartk"] = np.array([r["nextstartk"]])
+
+    for name, c in KNN.items():
+        v = knn_inputs(c)
+        df = ref.knn_graph.compute_exact_knn(v, n_neighbors=c["k"])
+        for col in ("src_vertex", "dst_vertex", "distance", "dst_rank"):
+            out[f"{name}/{col}"] = df[col].values
+    # the reference's own unit pin (multiscale_index.py:182-187)
+    out["pin/distinct_topk_positions"] = ref.multiscale.distinct_topk_positions(
+        np.array([10, 11, 11, 12, 12, 12, 13, 13]), 2)
+
+    path = os.path.join(ROOT, "tests", "golden", "reference_outputs.npz")
+    np.savez_compressed(path, **out)
+    with open(os.path.join(ROOT, "tests", "golden", "reference_cases.json"), "w") as f:
+        json.dump(dict(multiscale=CASES, coarse=COARSE, knn=KNN,
+                       note="outputs of the unmodified reference; regenerate with oracle/make_golden.py"), f, indent=1)
+    print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path)} bytes")
+
+
+if __name__ == "__main__":
+    main()
