@@ -1,0 +1,137 @@
+/*
+ * seesaw_b200 — C ABI of the B200-native SeeSaw vector-search hot path.
+ *
+ * This is the drop-in boundary.  The reference (orm011/seesaw 1.3.0) has no FFI: its hot path is
+ * numpy/pandas inside three Python plug points.  Every entry point below names
+ * the reference code it replaces (paths relative to /root/reference/seesaw); INTEGRATION.md
+ * shows the ctypes stub a reference maintainer would add at each plug point.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and a
+ * non-zero ssw_status otherwise, with a message available from ssw_last_error() (thread local).
+ * The caller owns every host buffer; the library owns device memory until ssw_db_destroy().
+ * A handle is thread-compatible (use from one thread at a time).  There is NO CPU fallback:
+ * without a CUDA device of compute capability 10.x every compute entry point fails with
+ * SSW_ERR_NO_DEVICE.
+ *
+ * Tie-breaking definition (the reference's np.argsort is unstable, so this is imposed):
+ *   rows are ranked by (score desc, original row asc); an image is represented by its best row;
+ *   images are ranked by (best score desc, best row asc).  kNN columns by (fp32(1-dot) asc, column asc).
+ */
+#ifndef SEESAW_B200_H_
+#define SEESAW_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ssw_db ssw_db;
+
+enum ssw_dtype { SSW_F32 = 0, SSW_F16 = 1 };
+enum ssw_synth_kind { SSW_SYNTH_TRI = 0, SSW_SYNTH_LATTICE = 1 };
+enum ssw_status {
+  SSW_OK = 0,
+  SSW_ERR_INVALID = 1,     /* bad argument (null pointer, unsupported dim, k out of range ...) */
+  SSW_ERR_NO_DEVICE = 2,   /* no sm_100 device / CUDA driver: there is no CPU path            */
+  SSW_ERR_CUDA = 3,        /* a CUDA runtime call or kernel failed                            */
+  SSW_ERR_OOM = 4
+};
+
+#define SSW_MAX_TOPK 2048      /* largest k of the fused scan epilogue                        */
+#define SSW_MAX_BATCH 64       /* queries per tensor-core batched pass (larger nq is looped)  */
+#define SSW_MAX_KNN_K1 64      /* largest n_neighbors+1 of the fused kNN epilogue             */
+
+const char* ssw_last_error(void);
+int ssw_version(void);
+/* number of usable sm_100 devices; 0 (and SSW_OK) when none */
+int ssw_device_count(int* out_count);
+
+/* ---- database --------------------------------------------------------------------------
+ * Replaces the in-RAM arrays of MultiscaleIndex.__init__ / CoarseIndex.__init__
+ * (indices/multiscale/multiscale_index.py:203-231, indices/coarse/coarse_index.py:22-30):
+ * `vectors` [n_rows, dim] row-major in ORIGINAL order plus vector_meta.dbidx per row.
+ * The device copy is stably grouped by dbidx (CSR over images); results always refer to
+ * original row positions.  dtype_in is the host buffer's type, dtype_store the HBM type
+ * (fp16 storage of fp32 input rounds to nearest: the "looser bound" case of the north star).
+ * global_row_base: original index of row 0 when this is one shard of a row-sharded database
+ * (tie-breaking and returned rows are global).  dim must be a multiple of 256 and <= 1024. */
+int ssw_db_create(ssw_db** out, int device, const void* vectors, int dtype_in, int dtype_store,
+                  int64_t n_rows, int dim, const int32_t* dbidx_per_row, int64_t global_row_base);
+/* Same, with the vectors generated in HBM by the counter-based generator of
+ * seesaw_b200/synth.py (row r of this shard is global row global_row_base + r). */
+int ssw_db_create_synthetic(ssw_db** out, int device, int dtype_store, int64_t n_rows, int dim,
+                            const int32_t* dbidx_per_row, int64_t global_row_base,
+                            uint64_t seed, int kind);
+int ssw_db_destroy(ssw_db* db);
+int ssw_db_info(const ssw_db* db, int64_t* n_rows, int64_t* n_images, int* dim, int* dtype_store,
+                int* device);
+/* device pointer to the stored vectors (grouped order) — for zero-copy consumers (kNN build) */
+int ssw_db_vectors_device(const ssw_db* db, void** dev_ptr);
+
+/* ---- stage-1 scan ----------------------------------------------------------------------
+ * Replaces _get_top_exact + _get_top_dbidxs as called by MultiscaleIndex._query_prelim
+ * (multiscale_index.py:170-175, 189-199, 291-312) and the mask/matvec/argsort of
+ * CoarseIndex.query (coarse_index.py:57-96); also serves VectorIndex.query
+ * (vector_index.py:55-60) when every row is its own image.
+ * For each of nq fp32 queries [nq, dim]: s = V.q per row, per-image max over rows, images whose
+ * dbidx is in that query's exclude list dropped, best k images returned best-first.
+ * exclude_dbidx / exclude_offsets [nq+1] form per-query id lists (any order, ids absent from
+ * the database are ignored); both may be NULL for "no exclusion".
+ * Outputs are [nq, k] row-major; out_count[q] = min(k, #eligible images); slots past the count
+ * are filled with dbidx -1, score -inf, row -1.  Any output pointer may be NULL. */
+int ssw_scan_topk(ssw_db* db, const float* queries, int nq, int k,
+                  const int32_t* exclude_dbidx, const int64_t* exclude_offsets,
+                  int32_t* out_dbidx, float* out_score, int64_t* out_row, int32_t* out_count);
+
+/* Device-resident variant used for the HBM-resident benchmark leg and the multi-GPU path.
+ * All pointers are DEVICE pointers on db's device; `stream` is a cudaStream_t (0 = default).
+ * exclude_bits: [nq, ssw_exclude_words(db)] uint32 bitmaps over LOCAL image indices, or NULL.
+ * out_key [nq,k] uint64 = (order-preserving score bits << 32) | ~global_row, 0 for empty slots,
+ * out_dbidx [nq,k] int32.  Asynchronous: returns after enqueueing. */
+int ssw_scan_topk_device(ssw_db* db, const float* d_queries, int nq, int k,
+                         const uint32_t* d_exclude_bits, uint64_t* d_out_key, int32_t* d_out_dbidx,
+                         void* stream);
+int ssw_exclude_words(const ssw_db* db, int64_t* words_per_query);
+/* Build the bitmaps on the device from id lists already in device memory. */
+int ssw_exclude_build_device(ssw_db* db, const int32_t* d_exclude_dbidx, const int64_t* d_exclude_offsets,
+                             int nq, int64_t n_ids_total, uint32_t* d_bits_out, void* stream);
+/* Merge n_lists candidate lists per query ([n_lists, nq, k] keys + dbidx, e.g. the all-gathered
+ * per-shard outputs of ssw_scan_topk_device) into the global top-k, and decode it.
+ * d_out_* are device pointers [nq,k] (each may be NULL). */
+int ssw_merge_topk_device(int device, const uint64_t* d_keys, const int32_t* d_dbidx, int n_lists,
+                          int nq, int k, uint64_t* d_out_key, int32_t* d_out_dbidx,
+                          float* d_out_score, int64_t* d_out_row, int32_t* d_out_count, void* stream);
+
+/* Kernel selection for ssw_scan_topk*: 0 = auto (streaming SIMT kernel for nq < 8 queries,
+ * tcgen05 batched kernel otherwise), 1 = force streaming kernel, 2 = force tcgen05 kernel. */
+int ssw_set_scan_mode(ssw_db* db, int mode);
+
+/* ---- full score vector -----------------------------------------------------------------
+ * Replaces MultiscaleIndex.score / CoarseIndex.score (multiscale_index.py:284-285,
+ * coarse_index.py:37-38): out_scores[n_rows] fp32 in ORIGINAL row order (host pointer). */
+int ssw_score_all(ssw_db* db, const float* query, float* out_scores);
+int ssw_score_all_device(ssw_db* db, const float* d_query, float* d_out_scores, void* stream);
+
+/* ---- exact kNN graph -------------------------------------------------------------------
+ * Replaces the matmul + row argsort of compute_exact_knn (knn_graph.py:170-182):
+ * for rows [row_begin,row_end) of vectors [n, dim]: the k1 = min(n_neighbors+1, n) columns j
+ * minimising (fp32(1 - dot(i,j)), j), self included when it ranks.  out_idx/out_dist are
+ * [(row_end-row_begin), k1] host buffers.  The caller runs post_process_graph_df unchanged
+ * (knn_graph.py:142-168).  dtype_in fp32 input is rounded to fp16 for the tensor cores
+ * (exact for fp16-valued data). */
+int ssw_knn_build(int device, const void* vectors, int dtype_in, int64_t n, int dim, int k1,
+                  int64_t row_begin, int64_t row_end, int32_t* out_idx, float* out_dist);
+/* d_vectors_f16: [n, dim] fp16 already in HBM; outputs device [(row_end-row_begin), k1]. */
+int ssw_knn_build_device(int device, const void* d_vectors_f16, int64_t n, int dim, int k1,
+                         int64_t row_begin, int64_t row_end, int32_t* d_out_idx, float* d_out_dist,
+                         void* stream);
+
+/* ---- introspection for benchmarks / tests ---------------------------------------------- */
+/* number of kernels this library has launched since load (all handles) */
+int64_t ssw_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEESAW_B200_H_ */

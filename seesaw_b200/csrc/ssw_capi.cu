@@ -1,0 +1,478 @@
+// C ABI of libseesaw_b200: handle management, uploads, and the host-pointer wrappers around the
+// device entry points.  See include/seesaw_b200.h for the contract and the reference citations.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "ssw_db.h"
+
+namespace ssw {
+
+static thread_local std::string t_error;
+int64_t g_launch_count = 0;
+
+void set_error(const std::string& msg) { t_error = msg; }
+
+int ensure_device(int device, int* sm_count) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available: seesaw_b200 has no CPU path");
+    return SSW_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) {
+    set_error("device index out of range");
+    return SSW_ERR_INVALID;
+  }
+  cudaDeviceProp p;
+  SSW_CUDA(cudaGetDeviceProperties(&p, device));
+  if (p.major != 10) {
+    set_error(std::string("device '") + p.name + "' is not sm_100 (Blackwell B200); kernels are sm_100a only");
+    return SSW_ERR_NO_DEVICE;
+  }
+  SSW_CUDA(cudaSetDevice(device));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  return SSW_OK;
+}
+
+template <typename T>
+static int dev_alloc(T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  SSW_CUDA(cudaMalloc((void**)p, n * sizeof(T)));
+  return SSW_OK;
+}
+
+static int ensure_lists(ssw_db* db, int nq, int lists, int k) {
+  const size_t need = (size_t)nq * lists * k;
+  if (need > db->list_capacity) {
+    if (db->d_list_keys) cudaFree(db->d_list_keys);
+    if (db->d_list_dbidx) cudaFree(db->d_list_dbidx);
+    db->list_capacity = 0;
+    int rc = dev_alloc(&db->d_list_keys, need);
+    if (rc) return rc;
+    rc = dev_alloc(&db->d_list_dbidx, need);
+    if (rc) return rc;
+    db->list_capacity = need;
+  }
+  if (nq > db->gthr_capacity) {
+    if (db->d_gthr) cudaFree(db->d_gthr);
+    db->gthr_capacity = 0;
+    int rc = dev_alloc(&db->d_gthr, (size_t)nq);
+    if (rc) return rc;
+    db->gthr_capacity = nq;
+  }
+  return SSW_OK;
+}
+
+static int ensure_stage(ssw_db* db, size_t dev_bytes, size_t host_bytes) {
+  if (dev_bytes > db->d_stage_bytes) {
+    if (db->d_stage) cudaFree(db->d_stage);
+    db->d_stage_bytes = 0;
+    SSW_CUDA(cudaMalloc(&db->d_stage, dev_bytes));
+    db->d_stage_bytes = dev_bytes;
+  }
+  if (host_bytes > db->h_stage_bytes) {
+    if (db->h_stage) cudaFreeHost(db->h_stage);
+    db->h_stage_bytes = 0;
+    SSW_CUDA(cudaMallocHost(&db->h_stage, host_bytes));
+    db->h_stage_bytes = host_bytes;
+  }
+  return SSW_OK;
+}
+
+// Builds the image CSR, the (optional) permutation and the scan partition; uploads the metadata.
+static int build_layout(ssw_db* db, const int32_t* dbidx_per_row, std::vector<int64_t>* perm_out) {
+  const int64_t n = db->n_rows;
+  bool sorted = true;
+  for (int64_t i = 1; i < n; ++i)
+    if (dbidx_per_row[i] < dbidx_per_row[i - 1]) {
+      sorted = false;
+      break;
+    }
+  std::vector<int64_t> perm;   // device row -> original row
+  if (!sorted) {
+    perm.resize(n);
+    std::iota(perm.begin(), perm.end(), (int64_t)0);
+    std::stable_sort(perm.begin(), perm.end(),
+                     [&](int64_t x, int64_t y) { return dbidx_per_row[x] < dbidx_per_row[y]; });
+  }
+  std::vector<int32_t> img_of_row(n + 1);
+  std::vector<int32_t> img_dbidx;
+  std::vector<int64_t> row_ptr;
+  int32_t prev = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int32_t d = dbidx_per_row[sorted ? i : perm[i]];
+    if (i == 0 || d != prev) {
+      img_dbidx.push_back(d);
+      row_ptr.push_back(i);
+      prev = d;
+    }
+    img_of_row[i] = (int32_t)img_dbidx.size() - 1;
+  }
+  img_of_row[n] = -1;
+  row_ptr.push_back(n);
+  db->n_images = (int64_t)img_dbidx.size();
+  db->excl_words = ((db->n_images + 31) / 32 + 3) / 4 * 4;
+  if (db->excl_words == 0) db->excl_words = 4;
+
+  // scan partition: warp g gets images [part[g], part[g+1]) with ~n/G rows each
+  const int G = db->scan_grid * kScanWarps;
+  std::vector<int32_t> part(G + 1);
+  for (int g = 0; g <= G; ++g) {
+    const int64_t target = (int64_t)((__int128)n * g / G);
+    part[g] = (int32_t)(std::lower_bound(row_ptr.begin(), row_ptr.end(), target) - row_ptr.begin());
+    if (part[g] > db->n_images) part[g] = (int32_t)db->n_images;
+  }
+  part[0] = 0;
+  part[G] = (int32_t)db->n_images;
+
+  int rc;
+  if ((rc = dev_alloc(&db->d_img_of_row, (size_t)n + 1))) return rc;
+  if ((rc = dev_alloc(&db->d_row_ptr, row_ptr.size()))) return rc;
+  if ((rc = dev_alloc(&db->d_img_dbidx, img_dbidx.size()))) return rc;
+  if ((rc = dev_alloc(&db->d_part, part.size()))) return rc;
+  SSW_CUDA(cudaMemcpy(db->d_img_of_row, img_of_row.data(), (n + 1) * 4, cudaMemcpyHostToDevice));
+  SSW_CUDA(cudaMemcpy(db->d_row_ptr, row_ptr.data(), row_ptr.size() * 8, cudaMemcpyHostToDevice));
+  if (!img_dbidx.empty())
+    SSW_CUDA(cudaMemcpy(db->d_img_dbidx, img_dbidx.data(), img_dbidx.size() * 4, cudaMemcpyHostToDevice));
+  SSW_CUDA(cudaMemcpy(db->d_part, part.data(), part.size() * 4, cudaMemcpyHostToDevice));
+  if (!sorted) {
+    if ((rc = dev_alloc(&db->d_orig_row, (size_t)n))) return rc;
+    SSW_CUDA(cudaMemcpy(db->d_orig_row, perm.data(), n * 8, cudaMemcpyHostToDevice));
+  }
+  if (perm_out) *perm_out = std::move(perm);
+  return SSW_OK;
+}
+
+static int db_new(ssw_db** out, int device, int dtype_store, int64_t n_rows, int dim, int64_t row_base) {
+  SSW_REQUIRE(out != nullptr, "out handle is null");
+  *out = nullptr;
+  SSW_REQUIRE(dtype_store == SSW_F16 || dtype_store == SSW_F32, "dtype_store must be SSW_F32 or SSW_F16");
+  SSW_REQUIRE(n_rows >= 0 && n_rows < (int64_t)0xFFFFFFFFll, "n_rows out of range");
+  SSW_REQUIRE(row_base >= 0 && row_base + n_rows < (int64_t)0xFFFFFFFFll, "global row index must fit 32 bits");
+  SSW_REQUIRE(dim == 256 || dim == 512 || dim == 768 || dim == 1024, "dim must be 256, 512, 768 or 1024");
+  int sms = 0;
+  int rc = ensure_device(device, &sms);
+  if (rc) return rc;
+  ssw_db* db = new ssw_db();
+  db->device = device;
+  db->dim = dim;
+  db->dtype = dtype_store;
+  db->n_rows = n_rows;
+  db->row_base = row_base;
+  db->sm_count = sms;
+  db->scan_grid = sms;
+  cudaError_t e = cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete db;
+    set_error(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    return SSW_ERR_CUDA;
+  }
+  *out = db;
+  return SSW_OK;
+}
+
+}  // namespace ssw
+
+using namespace ssw;
+
+extern "C" {
+
+const char* ssw_last_error(void) { return t_error.c_str(); }
+int ssw_version(void) { return 100; }
+int64_t ssw_kernel_launch_count(void) { return g_launch_count; }
+
+int ssw_device_count(int* out_count) {
+  SSW_REQUIRE(out_count != nullptr, "out_count is null");
+  *out_count = 0;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return SSW_OK;
+  }
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++*out_count;
+  }
+  return SSW_OK;
+}
+
+int ssw_db_destroy(ssw_db* db) {
+  if (!db) return SSW_OK;
+  cudaSetDevice(db->device);
+  if (db->stream) cudaStreamSynchronize(db->stream);
+  cudaFree(db->d_vecs);
+  cudaFree(db->d_img_of_row);
+  cudaFree(db->d_row_ptr);
+  cudaFree(db->d_img_dbidx);
+  cudaFree(db->d_orig_row);
+  cudaFree(db->d_part);
+  cudaFree(db->d_tile_img);
+  cudaFree(db->d_list_keys);
+  cudaFree(db->d_list_dbidx);
+  cudaFree(db->d_gthr);
+  cudaFree(db->d_stage);
+  if (db->h_stage) cudaFreeHost(db->h_stage);
+  if (db->stream) cudaStreamDestroy(db->stream);
+  delete db;
+  return SSW_OK;
+}
+
+int ssw_db_create(ssw_db** out, int device, const void* vectors, int dtype_in, int dtype_store,
+                  int64_t n_rows, int dim, const int32_t* dbidx_per_row, int64_t global_row_base) {
+  SSW_REQUIRE(vectors != nullptr || n_rows == 0, "vectors is null");
+  SSW_REQUIRE(dbidx_per_row != nullptr || n_rows == 0, "dbidx_per_row is null");
+  SSW_REQUIRE(dtype_in == SSW_F16 || dtype_in == SSW_F32, "dtype_in must be SSW_F32 or SSW_F16");
+  ssw_db* db = nullptr;
+  int rc = db_new(&db, device, dtype_store, n_rows, dim, global_row_base);
+  if (rc) return rc;
+  std::vector<int64_t> perm;
+  auto fail = [&](int code) {
+    ssw_db_destroy(db);
+    return code;
+  };
+  if ((rc = build_layout(db, dbidx_per_row, &perm))) return fail(rc);
+  const size_t es_in = dtype_in == SSW_F16 ? 2 : 4, es_st = dtype_store == SSW_F16 ? 2 : 4;
+  const size_t row_in = (size_t)dim * es_in;
+  cudaError_t e = cudaMalloc(&db->d_vecs, std::max<size_t>((size_t)n_rows * dim * es_st, 16));
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMalloc(vectors): ") + cudaGetErrorString(e));
+    return fail(e == cudaErrorMemoryAllocation ? SSW_ERR_OOM : SSW_ERR_CUDA);
+  }
+  const bool identity = perm.empty();
+  if (identity && dtype_in == dtype_store) {
+    e = cudaMemcpy(db->d_vecs, vectors, (size_t)n_rows * row_in, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      set_error(std::string("cudaMemcpy(vectors): ") + cudaGetErrorString(e));
+      return fail(SSW_ERR_CUDA);
+    }
+  } else {
+    // chunked: gather rows on the host into pinned staging, copy, convert/place on the device
+    const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)(32u << 20) / (int64_t)row_in);
+    if ((rc = ensure_stage(db, (size_t)chunk_rows * row_in, (size_t)chunk_rows * row_in))) return fail(rc);
+    const uint8_t* src = static_cast<const uint8_t*>(vectors);
+    for (int64_t r0 = 0; r0 < n_rows; r0 += chunk_rows) {
+      const int64_t nr = std::min(chunk_rows, n_rows - r0);
+      uint8_t* h = static_cast<uint8_t*>(db->h_stage);
+      if (identity) {
+        memcpy(h, src + (size_t)r0 * row_in, (size_t)nr * row_in);
+      } else {
+        for (int64_t i = 0; i < nr; ++i) memcpy(h + (size_t)i * row_in, src + (size_t)perm[r0 + i] * row_in, row_in);
+      }
+      e = cudaMemcpyAsync(db->d_stage, h, (size_t)nr * row_in, cudaMemcpyHostToDevice, db->stream);
+      if (e != cudaSuccess) {
+        set_error(std::string("cudaMemcpyAsync(stage): ") + cudaGetErrorString(e));
+        return fail(SSW_ERR_CUDA);
+      }
+      if ((rc = launch_convert_rows(db->d_stage, dtype_in, static_cast<uint8_t*>(db->d_vecs) + (size_t)r0 * dim * es_st,
+                                    dtype_store, nr * dim, db->stream)))
+        return fail(rc);
+      e = cudaStreamSynchronize(db->stream);
+      if (e != cudaSuccess) {
+        set_error(std::string("upload: ") + cudaGetErrorString(e));
+        return fail(SSW_ERR_CUDA);
+      }
+    }
+  }
+  *out = db;
+  return SSW_OK;
+}
+
+int ssw_db_create_synthetic(ssw_db** out, int device, int dtype_store, int64_t n_rows, int dim,
+                            const int32_t* dbidx_per_row, int64_t global_row_base, uint64_t seed, int kind) {
+  SSW_REQUIRE(dbidx_per_row != nullptr || n_rows == 0, "dbidx_per_row is null");
+  SSW_REQUIRE(kind == SSW_SYNTH_TRI || kind == SSW_SYNTH_LATTICE, "unknown synthetic kind");
+  ssw_db* db = nullptr;
+  int rc = db_new(&db, device, dtype_store, n_rows, dim, global_row_base);
+  if (rc) return rc;
+  auto fail = [&](int code) {
+    ssw_db_destroy(db);
+    return code;
+  };
+  for (int64_t i = 1; i < n_rows; ++i)
+    if (dbidx_per_row[i] < dbidx_per_row[i - 1]) {
+      set_error("synthetic databases need rows grouped by ascending dbidx");
+      return fail(SSW_ERR_INVALID);
+    }
+  if ((rc = build_layout(db, dbidx_per_row, nullptr))) return fail(rc);
+  const size_t es = dtype_store == SSW_F16 ? 2 : 4;
+  cudaError_t e = cudaMalloc(&db->d_vecs, std::max<size_t>((size_t)n_rows * dim * es, 16));
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMalloc(vectors): ") + cudaGetErrorString(e));
+    return fail(e == cudaErrorMemoryAllocation ? SSW_ERR_OOM : SSW_ERR_CUDA);
+  }
+  if ((rc = launch_synth(db->d_vecs, dtype_store, n_rows, dim, global_row_base, seed, kind, db->stream))) return fail(rc);
+  e = cudaStreamSynchronize(db->stream);
+  if (e != cudaSuccess) {
+    set_error(std::string("synthetic fill: ") + cudaGetErrorString(e));
+    return fail(SSW_ERR_CUDA);
+  }
+  *out = db;
+  return SSW_OK;
+}
+
+int ssw_db_info(const ssw_db* db, int64_t* n_rows, int64_t* n_images, int* dim, int* dtype_store, int* device) {
+  SSW_REQUIRE(db != nullptr, "db is null");
+  if (n_rows) *n_rows = db->n_rows;
+  if (n_images) *n_images = db->n_images;
+  if (dim) *dim = db->dim;
+  if (dtype_store) *dtype_store = db->dtype;
+  if (device) *device = db->device;
+  return SSW_OK;
+}
+
+int ssw_db_vectors_device(const ssw_db* db, void** dev_ptr) {
+  SSW_REQUIRE(db != nullptr && dev_ptr != nullptr, "null argument");
+  *dev_ptr = db->d_vecs;
+  return SSW_OK;
+}
+
+int ssw_set_scan_mode(ssw_db* db, int mode) {
+  SSW_REQUIRE(db != nullptr, "db is null");
+  SSW_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
+  db->scan_mode = mode;
+  return SSW_OK;
+}
+
+int ssw_exclude_words(const ssw_db* db, int64_t* words_per_query) {
+  SSW_REQUIRE(db != nullptr && words_per_query != nullptr, "null argument");
+  *words_per_query = db->excl_words;
+  return SSW_OK;
+}
+
+int ssw_exclude_build_device(ssw_db* db, const int32_t* d_exclude_dbidx, const int64_t* d_exclude_offsets,
+                             int nq, int64_t n_ids_total, uint32_t* d_bits_out, void* stream) {
+  SSW_REQUIRE(db != nullptr && d_bits_out != nullptr && d_exclude_offsets != nullptr, "null argument");
+  SSW_REQUIRE(nq > 0, "nq must be positive");
+  (void)n_ids_total;
+  SSW_CUDA(cudaSetDevice(db->device));
+  return launch_exclude_build(db, d_exclude_dbidx, d_exclude_offsets, nq, d_bits_out, (cudaStream_t)stream);
+}
+
+static int scan_topk_impl(ssw_db* db, const float* d_queries, int nq, int k, const uint32_t* d_exclude_bits,
+                          uint64_t* d_out_key, int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row,
+                          int32_t* d_out_count, cudaStream_t st) {
+  const int lists = db->scan_grid;
+  int rc = ensure_lists(db, nq, lists, k);
+  if (rc) return rc;
+  SSW_CUDA(cudaMemsetAsync(db->d_gthr, 0, (size_t)nq * 8, st));
+  for (int q = 0; q < nq; ++q) {
+    rc = launch_scan1(db, d_queries + (size_t)q * db->dim, k,
+                      d_exclude_bits ? d_exclude_bits + (size_t)q * db->excl_words : nullptr,
+                      db->d_list_keys + (size_t)q * lists * k, db->d_list_dbidx + (size_t)q * lists * k,
+                      db->d_gthr + q, st);
+    if (rc) return rc;
+  }
+  return launch_merge(db->d_list_keys, db->d_list_dbidx, lists, k, (int64_t)lists * k, nq, k, db->d_gthr,
+                      d_out_key, d_out_dbidx, d_out_score, d_out_row, d_out_count, st);
+}
+
+int ssw_scan_topk_device(ssw_db* db, const float* d_queries, int nq, int k, const uint32_t* d_exclude_bits,
+                         uint64_t* d_out_key, int32_t* d_out_dbidx, void* stream) {
+  SSW_REQUIRE(db != nullptr && d_queries != nullptr, "null argument");
+  SSW_REQUIRE(nq > 0, "nq must be positive");
+  SSW_REQUIRE(k > 0 && k <= SSW_MAX_TOPK, "k must be in [1, SSW_MAX_TOPK]");
+  SSW_CUDA(cudaSetDevice(db->device));
+  return scan_topk_impl(db, d_queries, nq, k, d_exclude_bits, d_out_key, d_out_dbidx, nullptr, nullptr, nullptr,
+                        (cudaStream_t)stream);
+}
+
+int ssw_merge_topk_device(int device, const uint64_t* d_keys, const int32_t* d_dbidx, int n_lists, int nq, int k,
+                          uint64_t* d_out_key, int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row,
+                          int32_t* d_out_count, void* stream) {
+  SSW_REQUIRE(d_keys != nullptr && d_dbidx != nullptr, "null argument");
+  SSW_REQUIRE(n_lists > 0 && nq > 0, "n_lists and nq must be positive");
+  SSW_REQUIRE(k > 0 && k <= SSW_MAX_TOPK, "k must be in [1, SSW_MAX_TOPK]");
+  int rc = ensure_device(device, nullptr);
+  if (rc) return rc;
+  return launch_merge(d_keys, d_dbidx, n_lists, (int64_t)nq * k, k, nq, k, nullptr, d_out_key, d_out_dbidx,
+                      d_out_score, d_out_row, d_out_count, (cudaStream_t)stream);
+}
+
+int ssw_scan_topk(ssw_db* db, const float* queries, int nq, int k, const int32_t* exclude_dbidx,
+                  const int64_t* exclude_offsets, int32_t* out_dbidx, float* out_score, int64_t* out_row,
+                  int32_t* out_count) {
+  SSW_REQUIRE(db != nullptr && queries != nullptr, "null argument");
+  SSW_REQUIRE(nq > 0, "nq must be positive");
+  SSW_REQUIRE(k > 0 && k <= SSW_MAX_TOPK, "k must be in [1, SSW_MAX_TOPK]");
+  SSW_REQUIRE((exclude_dbidx == nullptr) == (exclude_offsets == nullptr) || exclude_offsets != nullptr,
+              "exclude_offsets is required with exclude_dbidx");
+  SSW_CUDA(cudaSetDevice(db->device));
+  const int64_t n_ids = exclude_offsets ? exclude_offsets[nq] : 0;
+  SSW_REQUIRE(n_ids >= 0, "exclude_offsets must be non-decreasing");
+  const bool has_excl = exclude_offsets != nullptr && n_ids > 0;
+  // one staging block each side:  queries | offsets | ids   ->   + bitmaps | keys | dbidx | score | row | count
+  auto up16 = [](size_t x) { return (x + 15) / 16 * 16; };
+  const size_t q_bytes = up16((size_t)nq * db->dim * 4);
+  const size_t off_bytes = up16((size_t)(nq + 1) * 8);
+  const size_t ids_bytes = up16((size_t)n_ids * 4);
+  const size_t in_bytes = q_bytes + off_bytes + ids_bytes;
+  const size_t bits_bytes = has_excl ? up16((size_t)nq * db->excl_words * 4) : 0;
+  const size_t nk = (size_t)nq * k;
+  const size_t key_b = up16(nk * 8), db_b = up16(nk * 4), sc_b = up16(nk * 4), row_b = up16(nk * 8), cnt_b = up16((size_t)nq * 4);
+  const size_t out_bytes = db_b + sc_b + row_b + cnt_b;
+  const size_t dev_total = in_bytes + bits_bytes + key_b + out_bytes;
+  int rc = ensure_stage(db, dev_total, std::max(in_bytes, out_bytes));
+  if (rc) return rc;
+  uint8_t* h = static_cast<uint8_t*>(db->h_stage);
+  uint8_t* d = static_cast<uint8_t*>(db->d_stage);
+  memcpy(h, queries, (size_t)nq * db->dim * 4);
+  if (has_excl) {
+    memcpy(h + q_bytes, exclude_offsets, (size_t)(nq + 1) * 8);
+    memcpy(h + q_bytes + off_bytes, exclude_dbidx, (size_t)n_ids * 4);
+  }
+  cudaStream_t st = db->stream;
+  SSW_CUDA(cudaMemcpyAsync(d, h, has_excl ? in_bytes : q_bytes, cudaMemcpyHostToDevice, st));
+  const float* d_q = reinterpret_cast<const float*>(d);
+  uint32_t* d_bits = nullptr;
+  if (has_excl) {
+    d_bits = reinterpret_cast<uint32_t*>(d + in_bytes);
+    rc = launch_exclude_build(db, reinterpret_cast<const int32_t*>(d + q_bytes + off_bytes),
+                              reinterpret_cast<const int64_t*>(d + q_bytes), nq, d_bits, st);
+    if (rc) return rc;
+  }
+  uint64_t* d_key = reinterpret_cast<uint64_t*>(d + in_bytes + bits_bytes);
+  uint8_t* d_out = d + in_bytes + bits_bytes + key_b;
+  int32_t* d_dbidx = reinterpret_cast<int32_t*>(d_out);
+  float* d_score = reinterpret_cast<float*>(d_out + db_b);
+  int64_t* d_row = reinterpret_cast<int64_t*>(d_out + db_b + sc_b);
+  int32_t* d_cnt = reinterpret_cast<int32_t*>(d_out + db_b + sc_b + row_b);
+  rc = scan_topk_impl(db, d_q, nq, k, d_bits, d_key, d_dbidx, d_score, d_row, d_cnt, st);
+  if (rc) return rc;
+  SSW_CUDA(cudaMemcpyAsync(h, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+  SSW_CUDA(cudaStreamSynchronize(st));
+  if (out_dbidx) memcpy(out_dbidx, h, nk * 4);
+  if (out_score) memcpy(out_score, h + db_b, nk * 4);
+  if (out_row) memcpy(out_row, h + db_b + sc_b, nk * 8);
+  if (out_count) memcpy(out_count, h + db_b + sc_b + row_b, (size_t)nq * 4);
+  return SSW_OK;
+}
+
+int ssw_score_all_device(ssw_db* db, const float* d_query, float* d_out_scores, void* stream) {
+  SSW_REQUIRE(db != nullptr && d_query != nullptr && d_out_scores != nullptr, "null argument");
+  SSW_CUDA(cudaSetDevice(db->device));
+  return launch_score_all(db, d_query, d_out_scores, (cudaStream_t)stream);
+}
+
+int ssw_score_all(ssw_db* db, const float* query, float* out_scores) {
+  SSW_REQUIRE(db != nullptr && query != nullptr && out_scores != nullptr, "null argument");
+  SSW_CUDA(cudaSetDevice(db->device));
+  const size_t q_bytes = ((size_t)db->dim * 4 + 15) / 16 * 16;
+  const size_t s_bytes = (size_t)db->n_rows * 4;
+  int rc = ensure_stage(db, q_bytes + s_bytes, q_bytes);
+  if (rc) return rc;
+  memcpy(db->h_stage, query, (size_t)db->dim * 4);
+  uint8_t* d = static_cast<uint8_t*>(db->d_stage);
+  SSW_CUDA(cudaMemcpyAsync(d, db->h_stage, q_bytes, cudaMemcpyHostToDevice, db->stream));
+  rc = launch_score_all(db, reinterpret_cast<const float*>(d), reinterpret_cast<float*>(d + q_bytes), db->stream);
+  if (rc) return rc;
+  SSW_CUDA(cudaMemcpyAsync(out_scores, d + q_bytes, s_bytes, cudaMemcpyDeviceToHost, db->stream));
+  SSW_CUDA(cudaStreamSynchronize(db->stream));
+  return SSW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+// Shared device/host helpers for libseesaw_b200 (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/seesaw_b200.h"
+
+namespace ssw {
+
+// ---------------------------------------------------------------------------- errors
+void set_error(const std::string& msg);
+extern int64_t g_launch_count;
+
+#define SSW_CUDA(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      ssw::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
+      return (_e == cudaErrorMemoryAllocation) ? SSW_ERR_OOM : SSW_ERR_CUDA;                 \
+    }                                                                                        \
+  } while (0)
+
+#define SSW_REQUIRE(cond, msg)                                                               \
+  do {                                                                                       \
+    if (!(cond)) {                                                                           \
+      ssw::set_error(std::string(msg) + " (" #cond ")");                                     \
+      return SSW_ERR_INVALID;                                                                \
+    }                                                                                        \
+  } while (0)
+
+#define SSW_LAUNCHED()                                                                       \
+  do {                                                                                       \
+    ++ssw::g_launch_count;                                                                   \
+    SSW_CUDA(cudaGetLastError());                                                            \
+  } while (0)
+
+// ---------------------------------------------------------------------------- keys
+// A candidate is one 64-bit key: (order-preserving fp32 bits << 32) | ~global_row.
+// Larger key == better candidate: higher score first, lower original row on equal score.
+// Key 0 is reserved for "empty".
+__host__ __device__ __forceinline__ uint32_t f32_ordered(float f) {
+#ifdef __CUDA_ARCH__
+  uint32_t b = __float_as_uint(f + 0.0f);   // -0.0 -> +0.0 so that they tie (numpy sorts them equal)
+#else
+  float g = f + 0.0f;
+  uint32_t b;
+  memcpy(&b, &g, 4);
+#endif
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float f32_from_ordered(uint32_t u) {
+  uint32_t b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(b);
+#else
+  float f;
+  memcpy(&f, &b, 4);
+  return f;
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t make_key(float score, uint32_t global_row) {
+  return ((uint64_t)f32_ordered(score) << 32) | (uint64_t)(0xFFFFFFFFu - global_row);
+}
+__host__ __device__ __forceinline__ uint32_t key_row(uint64_t key) {
+  return 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFu);
+}
+__host__ __device__ __forceinline__ float key_score(uint64_t key) {
+  return f32_from_ordered((uint32_t)(key >> 32));
+}
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// 1-D bulk async copy global -> shared (UBLKCP), completion counted in bytes on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
+  uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
+  uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+  return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
+  uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m);
+  uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
+  return ((uint64_t)hi << 32) | lo;
+}
+#endif  // __CUDACC__
+
+}  // namespace ssw

@@ -1,0 +1,65 @@
+// Internal definition of the database handle and kernel launch entry points.
+#pragma once
+#include "ssw_common.cuh"
+
+struct ssw_db {
+  int device = 0;
+  int dim = 0;
+  int dtype = SSW_F16;          // storage type in HBM
+  int64_t n_rows = 0;
+  int64_t n_images = 0;
+  int64_t row_base = 0;         // global index of this shard's original row 0
+  int sm_count = 0;
+  int scan_mode = 0;
+
+  // HBM layout (SURVEY.md §7 "row order is not guaranteed grouped by image"):
+  void* d_vecs = nullptr;          // [n_rows, dim] stored type, rows STABLY grouped by image
+  int32_t* d_img_of_row = nullptr; // [n_rows + 1] local image index of each device row (+ sentinel -1)
+  int64_t* d_row_ptr = nullptr;    // [n_images + 1] CSR over device rows
+  int32_t* d_img_dbidx = nullptr;  // [n_images] dbidx of each local image, ascending
+  int64_t* d_orig_row = nullptr;   // [n_rows] device row -> original local row; NULL when identity
+  int32_t* d_part = nullptr;       // [scan_warps + 1] image range of every scan warp
+  int scan_grid = 0;               // CTAs of the streaming scan (one per SM)
+  int32_t* d_tile_img = nullptr;   // reserved for the tcgen05 batched scan
+
+  int64_t excl_words = 0;          // uint32 words of one exclusion bitmap (n_images bits, padded)
+
+  // per-handle workspace (grown on demand), all on `stream` unless the caller passes one
+  cudaStream_t stream = nullptr;
+  uint64_t* d_list_keys = nullptr; // [nq][lists][k] per-CTA candidate lists
+  int32_t* d_list_dbidx = nullptr;
+  uint64_t* d_gthr = nullptr;      // [nq] shared lower bound on the k-th best key
+  size_t list_capacity = 0;        // entries
+  int gthr_capacity = 0;
+  // staging for the host-pointer API
+  void* d_stage = nullptr;
+  size_t d_stage_bytes = 0;
+  void* h_stage = nullptr;         // pinned
+  size_t h_stage_bytes = 0;
+};
+
+namespace ssw {
+
+constexpr int kScanWarps = 8;             // warps per CTA of the streaming scan
+constexpr int kMergeCap = 8192;           // candidates the merge kernel sorts in shared memory
+
+int ensure_device(int device, int* sm_count);
+
+// streaming single-query scan (K1); MODE 0 = fused segmented max + exclusion + top-k lists,
+// MODE 1 = plain score vector (index.score)
+int launch_scan1(ssw_db* db, const float* d_query, int k, const uint32_t* d_excl, uint64_t* d_list_keys,
+                 int32_t* d_list_dbidx, uint64_t* d_gthr, cudaStream_t st);
+int launch_score_all(ssw_db* db, const float* d_query, float* d_out, cudaStream_t st);
+// merge kernel (K4)
+int launch_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_lists, int64_t list_stride,
+                 int64_t query_stride, int nq, int k, const uint64_t* d_thr, uint64_t* d_out_key,
+                 int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row, int32_t* d_out_count,
+                 cudaStream_t st);
+int launch_exclude_build(ssw_db* db, const int32_t* d_ids, const int64_t* d_offsets, int nq, uint32_t* d_bits,
+                         cudaStream_t st);
+int launch_synth(void* d_out, int dtype, int64_t n_rows, int dim, int64_t global_row0, uint64_t seed, int kind,
+                 cudaStream_t st);
+int launch_convert_rows(const void* d_src, int dtype_src, void* d_dst, int dtype_dst, int64_t n_elems,
+                        cudaStream_t st);
+
+}  // namespace ssw

@@ -1,0 +1,664 @@
+// K1: streaming single-query patch scan with a fused epilogue (sm_100a).
+//
+// Replaces, for one query vector, the reference's
+//     scores = vectors @ q ; argsort(-scores) ; dbidx.isin(exclude) ; np.unique first-occurrence ; head(k)
+// (seesaw/indices/multiscale/multiscale_index.py:170-199, called from _query_prelim :291-312) and
+// the mask/matvec/argsort of CoarseIndex.query (seesaw/indices/coarse/coarse_index.py:57-96).
+//
+// Data movement: the database is one contiguous [n_rows, dim] array, rows grouped by image.
+// Every warp owns a contiguous, image-aligned row range and streams it with 1-D bulk async
+// copies (cp.async.bulk -> UBLKCP, completion on an mbarrier) into a private 3-stage ring in
+// shared memory: 8 warps x 3 stages x 8 KB = 192 KB in flight per SM, far above the ~45 KB
+// Little's law needs at 6.5 TB/s.  No thread ever issues a global load for vector data.
+// Compute: conflict-free 128-bit LDS, fp32 FMA against the query held in registers, a
+// transposing butterfly so 8 row sums cost 9 shuffles, then a warp-uniform segmented max over
+// the image ids, the exclusion bitmap test and a threshold-filtered insert into the CTA's top-k
+// list.  A global lower bound on the k-th best key (max over CTAs of their k-th best) is shared
+// through one L2 word so late candidates are rejected with one compare.
+// HBM bytes per row: dim*sizeof(T) + 4 (image id)  -> the roofline in DESIGN.md.
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "ssw_db.h"
+
+namespace ssw {
+
+struct Scan1Args {
+  const void* vecs;
+  const int32_t* img_of_row;
+  const int64_t* row_ptr;
+  const int32_t* img_dbidx;
+  const int64_t* orig_row;   // may be null (identity)
+  const int32_t* part;       // [warps+1]
+  const float* q;
+  const uint32_t* excl;      // may be null
+  uint64_t* list_keys;       // [grid][k]
+  int32_t* list_dbidx;       // [grid][k]
+  uint64_t* g_thr;
+  float* scores_out;
+  int64_t row_base;
+  int k;
+};
+
+constexpr int kStages = 3;
+constexpr int kStageBytesMax = 8192;
+
+template <typename T, int C>
+struct Scan1Cfg {
+  static constexpr int EPC = 16 / sizeof(T);            // elements per 16-byte chunk
+  static constexpr int DIM = C * 32 * EPC;
+  static constexpr int ROW_BYTES = DIM * sizeof(T);
+  static constexpr int RT_RAW = kStageBytesMax / ROW_BYTES;
+  static constexpr int RT = RT_RAW >= 8 ? 8 : (RT_RAW >= 4 ? 4 : 2);   // rows per tile (power of two)
+  static constexpr int STAGE_BYTES = RT * ROW_BYTES;
+  static constexpr int LANES_PER_ROW = 32 / RT;         // lanes holding one row's total after the butterfly
+  static_assert(STAGE_BYTES <= kStageBytesMax, "stage too large");
+};
+
+__device__ __forceinline__ void cvt8(const uint4& v, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+// Sum RT per-lane partials across the warp so that lanes [r*LPR, (r+1)*LPR) all hold row r's total.
+template <int RT>
+__device__ __forceinline__ float transpose_reduce(float* acc, int lane) {
+  float v;
+  if constexpr (RT == 8) {
+    float a4[4], a2[2];
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float send = b4 ? acc[i] : acc[i + 4];
+      float keep = b4 ? acc[i + 4] : acc[i];
+      a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float send = b3 ? a4[i] : a4[i + 2];
+      float keep = b3 ? a4[i + 2] : a4[i];
+      a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    {
+      float send = b2 ? a2[0] : a2[1];
+      float keep = b2 ? a2[1] : a2[0];
+      v = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+  } else if constexpr (RT == 4) {
+    float a2[2];
+    const bool b4 = lane & 16, b3 = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float send = b4 ? acc[i] : acc[i + 2];
+      float keep = b4 ? acc[i + 2] : acc[i];
+      a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    {
+      float send = b3 ? a2[0] : a2[1];
+      float keep = b3 ? a2[1] : a2[0];
+      v = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+  } else {
+    const bool b4 = lane & 16;
+    float send = b4 ? acc[0] : acc[1];
+    float keep = b4 ? acc[1] : acc[0];
+    v = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+  }
+  return v;
+}
+
+// CTA-wide top-k list in shared memory, guarded by a spin lock; warps insert cooperatively.
+struct TopkList {
+  uint64_t* keys;
+  int32_t* dbidx;
+  volatile uint64_t* thr;    // k-th best key once the list is full, else 0
+  volatile int* cnt;
+  volatile int* minpos;
+  int* lock;
+};
+
+__device__ __forceinline__ void list_recompute_min(const TopkList& L, int k, int lane, uint64_t* g_thr) {
+  uint64_t mn = ~0ull;
+  int pos = 0;
+  for (int i = lane; i < k; i += 32) {
+    uint64_t v = L.keys[i];
+    if (v < mn) {
+      mn = v;
+      pos = i;
+    }
+  }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    uint64_t o = shfl_xor_u64(mn, m);
+    int op = __shfl_xor_sync(0xffffffffu, pos, m);
+    if (o < mn) {
+      mn = o;
+      pos = op;
+    }
+  }
+  if (lane == 0) {
+    *L.minpos = pos;
+    *L.thr = mn;
+    atomicMax(reinterpret_cast<unsigned long long*>(g_thr), (unsigned long long)mn);
+  }
+}
+
+// All 32 lanes call this with identical arguments.
+__device__ __forceinline__ void list_insert(const TopkList& L, int k, int lane, uint64_t key, int32_t dbidx,
+                                            uint64_t* g_thr) {
+  if (lane == 0) {
+    while (atomicCAS(L.lock, 0, 1) != 0) {
+    }
+  }
+  __syncwarp();
+  __threadfence_block();
+  const int cnt = *L.cnt;
+  if (cnt < k) {
+    if (lane == 0) {
+      L.keys[cnt] = key;
+      L.dbidx[cnt] = dbidx;
+      *L.cnt = cnt + 1;
+    }
+    __syncwarp();
+    if (cnt + 1 == k) list_recompute_min(L, k, lane, g_thr);
+  } else if (key > *L.thr) {
+    if (lane == 0) {
+      const int p = *L.minpos;
+      L.keys[p] = key;
+      L.dbidx[p] = dbidx;
+    }
+    __syncwarp();
+    list_recompute_min(L, k, lane, g_thr);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence_block();
+    atomicExch(L.lock, 0);
+  }
+}
+
+template <typename T, int C, int MODE>
+__global__ void __launch_bounds__(kScanWarps * 32, 1) scan1_kernel(const Scan1Args a) {
+  using Cfg = Scan1Cfg<T, C>;
+  constexpr int RT = Cfg::RT;
+  constexpr int EPC = Cfg::EPC;
+  constexpr int NQ = C * EPC;   // query values held per lane
+
+  extern __shared__ __align__(128) uint8_t smem[];
+  // [warps][stages][STAGE_BYTES] | keys[k] | dbidx[k] | mbar[warps*stages] | ctrl
+  uint8_t* ring_base = smem;
+  uint64_t* s_keys = reinterpret_cast<uint64_t*>(smem + kScanWarps * kStages * Cfg::STAGE_BYTES);
+  int32_t* s_dbidx = reinterpret_cast<int32_t*>(s_keys + a.k);
+  uint64_t* s_mbar = reinterpret_cast<uint64_t*>(
+      smem + kScanWarps * kStages * Cfg::STAGE_BYTES + ((a.k * 12 + 15) / 16) * 16);
+  uint64_t* s_thr = s_mbar + kScanWarps * kStages;
+  int* s_ctrl = reinterpret_cast<int*>(s_thr + 1);   // cnt, minpos, lock
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    *s_thr = 0;
+    s_ctrl[0] = 0;
+    s_ctrl[1] = 0;
+    s_ctrl[2] = 0;
+  }
+  const uint32_t ring = smem_u32(ring_base + warp * kStages * Cfg::STAGE_BYTES);
+  const uint32_t bar0 = smem_u32(s_mbar + warp * kStages);
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(bar0 + 8 * s, 1);
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  __syncthreads();
+
+  TopkList L{s_keys, s_dbidx, s_thr, s_ctrl, s_ctrl + 1, s_ctrl + 2};
+
+  // query slice of this lane: chunk c covers elements (c*32 + lane)*EPC ...
+  float qr[NQ];
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+#pragma unroll
+    for (int e = 0; e < EPC; ++e) qr[c * EPC + e] = __ldg(a.q + (c * 32 + lane) * EPC + e);
+
+  const int gw = blockIdx.x * kScanWarps + warp;
+  const int img0 = a.part[gw], img1 = a.part[gw + 1];
+  const int64_t r_begin = a.row_ptr[img0], r_end = a.row_ptr[img1];
+  const int64_t nrows = r_end - r_begin;
+  const int64_t ntiles = (nrows + RT - 1) / RT;
+  const uint8_t* gbase = reinterpret_cast<const uint8_t*>(a.vecs) + r_begin * (int64_t)Cfg::ROW_BYTES;
+
+  auto issue = [&](int64_t t) {
+    const int s = (int)(t % kStages);
+    const int64_t rows = (nrows - t * RT < (int64_t)RT ? nrows - t * RT : (int64_t)RT);
+    const uint32_t bytes = (uint32_t)rows * Cfg::ROW_BYTES;
+    mbar_expect_tx(bar0 + 8 * s, bytes);
+    bulk_g2s(ring + s * Cfg::STAGE_BYTES, gbase + t * (int64_t)Cfg::STAGE_BYTES, bytes, bar0 + 8 * s);
+  };
+  if (lane == 0) {
+    for (int64_t t = 0; t < (ntiles < (int64_t)kStages ? ntiles : (int64_t)kStages); ++t) issue(t);
+  }
+
+  int cur_img = -1;
+  uint64_t cur_key = 0;
+  uint64_t g_cached = 0;
+
+  auto emit = [&](int img, uint64_t key) {
+    // key carries the LOCAL device row; quick reject on the score half first
+    uint64_t thr = *L.thr;
+    thr = thr > g_cached ? thr : g_cached;
+    if ((key >> 32) < (thr >> 32)) return;
+    const uint32_t drow = key_row(key);
+    const int64_t orow = a.orig_row ? a.orig_row[drow] : (int64_t)drow;
+    key = (key & 0xFFFFFFFF00000000ull) | (uint64_t)(0xFFFFFFFFu - (uint32_t)(a.row_base + orow));
+    if (key <= thr) return;
+    if (a.excl && ((a.excl[img >> 5] >> (img & 31)) & 1u)) return;
+    list_insert(L, a.k, lane, key, a.img_dbidx[img], a.g_thr);
+  };
+
+  for (int64_t t = 0; t < ntiles; ++t) {
+    const int s = (int)(t % kStages);
+    const uint32_t parity = (uint32_t)((t / kStages) & 1);
+    const int64_t row0 = r_begin + t * RT;                 // device row of the tile's first row
+    const int rows_here = (int)(nrows - t * RT < (int64_t)RT ? nrows - t * RT : (int64_t)RT);
+    int my_img = -1;
+    if (MODE == 0) {
+      if (lane < rows_here) my_img = a.img_of_row[row0 + lane];
+      if ((t & 7) == 0) g_cached = ld_relaxed_u64(a.g_thr);
+    }
+    mbar_wait(bar0 + 8 * s, parity);
+
+    uint4 raw[RT][C];
+    const uint32_t sbase = ring + s * Cfg::STAGE_BYTES + lane * 16;
+#pragma unroll
+    for (int r = 0; r < RT; ++r)
+#pragma unroll
+      for (int c = 0; c < C; ++c) raw[r][c] = lds128(sbase + r * Cfg::ROW_BYTES + c * 512);
+    __syncwarp();
+    if (lane == 0 && t + kStages < ntiles) issue(t + kStages);
+
+    float acc[RT];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      float s0 = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        if constexpr (sizeof(T) == 2) {
+          float f[8];
+          cvt8(raw[r][c], f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) s0 = fmaf(f[e], qr[c * 8 + e], s0);
+        } else {
+          s0 = fmaf(__uint_as_float(raw[r][c].x), qr[c * 4 + 0], s0);
+          s0 = fmaf(__uint_as_float(raw[r][c].y), qr[c * 4 + 1], s0);
+          s0 = fmaf(__uint_as_float(raw[r][c].z), qr[c * 4 + 2], s0);
+          s0 = fmaf(__uint_as_float(raw[r][c].w), qr[c * 4 + 3], s0);
+        }
+      }
+      acc[r] = s0;
+    }
+    const float total = transpose_reduce<RT>(acc, lane);   // lanes [r*LPR,(r+1)*LPR) hold row r
+
+    if (MODE == 1) {
+      const int r = lane / Cfg::LANES_PER_ROW;
+      if ((lane % Cfg::LANES_PER_ROW) == 0 && r < rows_here) {
+        const int64_t drow = row0 + r;
+        const int64_t orow = a.orig_row ? a.orig_row[drow] : drow;
+        a.scores_out[orow] = total;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        if (r < rows_here) {     // warp-uniform
+          const float sc = __shfl_sync(0xffffffffu, total, r * Cfg::LANES_PER_ROW);
+          const int img = __shfl_sync(0xffffffffu, my_img, r);
+          const uint64_t key = make_key(sc, (uint32_t)(row0 + r));
+          if (img != cur_img) {
+            if (cur_img >= 0) emit(cur_img, cur_key);
+            cur_img = img;
+            cur_key = key;
+          } else {
+            cur_key = key > cur_key ? key : cur_key;
+          }
+        }
+      }
+    }
+  }
+  if (MODE == 0) {
+    if (cur_img >= 0) emit(cur_img, cur_key);
+    __syncthreads();
+    const int cnt = s_ctrl[0];
+    for (int i = threadIdx.x; i < a.k; i += blockDim.x) {
+      a.list_keys[(int64_t)blockIdx.x * a.k + i] = i < cnt ? s_keys[i] : 0ull;
+      a.list_dbidx[(int64_t)blockIdx.x * a.k + i] = i < cnt ? s_dbidx[i] : -1;
+    }
+  }
+}
+
+template <typename T, int C, int MODE>
+static int launch_scan1_t(ssw_db* db, const Scan1Args& a, cudaStream_t st) {
+  using Cfg = Scan1Cfg<T, C>;
+  const size_t smem = (size_t)kScanWarps * kStages * Cfg::STAGE_BYTES + ((a.k * 12 + 15) / 16) * 16 +
+                      kScanWarps * kStages * 8 + 8 + 16;
+  auto kern = scan1_kernel<T, C, MODE>;
+  SSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<db->scan_grid, kScanWarps * 32, smem, st>>>(a);
+  SSW_LAUNCHED();
+  return SSW_OK;
+}
+
+template <int MODE>
+static int dispatch_scan1(ssw_db* db, const Scan1Args& a, cudaStream_t st) {
+  const int d = db->dim;
+  if (db->dtype == SSW_F16) {
+    switch (d) {
+      case 256: return launch_scan1_t<__half, 1, MODE>(db, a, st);
+      case 512: return launch_scan1_t<__half, 2, MODE>(db, a, st);
+      case 768: return launch_scan1_t<__half, 3, MODE>(db, a, st);
+      case 1024: return launch_scan1_t<__half, 4, MODE>(db, a, st);
+    }
+  } else {
+    switch (d) {
+      case 256: return launch_scan1_t<float, 2, MODE>(db, a, st);
+      case 512: return launch_scan1_t<float, 4, MODE>(db, a, st);
+      case 768: return launch_scan1_t<float, 6, MODE>(db, a, st);
+      case 1024: return launch_scan1_t<float, 8, MODE>(db, a, st);
+    }
+  }
+  set_error("unsupported dim for the streaming scan (need 256, 512, 768 or 1024)");
+  return SSW_ERR_INVALID;
+}
+
+int launch_scan1(ssw_db* db, const float* d_query, int k, const uint32_t* d_excl, uint64_t* d_list_keys,
+                 int32_t* d_list_dbidx, uint64_t* d_gthr, cudaStream_t st) {
+  Scan1Args a{};
+  a.vecs = db->d_vecs;
+  a.img_of_row = db->d_img_of_row;
+  a.row_ptr = db->d_row_ptr;
+  a.img_dbidx = db->d_img_dbidx;
+  a.orig_row = db->d_orig_row;
+  a.part = db->d_part;
+  a.q = d_query;
+  a.excl = d_excl;
+  a.list_keys = d_list_keys;
+  a.list_dbidx = d_list_dbidx;
+  a.g_thr = d_gthr;
+  a.scores_out = nullptr;
+  a.row_base = db->row_base;
+  a.k = k;
+  return dispatch_scan1<0>(db, a, st);
+}
+
+int launch_score_all(ssw_db* db, const float* d_query, float* d_out, cudaStream_t st) {
+  Scan1Args a{};
+  a.vecs = db->d_vecs;
+  a.img_of_row = db->d_img_of_row;
+  a.row_ptr = db->d_row_ptr;
+  a.img_dbidx = db->d_img_dbidx;
+  a.orig_row = db->d_orig_row;
+  a.part = db->d_part;
+  a.q = d_query;
+  a.scores_out = d_out;
+  a.row_base = db->row_base;
+  a.k = 0;
+  return dispatch_scan1<1>(db, a, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: merge candidate lists -> exact top-k (one CTA per query).  Used after the per-CTA lists
+// of K1/K2 and after the NCCL all-gather of per-shard lists.
+// ------------------------------------------------------------------------------------------
+constexpr int kMergeThreads = 1024;
+
+struct MergeArgs {
+  const uint64_t* keys;
+  const int32_t* dbidx;
+  int n_lists;
+  int64_t list_stride, query_stride;
+  int k;
+  const uint64_t* thr;
+  uint64_t* out_key;
+  int32_t* out_dbidx;
+  float* out_score;
+  int64_t* out_row;
+  int32_t* out_count;
+};
+
+__global__ void __launch_bounds__(kMergeThreads, 1) merge_topk_kernel(const MergeArgs a) {
+  extern __shared__ __align__(16) uint8_t msmem[];
+  uint64_t* sk = reinterpret_cast<uint64_t*>(msmem);
+  int32_t* sd = reinterpret_cast<int32_t*>(sk + kMergeCap);
+  __shared__ int s_cnt;
+  __shared__ int s_hist[256];
+  __shared__ uint64_t s_prefix;
+  __shared__ int s_remaining;
+
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const int64_t total = (int64_t)a.n_lists * a.k;
+  const uint64_t* kq = a.keys + (int64_t)q * a.query_stride;
+  const int32_t* dq = a.dbidx + (int64_t)q * a.query_stride;
+  uint64_t thr = a.thr ? a.thr[q] : 0ull;
+  if (thr == 0) thr = 1;   // key 0 == empty slot
+
+  auto gather = [&](uint64_t lo) {
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    for (int64_t e = tid; e < total; e += kMergeThreads) {
+      const int64_t off = (e / a.k) * a.list_stride + (e % a.k);
+      const uint64_t key = kq[off];
+      if (key >= lo) {
+        const int p = atomicAdd(&s_cnt, 1);
+        if (p < kMergeCap) {
+          sk[p] = key;
+          sd[p] = dq[off];
+        }
+      }
+    }
+    __syncthreads();
+    return s_cnt;
+  };
+
+  int n = gather(thr);
+  if (n > kMergeCap) {
+    // Too many survivors for shared memory: exact k-th largest key by MSB-first radix select
+    // over the global lists (8 passes of 8 bits), then gather the >= T set (exactly k keys,
+    // keys are unique because every key embeds a distinct row).
+    if (tid == 0) {
+      s_prefix = 0;
+      s_remaining = a.k;
+    }
+    for (int d = 7; d >= 0; --d) {
+      for (int i = tid; i < 256; i += kMergeThreads) s_hist[i] = 0;
+      __syncthreads();
+      const uint64_t prefix = s_prefix;
+      for (int64_t e = tid; e < total; e += kMergeThreads) {
+        const int64_t off = (e / a.k) * a.list_stride + (e % a.k);
+        const uint64_t key = kq[off];
+        if (key < thr) continue;
+        const bool match = (d == 7) || ((key >> (8 * (d + 1))) == (prefix >> (8 * (d + 1))));
+        if (match) atomicAdd(&s_hist[(int)((key >> (8 * d)) & 255)], 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int rem = s_remaining, b = 255;
+        for (; b > 0; --b) {
+          if (s_hist[b] >= rem) break;
+          rem -= s_hist[b];
+        }
+        s_remaining = rem;
+        s_prefix = prefix | ((uint64_t)b << (8 * d));
+      }
+      __syncthreads();
+    }
+    n = gather(s_prefix);
+  }
+  n = min(n, kMergeCap);
+  int P = 1;
+  while (P < n) P <<= 1;
+  for (int i = n + tid; i < P; i += kMergeThreads) {
+    sk[i] = 0;
+    sd[i] = -1;
+  }
+  __syncthreads();
+  // bitonic sort, descending
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < (P >> 1); i += kMergeThreads) {
+        const int lo = ((i / stride) * stride * 2) + (i % stride);
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const uint64_t x = sk[lo], y = sk[hi];
+        if ((x < y) == desc) {
+          sk[lo] = y;
+          sk[hi] = x;
+          const int32_t t = sd[lo];
+          sd[lo] = sd[hi];
+          sd[hi] = t;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const int cnt = min(n, a.k);
+  for (int i = tid; i < a.k; i += kMergeThreads) {
+    const bool ok = i < cnt;
+    const uint64_t key = ok ? sk[i] : 0ull;
+    const int64_t o = (int64_t)q * a.k + i;
+    if (a.out_key) a.out_key[o] = key;
+    if (a.out_dbidx) a.out_dbidx[o] = ok ? sd[i] : -1;
+    if (a.out_score) a.out_score[o] = ok ? key_score(key) : -INFINITY;
+    if (a.out_row) a.out_row[o] = ok ? (int64_t)key_row(key) : -1;
+  }
+  if (tid == 0 && a.out_count) a.out_count[q] = cnt;
+}
+
+int launch_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_lists, int64_t list_stride,
+                 int64_t query_stride, int nq, int k, const uint64_t* d_thr, uint64_t* d_out_key,
+                 int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row, int32_t* d_out_count,
+                 cudaStream_t st) {
+  MergeArgs a{d_keys, d_dbidx, n_lists, list_stride, query_stride, k, d_thr,
+              d_out_key, d_out_dbidx, d_out_score, d_out_row, d_out_count};
+  const size_t smem = (size_t)kMergeCap * 12;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SSW_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  merge_topk_kernel<<<nq, kMergeThreads, smem, st>>>(a);
+  SSW_LAUNCHED();
+  return SSW_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// exclusion bitmaps: per query, bit i set <=> local image i is excluded
+// (replaces pr.BitMap difference / DataFrame.isin, multiscale_index.py:192-193, 295)
+// ------------------------------------------------------------------------------------------
+__global__ void exclude_build_kernel(const int32_t* ids, const int64_t* offsets, const int32_t* img_dbidx,
+                                     int64_t n_images, int64_t words, uint32_t* bits) {
+  const int q = blockIdx.y;
+  const int64_t b = offsets[q], e = offsets[q + 1];
+  for (int64_t i = b + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t id = ids[i];
+    int64_t lo = 0, hi = n_images;      // first position with img_dbidx >= id
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (img_dbidx[mid] < id) lo = mid + 1; else hi = mid;
+    }
+    if (lo < n_images && img_dbidx[lo] == id) atomicOr(bits + (int64_t)q * words + (lo >> 5), 1u << (lo & 31));
+  }
+}
+
+int launch_exclude_build(ssw_db* db, const int32_t* d_ids, const int64_t* d_offsets, int nq, uint32_t* d_bits,
+                         cudaStream_t st) {
+  SSW_CUDA(cudaMemsetAsync(d_bits, 0, (size_t)nq * db->excl_words * 4, st));
+  dim3 grid(8, nq);
+  exclude_build_kernel<<<grid, 256, 0, st>>>(d_ids, d_offsets, db->d_img_dbidx, db->n_images, db->excl_words, d_bits);
+  SSW_LAUNCHED();
+  return SSW_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// synthetic rows (bit-identical to seesaw_b200/synth.py) and dtype conversion
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+template <typename T>
+__global__ void synth_kernel(T* out, int64_t n_quads, int quads_per_row, int64_t global_row0, uint64_t seed, int kind) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_quads; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t ctr = (uint64_t)(global_row0 * quads_per_row + i) + seed * 0x9E3779B97F4A7C15ull;
+    const uint64_t h = splitmix(ctr);
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int pair = (int)((h >> (16 * j)) & 255) + (int)((h >> (16 * j + 8)) & 255);
+      v[j] = kind == SSW_SYNTH_TRI ? (float)(pair - 255) * (1.0f / 2048.0f) : (float)(pair % 9 - 4) * 0.125f;
+    }
+    if constexpr (sizeof(T) == 2) {
+      __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+      uint2 w;
+      w.x = *reinterpret_cast<uint32_t*>(&a);
+      w.y = *reinterpret_cast<uint32_t*>(&b);
+      reinterpret_cast<uint2*>(out)[i] = w;
+    } else {
+      reinterpret_cast<float4*>(out)[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
+int launch_synth(void* d_out, int dtype, int64_t n_rows, int dim, int64_t global_row0, uint64_t seed, int kind,
+                 cudaStream_t st) {
+  const int qpr = dim / 4;
+  const int64_t n_quads = n_rows * qpr;
+  const int grid = (int)std::min<int64_t>((n_quads + 255) / 256, 148 * 32);
+  if (n_quads == 0) return SSW_OK;
+  if (dtype == SSW_F16)
+    synth_kernel<__half><<<grid, 256, 0, st>>>((__half*)d_out, n_quads, qpr, global_row0, seed, kind);
+  else
+    synth_kernel<float><<<grid, 256, 0, st>>>((float*)d_out, n_quads, qpr, global_row0, seed, kind);
+  SSW_LAUNCHED();
+  return SSW_OK;
+}
+
+template <typename S, typename D>
+__global__ void convert_kernel(const S* src, D* dst, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if constexpr (sizeof(S) == 4 && sizeof(D) == 2) dst[i] = __float2half_rn(src[i]);
+    else if constexpr (sizeof(S) == 2 && sizeof(D) == 4) dst[i] = __half2float(src[i]);
+    else dst[i] = src[i];
+  }
+}
+
+int launch_convert_rows(const void* d_src, int dtype_src, void* d_dst, int dtype_dst, int64_t n, cudaStream_t st) {
+  if (n == 0) return SSW_OK;
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 32);
+  if (dtype_src == SSW_F32 && dtype_dst == SSW_F16)
+    convert_kernel<float, __half><<<grid, 256, 0, st>>>((const float*)d_src, (__half*)d_dst, n);
+  else if (dtype_src == SSW_F16 && dtype_dst == SSW_F32)
+    convert_kernel<__half, float><<<grid, 256, 0, st>>>((const __half*)d_src, (float*)d_dst, n);
+  else if (dtype_src == SSW_F32)
+    convert_kernel<float, float><<<grid, 256, 0, st>>>((const float*)d_src, (float*)d_dst, n);
+  else
+    convert_kernel<__half, __half><<<grid, 256, 0, st>>>((const __half*)d_src, (__half*)d_dst, n);
+  SSW_LAUNCHED();
+  return SSW_OK;
+}
+
+}  // namespace ssw

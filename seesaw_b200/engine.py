@@ -1,0 +1,177 @@
+"""Host-side handle over the C ABI: a patch database resident in the HBM of one B200.
+
+``PatchDatabase`` is what the reference-facing classes in ``seesaw_b200.indices`` hold instead of
+scanning ``self.vectors`` with numpy (indices/multiscale/multiscale_index.py:170-199)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib  # noqa: F401
+from ._lib import SSW_F16, SSW_F32, check, lib, ptr
+from .synth import kind_id
+
+_DT = {np.dtype(np.float32): SSW_F32, np.dtype(np.float16): SSW_F16}
+
+
+def _dtype_id(d):
+    if isinstance(d, str):
+        d = {"f32": np.float32, "fp32": np.float32, "float32": np.float32,
+             "f16": np.float16, "fp16": np.float16, "float16": np.float16}[d]
+    return _DT[np.dtype(d)]
+
+
+def _ids(e):
+    if isinstance(e, np.ndarray):
+        return e.astype(np.int32).reshape(-1)
+    return np.fromiter((int(v) for v in e), dtype=np.int32)
+
+
+def exclude_lists_to_csr(exclude, nq):
+    """None | list of nq iterables of dbidx -> (ids int32, offsets int64 [nq+1])."""
+    if exclude is None:
+        return None, None
+    assert len(exclude) == nq, "need one exclude list per query"
+    arrs = [_ids(e) if e is not None else np.zeros(0, np.int32) for e in exclude]
+    offsets = np.zeros(nq + 1, np.int64)
+    offsets[1:] = np.cumsum([len(a) for a in arrs])
+    ids = np.concatenate(arrs) if arrs else np.zeros(0, np.int32)
+    return np.ascontiguousarray(ids, np.int32), offsets
+
+
+class PatchDatabase:
+    """[n_rows, dim] patch vectors + image id per row, resident on one GPU."""
+
+    def __init__(self, handle):
+        self._h = handle
+        n_rows, n_images = C.c_int64(), C.c_int64()
+        dim, dt, dev = C.c_int(), C.c_int(), C.c_int()
+        check(lib.ssw_db_info(self._h, C.byref(n_rows), C.byref(n_images), C.byref(dim), C.byref(dt), C.byref(dev)))
+        self.n_rows, self.n_images, self.dim = n_rows.value, n_images.value, dim.value
+        self.dtype = np.float16 if dt.value == SSW_F16 else np.float32
+        self.device = dev.value
+        w = C.c_int64()
+        check(lib.ssw_exclude_words(self._h, C.byref(w)))
+        self.exclude_words = w.value
+
+    # ---- construction -------------------------------------------------------------------
+    @classmethod
+    def from_arrays(cls, vectors, dbidx_per_row, *, store="f16", device=0, global_row_base=0):
+        vectors = np.ascontiguousarray(vectors)
+        if vectors.dtype not in _DT:
+            vectors = vectors.astype(np.float32)
+        dbidx = np.ascontiguousarray(dbidx_per_row, dtype=np.int32).reshape(-1)
+        assert vectors.ndim == 2 and vectors.shape[0] == dbidx.shape[0]
+        h = C.c_void_p()
+        check(lib.ssw_db_create(C.byref(h), device, ptr(vectors), _DT[vectors.dtype], _dtype_id(store),
+                                vectors.shape[0], vectors.shape[1], ptr(dbidx), global_row_base))
+        return cls(h)
+
+    @classmethod
+    def synthetic(cls, dbidx_per_row, dim, *, seed, kind="tri", store="f16", device=0, global_row_base=0):
+        dbidx = np.ascontiguousarray(dbidx_per_row, dtype=np.int32).reshape(-1)
+        h = C.c_void_p()
+        check(lib.ssw_db_create_synthetic(C.byref(h), device, _dtype_id(store), dbidx.shape[0], dim, ptr(dbidx),
+                                          global_row_base, seed, kind_id(kind)))
+        return cls(h)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            lib.ssw_db_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_scan_mode(self, mode):
+        """0 auto, 1 streaming SIMT kernel, 2 tcgen05 batched kernel."""
+        check(lib.ssw_set_scan_mode(self._h, int(mode)))
+
+    # ---- host-buffer API (what the reference-facing classes call) --------------------------
+    def scan_topk(self, queries, k, exclude=None):
+        """queries [nq, dim] or [dim] fp32; exclude: list of nq iterables of dbidx (or None).
+        Returns dict(dbidx int32 [nq,k], score fp32, row int64, count int32 [nq])."""
+        q = np.ascontiguousarray(np.asarray(queries, dtype=np.float32).reshape(-1, self.dim))
+        nq = q.shape[0]
+        ids, offsets = exclude_lists_to_csr(exclude, nq)
+        out_dbidx = np.empty((nq, k), np.int32)
+        out_score = np.empty((nq, k), np.float32)
+        out_row = np.empty((nq, k), np.int64)
+        out_count = np.empty(nq, np.int32)
+        check(lib.ssw_scan_topk(self._h, ptr(q), nq, int(k), ptr(ids), ptr(offsets), ptr(out_dbidx),
+                                ptr(out_score), ptr(out_row), ptr(out_count)))
+        return dict(dbidx=out_dbidx, score=out_score, row=out_row, count=out_count)
+
+    def score_all(self, query):
+        q = np.ascontiguousarray(np.asarray(query, dtype=np.float32).reshape(-1))
+        assert q.shape[0] == self.dim
+        out = np.empty(self.n_rows, np.float32)
+        check(lib.ssw_score_all(self._h, ptr(q), ptr(out)))
+        return out
+
+    # ---- device-tensor API (torch tensors on this GPU; asynchronous on the given stream) ---
+    def _stream(self, stream):
+        import torch
+        s = torch.cuda.current_stream(self.device) if stream is None else stream
+        return C.c_void_p(s.cuda_stream)
+
+    def build_exclude_bits(self, exclude, nq, stream=None):
+        """Device bitmaps [nq, exclude_words] (int32 tensor holding the uint32 words)."""
+        import torch
+        ids, offsets = exclude_lists_to_csr(exclude, nq)
+        dev = torch.device("cuda", self.device)
+        d_ids = torch.from_numpy(ids if len(ids) else np.zeros(1, np.int32)).to(dev)
+        d_off = torch.from_numpy(offsets).to(dev)
+        bits = torch.empty((nq, self.exclude_words), dtype=torch.int32, device=dev)
+        check(lib.ssw_exclude_build_device(self._h, C.c_void_p(d_ids.data_ptr()), C.c_void_p(d_off.data_ptr()), nq,
+                                           int(offsets[-1]), C.c_void_p(bits.data_ptr()), self._stream(stream)))
+        return bits
+
+    def scan_topk_device(self, d_queries, k, d_exclude_bits=None, out_key=None, out_dbidx=None, stream=None):
+        """d_queries: float32 CUDA tensor [nq, dim].  Returns (keys [nq,k] int64 holding the uint64
+        keys, dbidx int32 [nq,k]); asynchronous."""
+        import torch
+        nq = d_queries.shape[0]
+        assert d_queries.is_cuda and d_queries.dtype == torch.float32 and d_queries.is_contiguous()
+        if out_key is None:
+            out_key = torch.empty((nq, k), dtype=torch.int64, device=d_queries.device)
+        if out_dbidx is None:
+            out_dbidx = torch.empty((nq, k), dtype=torch.int32, device=d_queries.device)
+        bits = None if d_exclude_bits is None else C.c_void_p(d_exclude_bits.data_ptr())
+        check(lib.ssw_scan_topk_device(self._h, C.c_void_p(d_queries.data_ptr()), nq, int(k), bits,
+                                       C.c_void_p(out_key.data_ptr()), C.c_void_p(out_dbidx.data_ptr()),
+                                       self._stream(stream)))
+        return out_key, out_dbidx
+
+    def score_all_device(self, d_query, out=None, stream=None):
+        import torch
+        if out is None:
+            out = torch.empty(self.n_rows, dtype=torch.float32, device=d_query.device)
+        check(lib.ssw_score_all_device(self._h, C.c_void_p(d_query.data_ptr()), C.c_void_p(out.data_ptr()),
+                                       self._stream(stream)))
+        return out
+
+
+def merge_topk_device(d_keys, d_dbidx, k, stream=None):
+    """d_keys/d_dbidx: CUDA tensors [n_lists, nq, k] (int64 holding uint64 keys, int32).
+    Returns dict of CUDA tensors key/dbidx/score/row/count for the merged top-k."""
+    import torch
+    n_lists, nq, kk = d_keys.shape
+    assert kk == k and d_keys.is_contiguous() and d_dbidx.is_contiguous()
+    dev = d_keys.device
+    out = dict(key=torch.empty((nq, k), dtype=torch.int64, device=dev),
+               dbidx=torch.empty((nq, k), dtype=torch.int32, device=dev),
+               score=torch.empty((nq, k), dtype=torch.float32, device=dev),
+               row=torch.empty((nq, k), dtype=torch.int64, device=dev),
+               count=torch.empty((nq,), dtype=torch.int32, device=dev))
+    s = torch.cuda.current_stream(dev) if stream is None else stream
+    check(lib.ssw_merge_topk_device(dev.index or 0, C.c_void_p(d_keys.data_ptr()), C.c_void_p(d_dbidx.data_ptr()),
+                                    n_lists, nq, k, C.c_void_p(out["key"].data_ptr()),
+                                    C.c_void_p(out["dbidx"].data_ptr()), C.c_void_p(out["score"].data_ptr()),
+                                    C.c_void_p(out["row"].data_ptr()), C.c_void_p(out["count"].data_ptr()),
+                                    C.c_void_p(s.cuda_stream)))
+    return out
