@@ -2,6 +2,7 @@
 // device entry points.  See include/seesaw_b200.h for the contract and the reference citations.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -14,6 +15,13 @@ static thread_local std::string t_error;
 int64_t g_launch_count = 0;
 
 void set_error(const std::string& msg) { t_error = msg; }
+bool debug_sync() {
+  static const bool on = [] {
+    const char* e = getenv("SSW_DEBUG_SYNC");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
 
 int ensure_device(int device, int* sm_count) {
   int n = 0;

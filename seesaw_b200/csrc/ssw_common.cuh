@@ -31,10 +31,21 @@ extern int64_t g_launch_count;
     }                                                                                        \
   } while (0)
 
+// After every kernel launch.  With SSW_DEBUG_SYNC=1 in the environment each launch is followed
+// by a device synchronize so that an asynchronous fault is attributed to the right kernel.
+bool debug_sync();
 #define SSW_LAUNCHED()                                                                       \
   do {                                                                                       \
     ++ssw::g_launch_count;                                                                   \
     SSW_CUDA(cudaGetLastError());                                                            \
+    if (ssw::debug_sync()) {                                                                 \
+      cudaError_t _e = cudaDeviceSynchronize();                                              \
+      if (_e != cudaSuccess) {                                                               \
+        ssw::set_error(std::string(__FILE__) + ":" + std::to_string(__LINE__) +              \
+                       " kernel failed: " + cudaGetErrorString(_e));                         \
+        return SSW_ERR_CUDA;                                                                 \
+      }                                                                                      \
+    }                                                                                        \
   } while (0)
 
 // ---------------------------------------------------------------------------- keys

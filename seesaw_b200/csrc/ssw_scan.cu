@@ -167,7 +167,12 @@ __device__ __forceinline__ void list_insert(const TopkList& L, int k, int lane, 
   }
   __syncwarp();
   __threadfence_block();
-  const int cnt = *L.cnt;
+  // One view of the list state for the whole warp: lane 0's, taken at the shuffle (a sync point),
+  // i.e. before lane 0 can run ahead and modify it.  Lanes reading the volatile words on their own
+  // could see cnt before/after lane 0's update and take different branches.
+  const int cnt = __shfl_sync(0xffffffffu, (int)*L.cnt, 0);
+  const uint64_t lthr = shfl_u64(*L.thr, 0);
+  const int mpos = __shfl_sync(0xffffffffu, (int)*L.minpos, 0);
   if (cnt < k) {
     if (lane == 0) {
       L.keys[cnt] = key;
@@ -176,11 +181,10 @@ __device__ __forceinline__ void list_insert(const TopkList& L, int k, int lane, 
     }
     __syncwarp();
     if (cnt + 1 == k) list_recompute_min(L, k, lane, g_thr);
-  } else if (key > *L.thr) {
+  } else if (key > lthr) {
     if (lane == 0) {
-      const int p = *L.minpos;
-      L.keys[p] = key;
-      L.dbidx[p] = dbidx;
+      L.keys[mpos] = key;
+      L.dbidx[mpos] = dbidx;
     }
     __syncwarp();
     list_recompute_min(L, k, lane, g_thr);
@@ -258,9 +262,14 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scan1_kernel(const Scan1Ar
   uint64_t g_cached = 0;
 
   auto emit = [&](int img, uint64_t key) {
+
     // key carries the LOCAL device row; quick reject on the score half first
+    // Lanes may arrive here at different times (no reconvergence guarantee after the lane-0
+    // blocks above), and *L.thr changes under other warps' inserts: take lane 0's view so the
+    // whole warp makes ONE decision before the warp-collective insert.
     uint64_t thr = *L.thr;
     thr = thr > g_cached ? thr : g_cached;
+    thr = shfl_u64(thr, 0);
     if ((key >> 32) < (thr >> 32)) return;
     const uint32_t drow = key_row(key);
     const int64_t orow = a.orig_row ? a.orig_row[drow] : (int64_t)drow;
@@ -290,6 +299,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scan1_kernel(const Scan1Ar
       for (int c = 0; c < C; ++c) raw[r][c] = lds128(sbase + r * Cfg::ROW_BYTES + c * 512);
     __syncwarp();
     if (lane == 0 && t + kStages < ntiles) issue(t + kStages);
+    __syncwarp();
 
     float acc[RT];
 #pragma unroll
