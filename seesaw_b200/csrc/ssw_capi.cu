@@ -368,12 +368,29 @@ static int scan_topk_impl(ssw_db* db, const float* d_queries, int nq, int k, con
   int rc = ensure_lists(db, nq, lists, k);
   if (rc) return rc;
   SSW_CUDA(cudaMemsetAsync(db->d_gthr, 0, (size_t)nq * 8, st));
-  for (int q = 0; q < nq; ++q) {
-    rc = launch_scan1(db, d_queries + (size_t)q * db->dim, k,
-                      d_exclude_bits ? d_exclude_bits + (size_t)q * db->excl_words : nullptr,
-                      db->d_list_keys + (size_t)q * lists * k, db->d_list_dbidx + (size_t)q * lists * k,
-                      db->d_gthr + q, st);
-    if (rc) return rc;
+  const bool tc_ok = scan_tc_supported(db, k);
+  if (db->scan_mode == 2 && !tc_ok) {
+    set_error("tcgen05 batched scan needs fp16 storage, dim 256/512/768 and k <= 64");
+    return SSW_ERR_INVALID;
+  }
+  const bool use_tc = db->scan_mode == 2 || (db->scan_mode == 0 && tc_ok && nq >= 8);
+  if (use_tc) {
+    for (int q0 = 0; q0 < nq; q0 += SSW_MAX_BATCH) {
+      const int nb = std::min(SSW_MAX_BATCH, nq - q0);
+      rc = launch_scan_tc(db, d_queries + (size_t)q0 * db->dim, nb, k,
+                          d_exclude_bits ? d_exclude_bits + (size_t)q0 * db->excl_words : nullptr,
+                          db->d_list_keys + (size_t)q0 * lists * k, db->d_list_dbidx + (size_t)q0 * lists * k,
+                          db->d_gthr + q0, st);
+      if (rc) return rc;
+    }
+  } else {
+    for (int q = 0; q < nq; ++q) {
+      rc = launch_scan1(db, d_queries + (size_t)q * db->dim, k,
+                        d_exclude_bits ? d_exclude_bits + (size_t)q * db->excl_words : nullptr,
+                        db->d_list_keys + (size_t)q * lists * k, db->d_list_dbidx + (size_t)q * lists * k,
+                        db->d_gthr + q, st);
+      if (rc) return rc;
+    }
   }
   return launch_merge(db->d_list_keys, db->d_list_dbidx, lists, k, (int64_t)lists * k, nq, k, db->d_gthr,
                       d_out_key, d_out_dbidx, d_out_score, d_out_row, d_out_count, st);

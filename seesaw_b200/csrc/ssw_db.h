@@ -50,6 +50,10 @@ int ensure_device(int device, int* sm_count);
 int launch_scan1(ssw_db* db, const float* d_query, int k, const uint32_t* d_excl, uint64_t* d_list_keys,
                  int32_t* d_list_dbidx, uint64_t* d_gthr, cudaStream_t st);
 int launch_score_all(ssw_db* db, const float* d_query, float* d_out, cudaStream_t st);
+// tcgen05 batched scan (K2): one pass for up to 64 queries; fp16 storage, dim 256/512/768, k <= 64
+bool scan_tc_supported(const ssw_db* db, int k);
+int launch_scan_tc(ssw_db* db, const float* d_queries, int nq, int k, const uint32_t* d_excl, uint64_t* d_list_keys,
+                   int32_t* d_list_dbidx, uint64_t* d_gthr, cudaStream_t st);
 // merge kernel (K4)
 int launch_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_lists, int64_t list_stride,
                  int64_t query_stride, int nq, int k, const uint64_t* d_thr, uint64_t* d_out_key,

@@ -1,12 +1,332 @@
-// placeholder until the tcgen05 kNN kernel lands
+// K3: exact all-pairs kNN-graph build on tcgen05 tiles with a fused per-row top-(k+1).
+//
+// Replaces   all_pairs = 1. - V @ V.T ; np.argsort(all_pairs, axis=-1)[:, :k+1]
+// (seesaw/knn_graph.py:170-182, compute_exact_knn).  The N x N matrix is never materialised:
+// a CTA keeps a 128-row block of V in tensor memory as the A operand, streams every row of V
+// through shared memory as B (TMA, SWIZZLE_128B), accumulates 128 x NT dot products in TMEM and
+// the four epilogue warps (one thread per output row) turn each accumulator tile into
+// d = fp32(1 - dot) and keep the k1 smallest (d, column) pairs of their row.
+// Ranking is on d, not on the dot: the rounding of 1 - dot merges near-equal dots into exact ties,
+// which break by ascending column (SURVEY.md §7 "Graph ties are created by the 1 - dot rounding").
+// Work: 2*N^2*DIM flops; HBM traffic is negligible (V is L2-resident for N <= ~60k, and streamed
+// once per 128-row block otherwise).
+#include <algorithm>
+#include <vector>
+
 #include "ssw_db.h"
+#include "ssw_tc.cuh"
+
+namespace ssw {
+
+struct KnnArgs {
+  const __half* v;      // [n, DIM] fp16
+  int64_t n;
+  int k1;
+  int64_t row_begin, row_end;   // output rows [row_begin, row_end)
+  int32_t* out_idx;     // [(row_end-row_begin), k1]
+  float* out_dist;
+};
+
+struct KnnRowState {
+  int cnt, maxpos;
+  uint64_t maxkey;
+};
+
+// Slow path of the epilogue (rare after warm-up): offer (d, col) to the row's list of the k1
+// smallest keys.  Columns arrive in ascending order, so on a tie with the current worst entry the
+// newcomer (larger column) loses through the key compare.  Returns the new distance threshold.
+__device__ __noinline__ float knn_offer(KnnRowState& st, uint64_t* mylist, int k1, float d, int64_t col, int64_t n,
+                                        float thr) {
+  if (col >= n) return thr;      // zero-filled out-of-range columns of the last tile
+  const uint64_t key = ((uint64_t)f32_ordered(d) << 32) | (uint32_t)col;
+  if (st.cnt < k1) {
+    mylist[st.cnt * 128] = key;
+    if (++st.cnt < k1) return thr;
+  } else if (key < st.maxkey) {
+    mylist[st.maxpos * 128] = key;
+  } else {
+    return thr;
+  }
+  uint64_t mk = 0;
+  int mp = 0;
+  for (int s = 0; s < k1; ++s) {
+    const uint64_t x = mylist[s * 128];
+    if (x >= mk) {
+      mk = x;
+      mp = s;
+    }
+  }
+  st.maxkey = mk;
+  st.maxpos = mp;
+  return key_score(mk);
+}
+
+template <int DIM, int NT, int NS>
+__global__ void __launch_bounds__(kTcThreads, 1) knn_kernel(const __grid_constant__ CUtensorMap tmap, const KnnArgs a) {
+  using Cfg = TcCfg<DIM, NT>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem;
+  const TcSmem S = tc_carve(smem_raw, NS, Cfg::STAGE_BYTES, &smem);
+  // per-row candidate lists after the barrier block: keys[k1][128]
+  uint64_t* lists = reinterpret_cast<uint64_t*>(smem + NS * Cfg::STAGE_BYTES + ((tc_bar_bytes(NS) + 15) / 16) * 16);
+  const uint32_t tmem = tc_setup(S, NS, Cfg::TMEM_ALLOC, &tmap);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int64_t nblocks = (a.row_end - a.row_begin + 127) / 128;
+  const int ntiles = (int)((a.n + NT - 1) / NT);
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      TcPipe p(NS);
+      for (int64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+        for (int t = 0; t < ntiles; ++t) {
+          for (int kc = 0; kc < Cfg::KC; ++kc) {
+            mbar_wait(S.empty + 8 * p.stage, p.phase ^ 1);
+            mbar_expect_tx(S.full + 8 * p.stage, Cfg::STAGE_BYTES);
+            tma_load_2d(S.stages + p.stage * Cfg::STAGE_BYTES, &tmap, kc * kTcKChunk, t * NT, S.full + 8 * p.stage);
+            p.advance();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    TcPipe p(NS);
+    uint32_t it = 0, blk_phase = 0;
+    for (int64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+      mbar_wait(S.a_ready, blk_phase);
+      blk_phase ^= 1;
+      tc_fence_after();
+      for (int t = 0; t < ntiles; ++t, ++it) {
+        const uint32_t as = it & 1;
+        mbar_wait(S.tmem_empty + 8 * as, ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kc = 0; kc < Cfg::KC; ++kc) {
+          mbar_wait(S.full + 8 * p.stage, p.phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint64_t bdesc = make_bdesc_sw128(S.stages + p.stage * Cfg::STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma_f16_ts(tmem + Cfg::ACC_BASE + as * NT, tmem + Cfg::A_BASE + kc * 32 + k * 8, bdesc + 2 * k,
+                         Cfg::IDESC, (kc | k) != 0);
+            tc_commit(S.empty + 8 * p.stage);
+          }
+          __syncwarp();
+          p.advance();
+        }
+        if (lane == 0) tc_commit(S.tmem_full + 8 * as);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== epilogue: one thread per output row =====
+    const int q4 = warp & 3;
+    const int lrow = q4 * 32 + lane;                     // TMEM lane == row within the block
+    const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
+    uint64_t* mylist = lists + lrow;                      // slot s at mylist[s * 128]
+    const int k1 = a.k1;
+    uint32_t it = 0;
+    for (int64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+      const int64_t row = a.row_begin + b * 128 + lrow;
+      const bool row_ok = row < a.row_end;
+      // ---- A operand: this thread's row of V into its TMEM lane (fp16 pairs are already packed)
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(a.v + (row_ok ? row : 0) * (int64_t)DIM);
+#pragma unroll 1
+        for (int c = 0; c < Cfg::A_COLS / 32; ++c) {
+          uint32_t r[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 w = row_ok ? __ldg(src + c * 8 + j) : make_uint4(0, 0, 0, 0);
+            r[4 * j] = w.x;
+            r[4 * j + 1] = w.y;
+            r[4 * j + 2] = w.z;
+            r[4 * j + 3] = w.w;
+          }
+          tmem_st32(lane_addr + Cfg::A_BASE + c * 32, r);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(S.a_ready);
+      }
+      KnnRowState stt{0, 0, ~0ull};
+      float thr = INFINITY;
+      for (int t = 0; t < ntiles; ++t, ++it) {
+        const uint32_t as = it & 1;
+        mbar_wait(S.tmem_full + 8 * as, (it >> 1) & 1);
+        tc_fence_after();
+        const int64_t col0 = (int64_t)t * NT;
+#pragma unroll 1
+        for (int c0 = 0; c0 < NT; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(lane_addr + Cfg::ACC_BASE + as * NT + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float d = __fsub_rn(1.0f, __uint_as_float(v[i]));
+            if (d <= thr) thr = knn_offer(stt, mylist, k1, d, col0 + c0 + i, a.n, thr);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(S.tmem_empty + 8 * as);
+      }
+      const int cnt = stt.cnt;
+      // ---- sort the row's k1 candidates ascending by (d, col) and write them out
+      if (row_ok) {
+        for (int i = 1; i < cnt; ++i) {
+          const uint64_t x = mylist[i * 128];
+          int j = i - 1;
+          while (j >= 0 && mylist[j * 128] > x) {
+            mylist[(j + 1) * 128] = mylist[j * 128];
+            --j;
+          }
+          mylist[(j + 1) * 128] = x;
+        }
+        const int64_t o = (row - a.row_begin) * k1;
+        for (int i = 0; i < k1; ++i) {
+          const uint64_t x = i < cnt ? mylist[i * 128] : 0;
+          a.out_idx[o + i] = i < cnt ? (int32_t)(x & 0xFFFFFFFFu) : -1;
+          a.out_dist[o + i] = i < cnt ? f32_from_ordered((uint32_t)(x >> 32)) : INFINITY;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, Cfg::TMEM_ALLOC);
+}
+
+int make_tmap_f16_rows(CUtensorMap* out, const void* base, int64_t n_rows, int dim, int box_rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    SSW_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled is not available from the driver");
+      return SSW_ERR_CUDA;
+    }
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)std::max<int64_t>(n_rows, 1)};
+  const cuuint64_t gstride[1] = {(cuuint64_t)dim * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kTcKChunk, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return SSW_ERR_CUDA;
+  }
+  return SSW_OK;
+}
+
+template <int DIM, int NT>
+static int launch_knn_t(int sm_count, const KnnArgs& a, cudaStream_t st) {
+  using Cfg = TcCfg<DIM, NT>;
+  const size_t list_bytes = (size_t)a.k1 * 128 * 8;
+  CUtensorMap tmap;
+  int rc = make_tmap_f16_rows(&tmap, a.v, a.n, DIM, NT);
+  if (rc) return rc;
+  const int64_t nblocks = (a.row_end - a.row_begin + 127) / 128;
+  const int grid = (int)std::min<int64_t>(sm_count, nblocks);
+  auto go = [&](auto kern, int NSv) -> int {
+    const size_t smem = (size_t)NSv * Cfg::STAGE_BYTES + ((tc_bar_bytes(NSv) + 15) / 16) * 16 + list_bytes + tc_smem_slack;
+    SSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kTcThreads, smem, st>>>(tmap, a);
+    SSW_LAUNCHED();
+    return SSW_OK;
+  };
+  // stage count by the shared memory left after the candidate lists (k1 <= 64 -> <= 64 KB)
+  if (list_bytes <= 24 * 1024) return go(knn_kernel<DIM, NT, 12>, 12);
+  return go(knn_kernel<DIM, NT, 8>, 8);
+}
+
+static int launch_knn(int sm_count, const KnnArgs& a, int dim, cudaStream_t st) {
+  switch (dim) {
+    case 256: return launch_knn_t<256, 128>(sm_count, a, st);
+    case 512: return launch_knn_t<512, 128>(sm_count, a, st);
+    case 768: return launch_knn_t<768, 64>(sm_count, a, st);
+  }
+  set_error("kNN build supports dim 256, 512 or 768");
+  return SSW_ERR_INVALID;
+}
+
+}  // namespace ssw
+
+using namespace ssw;
+
 extern "C" {
-int ssw_knn_build(int, const void*, int, int64_t, int, int, int64_t, int64_t, int32_t*, float*) {
-  ssw::set_error("ssw_knn_build: not built yet");
-  return SSW_ERR_INVALID;
+
+int ssw_knn_build_device(int device, const void* d_vectors_f16, int64_t n, int dim, int k1, int64_t row_begin,
+                         int64_t row_end, int32_t* d_out_idx, float* d_out_dist, void* stream) {
+  SSW_REQUIRE(d_vectors_f16 != nullptr && d_out_idx != nullptr && d_out_dist != nullptr, "null argument");
+  SSW_REQUIRE(n > 0 && n < (int64_t)0x7FFFFFFF, "n out of range");
+  SSW_REQUIRE(k1 >= 1 && k1 <= SSW_MAX_KNN_K1 && k1 <= n, "k1 must be in [1, min(n, SSW_MAX_KNN_K1)]");
+  SSW_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= n, "bad row range");
+  int sms = 0;
+  int rc = ensure_device(device, &sms);
+  if (rc) return rc;
+  if (row_begin == row_end) return SSW_OK;
+  KnnArgs a{static_cast<const __half*>(d_vectors_f16), n, k1, row_begin, row_end, d_out_idx, d_out_dist};
+  return launch_knn(sms, a, dim, (cudaStream_t)stream);
 }
-int ssw_knn_build_device(int, const void*, int64_t, int, int, int64_t, int64_t, int32_t*, float*, void*) {
-  ssw::set_error("ssw_knn_build_device: not built yet");
-  return SSW_ERR_INVALID;
+
+int ssw_knn_build(int device, const void* vectors, int dtype_in, int64_t n, int dim, int k1, int64_t row_begin,
+                  int64_t row_end, int32_t* out_idx, float* out_dist) {
+  SSW_REQUIRE(vectors != nullptr && out_idx != nullptr && out_dist != nullptr, "null argument");
+  SSW_REQUIRE(dtype_in == SSW_F16 || dtype_in == SSW_F32, "dtype_in must be SSW_F32 or SSW_F16");
+  SSW_REQUIRE(n > 0 && n < (int64_t)0x7FFFFFFF, "n out of range");
+  SSW_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= n, "bad row range");
+  int rc = ensure_device(device, nullptr);
+  if (rc) return rc;
+  const size_t es = dtype_in == SSW_F16 ? 2 : 4;
+  void *d_in = nullptr, *d_v = nullptr;
+  int32_t* d_idx = nullptr;
+  float* d_dist = nullptr;
+  const size_t nout = (size_t)(row_end - row_begin) * k1;
+  cudaStream_t st = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_in);
+    if (d_v != d_in) cudaFree(d_v);
+    cudaFree(d_idx);
+    cudaFree(d_dist);
+  };
+  auto chk = [&](cudaError_t e, const char* what) -> int {
+    if (e == cudaSuccess) return SSW_OK;
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    cleanup();
+    return e == cudaErrorMemoryAllocation ? SSW_ERR_OOM : SSW_ERR_CUDA;
+  };
+  if ((rc = chk(cudaMalloc(&d_in, (size_t)n * dim * es), "cudaMalloc(vectors)"))) return rc;
+  if ((rc = chk(cudaMemcpy(d_in, vectors, (size_t)n * dim * es, cudaMemcpyHostToDevice), "cudaMemcpy(vectors)"))) return rc;
+  if (dtype_in == SSW_F32) {
+    if ((rc = chk(cudaMalloc(&d_v, (size_t)n * dim * 2), "cudaMalloc(fp16 vectors)"))) return rc;
+    if ((rc = launch_convert_rows(d_in, SSW_F32, d_v, SSW_F16, n * dim, st))) {
+      cleanup();
+      return rc;
+    }
+  } else {
+    d_v = d_in;
+  }
+  if ((rc = chk(cudaMalloc((void**)&d_idx, std::max<size_t>(nout, 1) * 4), "cudaMalloc(out_idx)"))) return rc;
+  if ((rc = chk(cudaMalloc((void**)&d_dist, std::max<size_t>(nout, 1) * 4), "cudaMalloc(out_dist)"))) return rc;
+  rc = ssw_knn_build_device(device, d_v, n, dim, k1, row_begin, row_end, d_idx, d_dist, st);
+  if (rc) {
+    cleanup();
+    return rc;
+  }
+  if ((rc = chk(cudaDeviceSynchronize(), "knn kernel"))) return rc;
+  if ((rc = chk(cudaMemcpy(out_idx, d_idx, nout * 4, cudaMemcpyDeviceToHost), "cudaMemcpy(out_idx)"))) return rc;
+  if ((rc = chk(cudaMemcpy(out_dist, d_dist, nout * 4, cudaMemcpyDeviceToHost), "cudaMemcpy(out_dist)"))) return rc;
+  cleanup();
+  return SSW_OK;
 }
-}
+
+}  // extern "C"

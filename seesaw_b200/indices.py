@@ -1,0 +1,271 @@
+"""Reference-facing index classes: same constructor registry, attributes, method names, keyword
+arguments and result shapes as the reference's plug points, with the scan running on the B200.
+
+  B200MultiscaleIndex  <->  seesaw/indices/multiscale/multiscale_index.py:201-376 (MultiscaleIndex)
+  B200CoarseIndex      <->  seesaw/indices/coarse/coarse_index.py:16-108        (CoarseIndex)
+  B200VectorIndex      <->  seesaw/vector_index.py:44-60                         (VectorIndex, the ANN slot)
+  InteractiveQuery     <->  seesaw/query_interface.py:7-52
+
+To switch an on-disk index over, set ``"constructor": "seesaw_b200.indices.B200MultiscaleIndex"`` in
+its ``info.json`` (seesaw/indices/interface.py:36-45); see INTEGRATION.md.  None of these classes
+scans on the CPU: without the CUDA library / a B200 they raise.
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import pandas as pd
+
+from .bitmap import BitMap, FrozenBitMap, as_id_array
+from .engine import PatchDatabase
+from .rescore import rescore_candidates
+
+try:  # inside the reference's environment: be a real subclass of its plug-in base classes
+    from seesaw.indices.interface import AccessMethod as _AccessMethodBase  # type: ignore
+except Exception:  # pragma: no cover - standalone use
+    class _AccessMethodBase:  # mirrors seesaw/indices/interface.py:10-45
+        path: str = None
+
+        def get_knng_path(self, name: str = None):
+            return f"{self.path}/knn_graph/{'' if name is None else name}"
+
+        @staticmethod
+        def load(index_path: str, *, options: dict = None, exclude=None):
+            meta = json.load(open(f"{index_path}/info.json", "r"))
+            pieces = meta["constructor"].split(".")
+            import importlib
+            cons = getattr(importlib.import_module(".".join(pieces[:-1])), pieces[-1])
+            return cons.from_path(index_path, **(options or {}), exclude=exclude)
+
+
+AccessMethod = _AccessMethodBase
+
+
+class InteractiveQuery:
+    """Tracks what has been returned and passes it as ``exclude`` (query_interface.py:34-49)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.returned = BitMap()
+        self.label_db = None
+
+    def query_stateful(self, *args, **kwargs):
+        batch_size = kwargs.pop("batch_size")
+        res = self.index.query(*args, topk=batch_size, **kwargs, exclude=self.returned)
+        self.returned.update(np.asarray(res["dbidxs"]).astype(np.int64).tolist())
+        return res
+
+
+def _read_vectors_parquet(path, columns=None):
+    """``vectors.sorted.cached`` / ``vectors`` parquet dataset -> DataFrame (the reference goes
+    through Ray: services.py:25-30, util.py:110-128)."""
+    import pyarrow.parquet as pq
+    return pq.read_table(path, columns=columns).to_pandas()
+
+
+def _column_to_matrix(col) -> np.ndarray:
+    if hasattr(col, "to_numpy") and getattr(col.dtype, "name", "") != "object":
+        arr = col.to_numpy()
+        if arr.ndim == 2:
+            return np.ascontiguousarray(arr, dtype=np.float32)
+    return np.ascontiguousarray(np.stack([np.asarray(v, dtype=np.float32) for v in col]))
+
+
+class _GpuIndexMixin:
+    """Device copy + host CSR shared by the multiscale and coarse classes."""
+
+    def _init_device(self, device, store):
+        dbidx = self.vector_meta["dbidx"].to_numpy()
+        self._dbidx_of_row = dbidx.astype(np.int64)
+        self.device = device
+        self.store = store
+        self.db = PatchDatabase.from_arrays(self.vectors, dbidx.astype(np.int32), store=store, device=device)
+        # host CSR over ORIGINAL rows: rows of image i are _rows_sorted[_starts[i]:_starts[i+1]], ascending
+        order = np.argsort(self._dbidx_of_row, kind="stable")
+        sorted_ids = self._dbidx_of_row[order]
+        self._img_ids, self._starts = np.unique(sorted_ids, return_index=True)
+        self._starts = np.append(self._starts, len(order))
+        self._rows_sorted = order
+
+    def _rows_of(self, dbidx):
+        i = np.searchsorted(self._img_ids, dbidx)
+        return self._rows_sorted[self._starts[i]:self._starts[i + 1]]
+
+    def score(self, vec):
+        """Full score vector in original row order (multiscale_index.py:284-285, coarse_index.py:37-38)."""
+        return self.db.score_all(np.asarray(vec, dtype=np.float32).reshape(-1))
+
+    def string2vec(self, string: str) -> np.ndarray:
+        init_vec = self.embedding.from_string(string=string)
+        return init_vec / np.linalg.norm(init_vec)
+
+    def close(self):
+        self.db.close()
+
+
+class B200MultiscaleIndex(_GpuIndexMixin, AccessMethod):
+    """Two-stage lookup (scan -> per-image max -> exclusion -> shortlist -> rescore) with stage 1 on
+    the GPU.  Constructor and attributes follow MultiscaleIndex (multiscale_index.py:203-231)."""
+
+    def __init__(self, *, embedding, vectors: np.ndarray, vector_meta: pd.DataFrame, vec_index=None,
+                 min_zoom_level=1, path: str = None, excluded=None, device: int = 0, store: str = "f16"):
+        self.embedding = embedding
+        self.path = path
+        self.excluded = BitMap([]) if excluded is None else BitMap(as_id_array(excluded))
+        if min_zoom_level != 1:   # multiscale_index.py:224-231
+            keep = (vector_meta["zoom_level"] >= min_zoom_level).to_numpy()
+            vector_meta = vector_meta[keep].reset_index(drop=True)
+            vectors = vectors[keep]
+        self.vectors = np.ascontiguousarray(vectors)
+        self.vector_meta = vector_meta
+        self.vec_index = vec_index          # accepted for interface parity; the exact GPU scan supersedes it
+        self.all_indices = FrozenBitMap(self.vector_meta["dbidx"].to_numpy()) - self.excluded
+        self._init_device(device, store)
+        self._meta_cols = {c: self.vector_meta[c].to_numpy() for c in ("x1", "y1", "x2", "y2", "zoom_level")
+                           if c in self.vector_meta.columns}
+
+    @staticmethod
+    def from_path(index_path: str, *, use_vec_index=False, device=0, store="f16", exclude=None, **options):
+        """multiscale_index.py:234-269; reads ``info.json`` and ``vectors.sorted.cached`` directly
+        (no Ray).  The embedding model is resolved lazily by the caller through ``embedding=``."""
+        info = json.load(open(f"{index_path}/info.json"))
+        df = _read_vectors_parquet(f"{index_path}/vectors.sorted.cached").reset_index(drop=True)
+        meta = df[["dbidx", "zoom_level", "x1", "y1", "x2", "y2"]]
+        vectors = _column_to_matrix(df["vectors"])
+        return B200MultiscaleIndex(embedding=options.get("embedding"), vectors=vectors, vector_meta=meta,
+                                   path=index_path, excluded=info.get("excluded", None), device=device, store=store)
+
+    def __len__(self):
+        return len(self.all_indices)
+
+    # ---- stage 1 ---------------------------------------------------------------------------
+    def _query_prelim(self, *, vector, topk_dbidx, exclude_dbidx=None, force_exact=False):
+        """multiscale_index.py:291-312.  Returns DataFrame(dbidx, max_score) like the reference
+        (plus best_row); an EMPTY frame when nothing is eligible (the reference returns the tuple
+        ``[], [], []`` there, which its own caller cannot use)."""
+        ex = as_id_array(exclude_dbidx)
+        included = np.setdiff1d(as_id_array(self.all_indices), ex)
+        k = min(int(topk_dbidx), included.shape[0])
+        if k == 0:
+            return pd.DataFrame({"dbidx": np.zeros(0, np.int64), "max_score": np.zeros(0, np.float32),
+                                 "best_row": np.zeros(0, np.int64)})
+        r = self.db.scan_topk(np.asarray(vector, dtype=np.float32).reshape(1, -1), k, exclude=[ex])
+        n = int(r["count"][0])
+        return pd.DataFrame({"dbidx": r["dbidx"][0, :n].astype(np.int64), "max_score": r["score"][0, :n],
+                             "best_row": r["row"][0, :n]})
+
+    # ---- stage 1 + 2 -----------------------------------------------------------------------
+    def query(self, *, vector, vector2=None, topk, shortlist_size, exclude=None, force_exact=False, **kwargs):
+        """multiscale_index.py:314-352."""
+        if shortlist_size is None:
+            shortlist_size = topk * 5
+        qvec = np.asarray(vector, dtype=np.float32).reshape(-1)
+        cand = self._query_prelim(vector=qvec, topk_dbidx=shortlist_size, exclude_dbidx=exclude,
+                                  force_exact=force_exact)
+        if len(cand) == 0:
+            return {"dbidxs": np.zeros(0, dtype="int"), "activations": []}
+        ids = np.sort(cand["dbidx"].to_numpy())
+        groups = [self._rows_of(d) for d in ids]                      # CSR ranges, not an O(N) isin
+        rows = np.concatenate(groups)
+        sub = self.vectors[rows]
+        scores = sub @ qvec                                            # :345
+        if vector2 is not None:
+            scores = scores - sub @ np.asarray(vector2, dtype=np.float32).reshape(-1)   # :347-349
+        cuts = np.cumsum([len(g) for g in groups])[:-1]
+        return rescore_candidates(groups, ids, np.split(scores, cuts), self._meta_cols, topk,
+                                  agg_method=kwargs.get("agg_method", "plain_score"),
+                                  aug_larger=kwargs.get("aug_larger", "all"))
+
+    def new_query(self):
+        return InteractiveQuery(self)
+
+    def get_data(self, dbidx) -> pd.DataFrame:
+        rows = self._rows_of(dbidx)
+        return self.vector_meta.iloc[rows].assign(vectors=list(self.vectors[rows]))
+
+    def subset(self, indices):
+        """multiscale_index.py:364-376 — a new index over the rows of the given images."""
+        mask = np.isin(self._dbidx_of_row, as_id_array(indices))
+        if mask.all():
+            return self
+        return B200MultiscaleIndex(embedding=self.embedding, vectors=self.vectors[mask],
+                                   vector_meta=self.vector_meta[mask].reset_index(drop=True),
+                                   device=self.device, store=self.store)
+
+
+class B200CoarseIndex(_GpuIndexMixin, AccessMethod):
+    """One vector per image (coarse_index.py:16-108)."""
+
+    def __init__(self, embedding, vectors: np.ndarray, vector_meta: pd.DataFrame, path: str = None,
+                 device: int = 0, store: str = "f16"):
+        self.path = path
+        self.embedding = embedding
+        self.vectors = np.ascontiguousarray(vectors)
+        self.vector_meta = vector_meta
+        self.all_indices = FrozenBitMap(self.vector_meta["dbidx"].to_numpy())
+        self._init_device(device, store)
+
+    @staticmethod
+    def from_path(index_path: str, *, use_vec_index=False, device=0, store="f16", exclude=None, **options):
+        df = _read_vectors_parquet(f"{index_path}/vectors")
+        assert df.dbidx.is_monotonic_increasing, "sanity check"        # coarse_index.py:49
+        return B200CoarseIndex(embedding=options.get("embedding"), vectors=_column_to_matrix(df["vectors"]),
+                               vector_meta=df.drop("vectors", axis=1), path=index_path, device=device, store=store)
+
+    def __len__(self):
+        return len(self.all_indices)
+
+    def query(self, *, topk, vector=None, exclude=None, startk=None, **kwargs):
+        """coarse_index.py:57-96.  ``vector=None`` ranks by N(0,1) noise like the reference (:70-71);
+        that branch needs no scan and is drawn on the host."""
+        ex = as_id_array(exclude)
+        included = np.setdiff1d(as_id_array(self.all_indices), ex)
+        if included.shape[0] == 0:
+            return np.array([]), np.array([])                          # :61-62
+        topk = min(int(topk), included.shape[0])
+        if vector is None:
+            scores = np.random.randn(included.shape[0])
+            best = np.argsort(-scores, kind="stable")[:topk]
+            ret, sc = included[best], scores[best]
+        else:
+            r = self.db.scan_topk(np.asarray(vector, dtype=np.float32).reshape(1, -1), topk, exclude=[ex])
+            n = int(r["count"][0])
+            ret, sc = r["dbidx"][0, :n].astype(np.int64), r["score"][0, :n]
+        assert ret.shape[0] == topk and len(set(ret.tolist())) == topk                 # :81-85
+        assert np.intersect1d(ret, ex).shape[0] == 0
+        acts = [pd.DataFrame.from_records([dict(x1=0, y1=0, x2=224, y2=224, dbidx=d, score=s)])
+                for s, d in zip(sc, ret)]
+        return {"dbidxs": ret, "nextstartk": len(ex) + ret.shape[0], "activations": acts}
+
+    def new_query(self):
+        return InteractiveQuery(self)
+
+    def subset(self, indices):
+        mask = np.isin(self._dbidx_of_row, as_id_array(indices))
+        return B200CoarseIndex(embedding=self.embedding, vectors=self.vectors[mask],
+                               vector_meta=self.vector_meta[mask].reset_index(drop=True),
+                               device=self.device, store=self.store)
+
+
+class B200VectorIndex:
+    """Exact replacement for the annoy wrapper in the ``vec_index`` slot (vector_index.py:44-60):
+    ``query(vector, top_k) -> (row indices, scores)`` best-first, recall 1.0, any supported dim."""
+
+    def __init__(self, *, vectors=None, load_path=None, prefault=False, device=0, store="f16"):
+        if vectors is None:
+            vectors = np.load(load_path)
+        self.dim = vectors.shape[1]
+        self.db = PatchDatabase.from_arrays(vectors, np.arange(vectors.shape[0], dtype=np.int32),
+                                            store=store, device=device)
+
+    def ready(self):
+        return True
+
+    def query(self, vector, top_k):
+        vector = np.asarray(vector, dtype=np.float32)
+        assert vector.shape == (1, self.dim) or vector.shape == (self.dim,)      # vector_index.py:56
+        r = self.db.scan_topk(vector.reshape(1, -1), int(top_k))
+        n = int(r["count"][0])
+        return r["row"][0, :n].copy(), r["score"][0, :n].copy()

@@ -1,0 +1,84 @@
+"""GPU parity tests of the tcgen05 kNN-graph build (K3) against the reference outputs and the oracle."""
+import numpy as np
+import pandas as pd
+import pytest
+
+import cases
+import seesaw_oracle as orc
+from seesaw_b200 import synth
+from test_oracle import assert_graph_equal_mod_ties
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def kg():
+    from seesaw_b200 import knn_graph
+    return knn_graph
+
+
+def _ref_df(golden, name):
+    return pd.DataFrame({c: golden[f"{name}/{c}"] for c in ("src_vertex", "dst_vertex", "distance", "dst_rank")})
+
+
+def check_candidates(idx, dist, v, k, rel=1e-5):
+    """ids equal to the oracle's, or differing only between entries whose fp64 distances are within
+    rel (tensor-core vs BLAS summation order); distances within 2e-6 absolute."""
+    oi, od = orc.exact_knn_candidates_blockwise(v, k, block=512)
+    np.testing.assert_allclose(dist, od, rtol=0, atol=2e-6)
+    bad = np.argwhere(idx != oi)
+    if len(bad):
+        v64 = v.astype(np.float64)
+        for r, c in bad:
+            da = 1.0 - v64[r] @ v64[idx[r, c]]
+            db = 1.0 - v64[r] @ v64[oi[r, c]]
+            assert abs(da - db) <= rel * max(abs(da), abs(db), 1e-3), (r, c, da, db)
+    return len(bad)
+
+
+@pytest.mark.parametrize("name", ["knn_600", "knn_small_n"])
+def test_knn_vs_reference_golden(kg, golden, name):
+    c = cases.KNN[name]
+    v = cases.knn_inputs(c)
+    df = kg.compute_exact_knn(v, c["k"])
+    ref = _ref_df(golden, name)
+    assert list(df.columns) == list(ref.columns) and [str(t) for t in df.dtypes] == [str(t) for t in ref.dtypes]
+    assert len(df) == len(ref)
+    np.testing.assert_allclose(df.distance.values, ref.distance.values, rtol=0, atol=2e-6)
+    if not (df.dst_vertex.values == ref.dst_vertex.values).all():
+        idx, dist = kg.knn_candidates(v, c["k"])
+        check_candidates(idx, dist, v, c["k"])
+
+
+def test_knn_duplicates_mod_ties(kg, golden):
+    c = cases.KNN["knn_dups"]
+    v = cases.knn_inputs(c)
+    idx, dist = kg.knn_candidates(v, c["k"])
+    check_candidates(idx, dist, v, c["k"])
+    # duplicates: self is not always the first column, and exact ties break by ascending column
+    assert (idx[:, 0] != np.arange(len(v))).any()
+
+
+@pytest.mark.parametrize("n,dim", [(3000, 512), (1000, 256), (1500, 768), (129, 512), (128, 512)])
+def test_knn_lattice_bit_exact(kg, n, dim):
+    """Exact arithmetic, massive exact ties: ids and distances must be bit-identical to the oracle."""
+    v = synth.synth_rows(0, n, dim, 21, "lattice", np.float32) * np.float32(0.25)
+    idx, dist = kg.knn_candidates(v, 10)
+    oi, od = orc.exact_knn_candidates_blockwise(v, 10, block=512)
+    assert (dist == od).all()
+    assert (idx == oi).all()
+    df = kg.edges_from_candidates(idx, dist, n)
+    pd.testing.assert_frame_equal(df, orc.post_process_graph(oi, od, n))
+
+
+def test_knn_gaussian_and_row_ranges(kg):
+    n = 5000
+    v = synth.synth_rows(0, n, 512, 33, "tri", np.float32)
+    v = (v / np.linalg.norm(v, axis=1, keepdims=True)).astype(np.float16).astype(np.float32)
+    idx, dist = kg.knn_candidates(v, 10)
+    check_candidates(idx, dist, v, 10)
+    # a row range (the multi-GPU sharding unit) reproduces the same rows; fp16 input == fp32 input
+    i2, d2 = kg.knn_candidates(v.astype(np.float16), 10, rows=(1000, 1777))
+    assert (i2 == idx[1000:1777]).all() and (d2 == dist[1000:1777]).all()
+    g, _ = kg.KNNGraph.from_vectors(v[:700], n_neighbors=5)
+    assert g.nvecs == 700 and g.k >= 5

@@ -159,3 +159,79 @@ def test_config1_coarse_golden(eng, golden):
     assert (r["dbidx"][0] == golden["coarse/dbidxs"]).all()
     np.testing.assert_allclose(r["score"][0], golden["coarse/scores"], rtol=1e-5, atol=1e-6)
     db.close()
+
+
+# ------------------------------------------------------------------ K2: tcgen05 batched scan
+def test_batched_tc_lattice_bit_exact(eng):
+    """64-query batch on the tensor-core kernel: exact arithmetic + ties, per-query exclude sets."""
+    counts = synth.patches_per_image(4000, 1, 40, 6)
+    dbidx = synth.dbidx_of_rows(counts, 7, 3)
+    n = int(counts.sum())
+    vecs = synth.synth_rows(0, n, 512, 19, "lattice", np.float32)
+    qs = synth.lattice_queries(64, 512, 20)
+    db = eng.PatchDatabase.from_arrays(vecs, dbidx, store="f16")
+    db.set_scan_mode(2)
+    ids = np.unique(dbidx)
+    rng = np.random.default_rng(1)
+    ex = [rng.choice(ids, size=s, replace=False) for s in rng.choice([0, 5, 50, 500], size=64)]
+    for k in (50, 7):
+        r = db.scan_topk(qs, k, exclude=ex)
+        for qi in range(64):
+            o = orc.query_prelim(vecs, dbidx, qs[qi], k, exclude=ex[qi])
+            kk = len(o["dbidx"])
+            assert r["count"][qi] == kk
+            assert (r["dbidx"][qi, :kk] == o["dbidx"]).all(), (k, qi)
+            assert (r["row"][qi, :kk] == o["best_row"]).all(), (k, qi)
+            assert (r["score"][qi, :kk] == o["max_score"]).all(), (k, qi)
+    # partial batch, and more than 64 queries (two passes)
+    for nq in (3, 100):
+        qq = synth.lattice_queries(nq, 512, 30 + nq)
+        r = db.scan_topk(qq, 10)
+        for qi in range(nq):
+            o = orc.query_prelim(vecs, dbidx, qq[qi], 10)
+            assert (r["dbidx"][qi] == o["dbidx"]).all() and (r["row"][qi] == o["best_row"]).all()
+    db.close()
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_batched_tc_vs_reference_golden(eng, golden, name):
+    c = cases.CASES[name]
+    vecs, meta, qs = cases.ms_inputs(c)
+    dbidx = meta.dbidx.values
+    db = eng.PatchDatabase.from_arrays(vecs, dbidx, store="f16")
+    db.set_scan_mode(2)
+    sets = cases.exclude_sets(meta, c["seed"] + 7)
+    names = list(sets)
+    # one batch holding every (exclude set, query) pair of the golden file
+    batch_q = np.stack([qs[qi] for x in names for qi in range(2)])
+    batch_ex = [sets[x] for x in names for qi in range(2)]
+    r = db.scan_topk(batch_q, 50, exclude=batch_ex)
+    j = 0
+    for x in names:
+        for qi in range(2):
+            key = f"{name}/prelim/{x}/{qi}"
+            gd, gs = golden[key + "/dbidx"], golden[key + "/score"]
+            n = r["count"][j]
+            assert n == len(gd), key
+            np.testing.assert_allclose(r["score"][j, :n], gs, rtol=1e-5, atol=1e-6)
+            if not (r["dbidx"][j, :n] == gd).all():
+                admissible(r["dbidx"][j, :n], r["score"][j, :n], vecs, dbidx, qs[qi], sets[x], 50)
+            j += 1
+    db.close()
+
+
+def test_batched_matches_streaming_kernel(eng):
+    """K2 and K1 must return identical ids on Gaussian data (scores within 1e-5 relative)."""
+    counts = synth.patches_per_image(20000, 20, 60, 3)
+    dbidx = synth.dbidx_of_rows(counts)
+    db = eng.PatchDatabase.synthetic(dbidx, 512, seed=4, kind="tri", store="f16")
+    qs = synth.unit_queries(64, 512, 5)
+    ex = [np.arange(i, 20000, 97) for i in range(64)]
+    db.set_scan_mode(1)
+    a = db.scan_topk(qs, 50, exclude=ex)
+    db.set_scan_mode(2)
+    b = db.scan_topk(qs, 50, exclude=ex)
+    np.testing.assert_allclose(a["score"], b["score"], rtol=1e-5, atol=1e-6)
+    mism = (a["dbidx"] != b["dbidx"]).sum()
+    assert mism <= 4, mism      # only adjacent near-ties may swap
+    db.close()
