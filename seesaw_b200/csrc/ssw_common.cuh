@@ -117,6 +117,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Same, with a long suspend-time hint: the waiting warp sleeps in hardware until the phase completes
+// instead of re-polling every few hundred cycles and stealing issue slots from the warps that share
+// its scheduler (ncu on K2: 21M TRYWAIT executions from the producer/MMA warps).
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(0x989680u)
+        : "memory");
+  } while (!ok);
+}
 // 1-D bulk async copy global -> shared (UBLKCP), completion counted in bytes on an mbarrier.
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile(

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_kernel(const __grid_constan
       for (int64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
         for (int t = 0; t < ntiles; ++t) {
           for (int kc = 0; kc < Cfg::KC; ++kc) {
-            mbar_wait(S.empty + 8 * p.stage, p.phase ^ 1);
+            mbar_wait_parked(S.empty + 8 * p.stage, p.phase ^ 1);
             mbar_expect_tx(S.full + 8 * p.stage, Cfg::STAGE_BYTES);
             tma_load_2d(S.stages + p.stage * Cfg::STAGE_BYTES, &tmap, kc * kTcKChunk, t * NT, S.full + 8 * p.stage);
             p.advance();
@@ -95,15 +95,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_kernel(const __grid_constan
     TcPipe p(NS);
     uint32_t it = 0, blk_phase = 0;
     for (int64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
-      mbar_wait(S.a_ready, blk_phase);
+      mbar_wait_parked(S.a_ready, blk_phase);
       blk_phase ^= 1;
       tc_fence_after();
       for (int t = 0; t < ntiles; ++t, ++it) {
         const uint32_t as = it & 1;
-        mbar_wait(S.tmem_empty + 8 * as, ((it >> 1) & 1) ^ 1);
+        mbar_wait_parked(S.tmem_empty + 8 * as, ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         for (int kc = 0; kc < Cfg::KC; ++kc) {
-          mbar_wait(S.full + 8 * p.stage, p.phase);
+          mbar_wait_parked(S.full + 8 * p.stage, p.phase);
           tc_fence_after();
           if (lane == 0) {
             const uint64_t bdesc = make_bdesc_sw128(S.stages + p.stage * Cfg::STAGE_BYTES);

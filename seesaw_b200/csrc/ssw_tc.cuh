@@ -71,6 +71,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+// 16 lanes x 32 columns, mma-accumulator style: with j = lane%4, r = lane/4 the thread receives, for
+// every 8-column group i (0..3):  v[4i+0] = (lane r, col 8i+2j)   v[4i+1] = (lane r,   col 8i+2j+1)
+//                                  v[4i+2] = (lane r+8, col 8i+2j) v[4i+3] = (lane r+8, col 8i+2j+1)
+// (cute/atom/copy_traits_sm100.hpp, SM100_TMEM_LOAD_16dp256b4x).  taddr's lane field selects the
+// 16-lane half of the warp's quarter.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
