@@ -128,6 +128,11 @@ int ssw_knn_build_device(int device, const void* d_vectors_f16, int64_t n, int d
                          void* stream);
 
 /* ---- introspection for benchmarks / tests ---------------------------------------------- */
+/* With profiling on, every launch of the dominant scan kernel (K1 streaming or K2 tcgen05) is
+ * bracketed by CUDA events on its own stream.  ssw_profile_read synchronises those events and
+ * returns the summed kernel time and launch count since the last read, then resets them. */
+int ssw_profile_enable(ssw_db* db, int on);
+int ssw_profile_read(ssw_db* db, double* scan_kernel_ms, int64_t* scan_kernel_launches);
 /* number of kernels this library has launched since load (all handles) */
 int64_t ssw_kernel_launch_count(void);
 

@@ -56,6 +56,8 @@ SIGNATURES = {
     "ssw_knn_build": (C.c_int, [C.c_int, _p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64, _p, _p]),
     "ssw_knn_build_device": (C.c_int, [C.c_int, _p, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64, _p, _p, _p]),
     "ssw_kernel_launch_count": (C.c_int64, []),
+    "ssw_profile_enable": (C.c_int, [_p, C.c_int]),
+    "ssw_profile_read": (C.c_int, [_p, C.POINTER(C.c_double), _i64p]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
     _f = getattr(lib, _name)

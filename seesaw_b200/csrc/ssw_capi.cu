@@ -46,6 +46,24 @@ int ensure_device(int device, int* sm_count) {
   return SSW_OK;
 }
 
+void prof_begin(ssw_db* db, cudaStream_t st) {
+  if (!db->profiling) return;
+  std::pair<cudaEvent_t, cudaEvent_t> ev;
+  if (!db->prof_free.empty()) {
+    ev = db->prof_free.back();
+    db->prof_free.pop_back();
+  } else {
+    cudaEventCreate(&ev.first);
+    cudaEventCreate(&ev.second);
+  }
+  cudaEventRecord(ev.first, st);
+  db->prof_pending.push_back(ev);
+}
+void prof_end(ssw_db* db, cudaStream_t st) {
+  if (!db->profiling || db->prof_pending.empty()) return;
+  cudaEventRecord(db->prof_pending.back().second, st);
+}
+
 template <typename T>
 static int dev_alloc(T** p, size_t n) {
   *p = nullptr;
@@ -225,6 +243,11 @@ int ssw_db_destroy(ssw_db* db) {
   cudaFree(db->d_gthr);
   cudaFree(db->d_stage);
   if (db->h_stage) cudaFreeHost(db->h_stage);
+  for (auto* v : {&db->prof_pending, &db->prof_free})
+    for (auto& ev : *v) {
+      cudaEventDestroy(ev.first);
+      cudaEventDestroy(ev.second);
+    }
   if (db->stream) cudaStreamDestroy(db->stream);
   delete db;
   return SSW_OK;
@@ -339,6 +362,31 @@ int ssw_db_vectors_device(const ssw_db* db, void** dev_ptr) {
   return SSW_OK;
 }
 
+int ssw_profile_enable(ssw_db* db, int on) {
+  SSW_REQUIRE(db != nullptr, "db is null");
+  db->profiling = on != 0;
+  return SSW_OK;
+}
+
+int ssw_profile_read(ssw_db* db, double* scan_kernel_ms, int64_t* scan_kernel_launches) {
+  SSW_REQUIRE(db != nullptr, "db is null");
+  SSW_CUDA(cudaSetDevice(db->device));
+  double total = 0.0;
+  int64_t n = 0;
+  for (auto& ev : db->prof_pending) {
+    SSW_CUDA(cudaEventSynchronize(ev.second));
+    float ms = 0.f;
+    SSW_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+    total += ms;
+    ++n;
+    db->prof_free.push_back(ev);
+  }
+  db->prof_pending.clear();
+  if (scan_kernel_ms) *scan_kernel_ms = total;
+  if (scan_kernel_launches) *scan_kernel_launches = n;
+  return SSW_OK;
+}
+
 int ssw_set_scan_mode(ssw_db* db, int mode) {
   SSW_REQUIRE(db != nullptr, "db is null");
   SSW_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
@@ -377,18 +425,22 @@ static int scan_topk_impl(ssw_db* db, const float* d_queries, int nq, int k, con
   if (use_tc) {
     for (int q0 = 0; q0 < nq; q0 += SSW_MAX_BATCH) {
       const int nb = std::min(SSW_MAX_BATCH, nq - q0);
+      prof_begin(db, st);
       rc = launch_scan_tc(db, d_queries + (size_t)q0 * db->dim, nb, k,
                           d_exclude_bits ? d_exclude_bits + (size_t)q0 * db->excl_words : nullptr,
                           db->d_list_keys + (size_t)q0 * lists * k, db->d_list_dbidx + (size_t)q0 * lists * k,
                           db->d_gthr + q0, st);
+      prof_end(db, st);
       if (rc) return rc;
     }
   } else {
     for (int q = 0; q < nq; ++q) {
+      prof_begin(db, st);
       rc = launch_scan1(db, d_queries + (size_t)q * db->dim, k,
                         d_exclude_bits ? d_exclude_bits + (size_t)q * db->excl_words : nullptr,
                         db->d_list_keys + (size_t)q * lists * k, db->d_list_dbidx + (size_t)q * lists * k,
                         db->d_gthr + q, st);
+      prof_end(db, st);
       if (rc) return rc;
     }
   }

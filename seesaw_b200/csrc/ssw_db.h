@@ -1,5 +1,8 @@
 // Internal definition of the database handle and kernel launch entry points.
 #pragma once
+#include <utility>
+#include <vector>
+
 #include "ssw_common.cuh"
 
 struct ssw_db {
@@ -36,6 +39,10 @@ struct ssw_db {
   size_t d_stage_bytes = 0;
   void* h_stage = nullptr;         // pinned
   size_t h_stage_bytes = 0;
+  // optional per-launch timing of the scan kernel (ssw_profile_enable)
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pending;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_free;
 };
 
 namespace ssw {
@@ -44,6 +51,9 @@ constexpr int kScanWarps = 8;             // warps per CTA of the streaming scan
 constexpr int kMergeCap = 8192;           // candidates the merge kernel sorts in shared memory
 
 int ensure_device(int device, int* sm_count);
+// event pair around the scan kernel when profiling is on (no-ops otherwise)
+void prof_begin(ssw_db* db, cudaStream_t st);
+void prof_end(ssw_db* db, cudaStream_t st);
 
 // streaming single-query scan (K1); MODE 0 = fused segmented max + exclusion + top-k lists,
 // MODE 1 = plain score vector (index.score)

@@ -91,6 +91,16 @@ class PatchDatabase:
         """0 auto, 1 streaming SIMT kernel, 2 tcgen05 batched kernel."""
         check(lib.ssw_set_scan_mode(self._h, int(mode)))
 
+    def profile(self, on=True):
+        """Bracket every scan-kernel launch with CUDA events (read back with :meth:`profile_read`)."""
+        check(lib.ssw_profile_enable(self._h, int(bool(on))))
+
+    def profile_read(self):
+        """(summed scan-kernel milliseconds, launches) since the last read."""
+        ms, n = C.c_double(), C.c_int64()
+        check(lib.ssw_profile_read(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     # ---- host-buffer API (what the reference-facing classes call) --------------------------
     def scan_topk(self, queries, k, exclude=None):
         """queries [nq, dim] or [dim] fp32; exclude: list of nq iterables of dbidx (or None).

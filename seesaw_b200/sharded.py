@@ -1,0 +1,95 @@
+"""Row-sharded patch database: one process per GPU, one NCCL all-gather per query batch.
+
+The reference has no multi-device path (its only scaling axes are annoy and subsetting,
+multiscale_index.py:304-308, 364-376).  Here the database is split by IMAGE into contiguous ranges of
+about equal row count, so every image's patches live on one GPU and the per-image max stays local
+(SURVEY.md §8e).  Each rank scans its shard for the same query batch, emits [nq, k] (key, dbidx)
+candidates whose keys embed GLOBAL row numbers (tie-breaking is therefore shard-invariant), the
+lists are all-gathered (nq*k*12 bytes per rank) and every rank merges them with the K4 kernel.
+
+The collective plumbing is backend-agnostic: with the ``gloo`` backend and an injected scanner the
+same code runs on CPU tensors, which is how tests/test_sharded_cpu.py covers world_size 2."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_image_ranges(rows_per_image, world_size):
+    """Contiguous image ranges with ~equal rows: returns int64 [world_size+1] image boundaries."""
+    rows_per_image = np.asarray(rows_per_image, dtype=np.int64)
+    cum = np.concatenate([[0], np.cumsum(rows_per_image)])
+    total = int(cum[-1])
+    targets = (np.arange(world_size + 1, dtype=np.float64) * total / world_size).astype(np.int64)
+    bounds = np.searchsorted(cum, targets, side="left")
+    bounds[0], bounds[-1] = 0, len(rows_per_image)
+    return np.maximum.accumulate(bounds).astype(np.int64)
+
+
+def merge_candidates_host(keys, dbidx, k):
+    """numpy statement of the merge (K4) for CPU tensors: keys uint64 [n_lists, nq, k], 0 = empty.
+    Returns (key, dbidx) [nq, k] best-first.  Used by the gloo path and as the checker of K4."""
+    n_lists, nq, kk = keys.shape
+    flat_k = np.transpose(keys, (1, 0, 2)).reshape(nq, n_lists * kk)
+    flat_d = np.transpose(dbidx, (1, 0, 2)).reshape(nq, n_lists * kk)
+    order = np.argsort(~flat_k, axis=1, kind="stable")[:, :k]        # descending by key
+    out_k = np.take_along_axis(flat_k, order, axis=1)
+    out_d = np.where(out_k != 0, np.take_along_axis(flat_d, order, axis=1), -1)
+    return out_k, out_d.astype(np.int32)
+
+
+def decode_keys(keys):
+    """uint64 keys -> (score fp32, global row int64); empty slots -> (-inf, -1)."""
+    keys = np.asarray(keys, dtype=np.uint64)
+    u = (keys >> np.uint64(32)).astype(np.uint32)
+    bits = np.where(u & np.uint32(0x80000000), u & np.uint32(0x7FFFFFFF), ~u).astype(np.uint32)
+    score = bits.view(np.float32).copy()
+    row = (np.uint64(0xFFFFFFFF) - (keys & np.uint64(0xFFFFFFFF))).astype(np.int64)
+    empty = keys == 0
+    score[empty] = -np.inf
+    row[empty] = -1
+    return score, row
+
+
+class ShardedPatchDatabase:
+    """One rank's view of a row-sharded database.
+
+    ``local`` must offer ``scan_topk_device(d_queries, k, d_exclude_bits) -> (keys, dbidx)`` and
+    ``build_exclude_bits(exclude, nq)``: a :class:`seesaw_b200.engine.PatchDatabase` on GPUs."""
+
+    def __init__(self, local, *, rank, world_size, group=None, merge=None):
+        self.local, self.rank, self.world_size, self.group = local, rank, world_size, group
+        self._merge = merge
+
+    @classmethod
+    def synthetic(cls, rows_per_image, dim, *, seed, rank, world_size, device, kind="tri", store="f16", group=None):
+        """Every rank calls this with the SAME rows_per_image; rank r materialises only its images."""
+        from .engine import PatchDatabase
+        from .synth import dbidx_of_rows
+        rows_per_image = np.asarray(rows_per_image, dtype=np.int64)
+        bounds = shard_image_ranges(rows_per_image, world_size)
+        i0, i1 = int(bounds[rank]), int(bounds[rank + 1])
+        row_base = int(rows_per_image[:i0].sum())
+        dbidx = dbidx_of_rows(rows_per_image[i0:i1], dbidx_start=i0)
+        local = PatchDatabase.synthetic(dbidx, dim, seed=seed, kind=kind, store=store, device=device,
+                                        global_row_base=row_base)
+        return cls(local, rank=rank, world_size=world_size, group=group)
+
+    def scan_topk_device(self, d_queries, k, exclude=None, d_exclude_bits=None):
+        """Same result on every rank: dict(key, dbidx [nq,k], and on GPUs score/row/count)."""
+        import torch
+        import torch.distributed as dist
+        nq = d_queries.shape[0]
+        if d_exclude_bits is None and exclude is not None:
+            d_exclude_bits = self.local.build_exclude_bits(exclude, nq)
+        keys, dbidx = self.local.scan_topk_device(d_queries, k, d_exclude_bits)
+        if self.world_size == 1 and self._merge is None:
+            from .engine import merge_topk_device
+            return merge_topk_device(keys.unsqueeze(0), dbidx.unsqueeze(0), k)
+        all_k = torch.empty((self.world_size,) + tuple(keys.shape), dtype=keys.dtype, device=keys.device)
+        all_d = torch.empty((self.world_size,) + tuple(dbidx.shape), dtype=dbidx.dtype, device=dbidx.device)
+        dist.all_gather_into_tensor(all_k, keys.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(all_d, dbidx.contiguous(), group=self.group)
+        if self._merge is not None:
+            return self._merge(all_k, all_d, k)
+        from .engine import merge_topk_device
+        return merge_topk_device(all_k, all_d, k)
