@@ -23,26 +23,37 @@ bool debug_sync() {
   return on;
 }
 
+// cudaGetDeviceProperties costs milliseconds per call; the answer per device never changes.
 int ensure_device(int device, int* sm_count) {
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess || n == 0) {
-    cudaGetLastError();
-    set_error("no CUDA device available: seesaw_b200 has no CPU path");
-    return SSW_ERR_NO_DEVICE;
+  constexpr int kMaxDev = 64;
+  static int n_dev = -1;
+  static int sm_of[kMaxDev];          // 0 = not probed yet, -1 = not sm_100
+  if (n_dev < 0) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+      cudaGetLastError();
+      set_error("no CUDA device available: seesaw_b200 has no CPU path");
+      return SSW_ERR_NO_DEVICE;
+    }
+    n_dev = n < kMaxDev ? n : kMaxDev;
   }
-  if (device < 0 || device >= n) {
+  if (device < 0 || device >= n_dev) {
     set_error("device index out of range");
     return SSW_ERR_INVALID;
   }
-  cudaDeviceProp p;
-  SSW_CUDA(cudaGetDeviceProperties(&p, device));
-  if (p.major != 10) {
-    set_error(std::string("device '") + p.name + "' is not sm_100 (Blackwell B200); kernels are sm_100a only");
+  if (sm_of[device] == 0) {
+    int major = 0, sms = 0;
+    SSW_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    SSW_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    sm_of[device] = major == 10 ? sms : -1;
+  }
+  if (sm_of[device] < 0) {
+    set_error("device " + std::to_string(device) + " is not sm_100 (Blackwell B200); kernels are sm_100a only");
     return SSW_ERR_NO_DEVICE;
   }
   SSW_CUDA(cudaSetDevice(device));
-  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (sm_count) *sm_count = sm_of[device];
   return SSW_OK;
 }
 
@@ -141,6 +152,12 @@ static int build_layout(ssw_db* db, const int32_t* dbidx_per_row, std::vector<in
   }
   img_of_row[n] = -1;
   row_ptr.push_back(n);
+  // one bit per device row: last row of its image (read by the batched scan instead of the 4-byte ids)
+  std::vector<uint32_t> last_bits((size_t)(n / 32) + 8, 0u);
+  for (size_t i = 1; i < row_ptr.size(); ++i) {
+    const int64_t r = row_ptr[i] - 1;
+    if (r >= 0) last_bits[r >> 5] |= 1u << (r & 31);
+  }
   db->n_images = (int64_t)img_dbidx.size();
   db->excl_words = ((db->n_images + 31) / 32 + 3) / 4 * 4;
   if (db->excl_words == 0) db->excl_words = 4;
@@ -161,6 +178,8 @@ static int build_layout(ssw_db* db, const int32_t* dbidx_per_row, std::vector<in
   if ((rc = dev_alloc(&db->d_row_ptr, row_ptr.size()))) return rc;
   if ((rc = dev_alloc(&db->d_img_dbidx, img_dbidx.size()))) return rc;
   if ((rc = dev_alloc(&db->d_part, part.size()))) return rc;
+  if ((rc = dev_alloc(&db->d_last_bits, last_bits.size()))) return rc;
+  SSW_CUDA(cudaMemcpy(db->d_last_bits, last_bits.data(), last_bits.size() * 4, cudaMemcpyHostToDevice));
   SSW_CUDA(cudaMemcpy(db->d_img_of_row, img_of_row.data(), (n + 1) * 4, cudaMemcpyHostToDevice));
   SSW_CUDA(cudaMemcpy(db->d_row_ptr, row_ptr.data(), row_ptr.size() * 8, cudaMemcpyHostToDevice));
   if (!img_dbidx.empty())
@@ -221,8 +240,8 @@ int ssw_device_count(int* out_count) {
     return SSW_OK;
   }
   for (int i = 0; i < n; ++i) {
-    cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++*out_count;
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ++*out_count;
   }
   return SSW_OK;
 }
@@ -237,7 +256,8 @@ int ssw_db_destroy(ssw_db* db) {
   cudaFree(db->d_img_dbidx);
   cudaFree(db->d_orig_row);
   cudaFree(db->d_part);
-  cudaFree(db->d_tile_img);
+  cudaFree(db->d_last_bits);
+  cudaFree(db->d_tc_ws);
   cudaFree(db->d_list_keys);
   cudaFree(db->d_list_dbidx);
   cudaFree(db->d_gthr);
@@ -415,7 +435,6 @@ static int scan_topk_impl(ssw_db* db, const float* d_queries, int nq, int k, con
   const int lists = db->scan_grid;
   int rc = ensure_lists(db, nq, lists, k);
   if (rc) return rc;
-  SSW_CUDA(cudaMemsetAsync(db->d_gthr, 0, (size_t)nq * 8, st));
   const bool tc_ok = scan_tc_supported(db, k);
   if (db->scan_mode == 2 && !tc_ok) {
     set_error("tcgen05 batched scan needs fp16 storage, dim 256/512/768 and k <= 64");
@@ -423,17 +442,17 @@ static int scan_topk_impl(ssw_db* db, const float* d_queries, int nq, int k, con
   }
   const bool use_tc = db->scan_mode == 2 || (db->scan_mode == 0 && tc_ok && nq >= 8);
   if (use_tc) {
+    if (!db->d_tc_ws) SSW_CUDA(cudaMalloc(&db->d_tc_ws, scan_tc_workspace_bytes(db->dim)));
     for (int q0 = 0; q0 < nq; q0 += SSW_MAX_BATCH) {
       const int nb = std::min(SSW_MAX_BATCH, nq - q0);
-      prof_begin(db, st);
       rc = launch_scan_tc(db, d_queries + (size_t)q0 * db->dim, nb, k,
                           d_exclude_bits ? d_exclude_bits + (size_t)q0 * db->excl_words : nullptr,
                           db->d_list_keys + (size_t)q0 * lists * k, db->d_list_dbidx + (size_t)q0 * lists * k,
-                          db->d_gthr + q0, st);
-      prof_end(db, st);
+                          db->d_gthr + q0, db->d_tc_ws, st);
       if (rc) return rc;
     }
   } else {
+    SSW_CUDA(cudaMemsetAsync(db->d_gthr, 0, (size_t)nq * 8, st));
     for (int q = 0; q < nq; ++q) {
       prof_begin(db, st);
       rc = launch_scan1(db, d_queries + (size_t)q * db->dim, k,

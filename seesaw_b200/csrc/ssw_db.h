@@ -23,7 +23,8 @@ struct ssw_db {
   int64_t* d_orig_row = nullptr;   // [n_rows] device row -> original local row; NULL when identity
   int32_t* d_part = nullptr;       // [scan_warps + 1] image range of every scan warp
   int scan_grid = 0;               // CTAs of the streaming scan (one per SM)
-  int32_t* d_tile_img = nullptr;   // reserved for the tcgen05 batched scan
+  uint32_t* d_last_bits = nullptr; // [n_rows/32 + pad] bit r set <=> device row r is the last row of its image
+  void* d_tc_ws = nullptr;         // prepared A operand of the tcgen05 batched scan (one batch)
 
   int64_t excl_words = 0;          // uint32 words of one exclusion bitmap (n_images bits, padded)
 
@@ -62,8 +63,9 @@ int launch_scan1(ssw_db* db, const float* d_query, int k, const uint32_t* d_excl
 int launch_score_all(ssw_db* db, const float* d_query, float* d_out, cudaStream_t st);
 // tcgen05 batched scan (K2): one pass for up to 64 queries; fp16 storage, dim 256/512/768, k <= 64
 bool scan_tc_supported(const ssw_db* db, int k);
+size_t scan_tc_workspace_bytes(int dim);
 int launch_scan_tc(ssw_db* db, const float* d_queries, int nq, int k, const uint32_t* d_excl, uint64_t* d_list_keys,
-                   int32_t* d_list_dbidx, uint64_t* d_gthr, cudaStream_t st);
+                   int32_t* d_list_dbidx, uint64_t* d_gthr, void* workspace, cudaStream_t st);
 // merge kernel (K4)
 int launch_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_lists, int64_t list_stride,
                  int64_t query_stride, int nq, int k, const uint64_t* d_thr, uint64_t* d_out_key,

@@ -433,6 +433,7 @@ int launch_score_all(ssw_db* db, const float* d_query, float* d_out, cudaStream_
 // of K1/K2 and after the NCCL all-gather of per-shard lists.
 // ------------------------------------------------------------------------------------------
 constexpr int kMergeThreads = 1024;
+constexpr int kMergeOut = SSW_MAX_TOPK;     // selected candidates are sorted in a second, small buffer
 
 struct MergeArgs {
   const uint64_t* keys;
@@ -448,17 +449,58 @@ struct MergeArgs {
   int32_t* out_count;
 };
 
+// One MSB-first radix-select step over 8 bits: given the histogram of byte d of the keys that match
+// the prefix above it, warp 0 finds the bin holding the `remaining`-th largest key.
+__device__ __forceinline__ void merge_pick_bin(const int* hist, int d, uint64_t* s_prefix, int* s_remaining) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    // lane l owns bins 255-8l .. 248-8l (descending order of key value)
+    int c[8], tot = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      c[i] = hist[255 - 8 * lane - i];
+      tot += c[i];
+    }
+    int incl = tot;
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, incl, m);
+      if (lane >= m) incl += o;
+    }
+    const int rem = *s_remaining;
+    const int excl = incl - tot;
+    __syncwarp();
+    if (excl < rem && rem <= incl) {     // exactly one lane
+      int need = rem - excl, b = 255 - 8 * lane;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (need > 0 && c[i] >= need) {
+          b = 255 - 8 * lane - i;
+          *s_remaining = need;
+          need = 0;
+        } else if (need > 0) {
+          need -= c[i];
+        }
+      }
+      *s_prefix = *s_prefix | ((uint64_t)b << (8 * d));
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kMergeThreads, 1) merge_topk_kernel(const MergeArgs a) {
   extern __shared__ __align__(16) uint8_t msmem[];
-  uint64_t* sk = reinterpret_cast<uint64_t*>(msmem);
-  int32_t* sd = reinterpret_cast<int32_t*>(sk + kMergeCap);
+  uint64_t* sk = reinterpret_cast<uint64_t*>(msmem);                 // [kMergeCap] survivors
+  uint64_t* ok = sk + kMergeCap;                                     // [kMergeOut] selected top-k
+  int32_t* sd = reinterpret_cast<int32_t*>(ok + kMergeOut);          // [kMergeCap]
+  int32_t* od = sd + kMergeCap;                                      // [kMergeOut]
   __shared__ int s_cnt;
   __shared__ int s_hist[256];
   __shared__ uint64_t s_prefix;
   __shared__ int s_remaining;
 
   const int q = blockIdx.x, tid = threadIdx.x;
-  const int64_t total = (int64_t)a.n_lists * a.k;
+  const uint32_t k = (uint32_t)a.k;
+  const uint32_t total = (uint32_t)a.n_lists * k;
   const uint64_t* kq = a.keys + (int64_t)q * a.query_stride;
   const int32_t* dq = a.dbidx + (int64_t)q * a.query_stride;
   uint64_t thr = a.thr ? a.thr[q] : 0ull;
@@ -467,8 +509,8 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_topk_kernel(const Merg
   auto gather = [&](uint64_t lo) {
     if (tid == 0) s_cnt = 0;
     __syncthreads();
-    for (int64_t e = tid; e < total; e += kMergeThreads) {
-      const int64_t off = (e / a.k) * a.list_stride + (e % a.k);
+    for (uint32_t e = tid; e < total; e += kMergeThreads) {
+      const int64_t off = (int64_t)(e / k) * a.list_stride + (e % k);
       const uint64_t key = kq[off];
       if (key >= lo) {
         const int p = atomicAdd(&s_cnt, 1);
@@ -484,9 +526,8 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_topk_kernel(const Merg
 
   int n = gather(thr);
   if (n > kMergeCap) {
-    // Too many survivors for shared memory: exact k-th largest key by MSB-first radix select
-    // over the global lists (8 passes of 8 bits), then gather the >= T set (exactly k keys,
-    // keys are unique because every key embeds a distinct row).
+    // Too many survivors for shared memory: exact k-th largest key by radix select over the global
+    // lists, then gather the >= T set (exactly k keys: every key embeds a distinct row).
     if (tid == 0) {
       s_prefix = 0;
       s_remaining = a.k;
@@ -495,63 +536,98 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_topk_kernel(const Merg
       for (int i = tid; i < 256; i += kMergeThreads) s_hist[i] = 0;
       __syncthreads();
       const uint64_t prefix = s_prefix;
-      for (int64_t e = tid; e < total; e += kMergeThreads) {
-        const int64_t off = (e / a.k) * a.list_stride + (e % a.k);
+      for (uint32_t e = tid; e < total; e += kMergeThreads) {
+        const int64_t off = (int64_t)(e / k) * a.list_stride + (e % k);
         const uint64_t key = kq[off];
         if (key < thr) continue;
         const bool match = (d == 7) || ((key >> (8 * (d + 1))) == (prefix >> (8 * (d + 1))));
         if (match) atomicAdd(&s_hist[(int)((key >> (8 * d)) & 255)], 1);
       }
       __syncthreads();
-      if (tid == 0) {
-        int rem = s_remaining, b = 255;
-        for (; b > 0; --b) {
-          if (s_hist[b] >= rem) break;
-          rem -= s_hist[b];
-        }
-        s_remaining = rem;
-        s_prefix = prefix | ((uint64_t)b << (8 * d));
-      }
+      merge_pick_bin(s_hist, d, &s_prefix, &s_remaining);
       __syncthreads();
     }
     n = gather(s_prefix);
   }
   n = min(n, kMergeCap);
+  // ---- select the top min(n, k) survivors into (ok, od)
+  int m;
+  if (n <= a.k) {
+    m = n;
+    for (int i = tid; i < n; i += kMergeThreads) {
+      ok[i] = sk[i];
+      od[i] = sd[i];
+    }
+    __syncthreads();
+  } else {
+    if (tid == 0) {
+      s_prefix = 0;
+      s_remaining = a.k;
+    }
+    for (int d = 7; d >= 0; --d) {
+      for (int i = tid; i < 256; i += kMergeThreads) s_hist[i] = 0;
+      __syncthreads();
+      const uint64_t prefix = s_prefix;
+      for (int i = tid; i < n; i += kMergeThreads) {
+        const uint64_t key = sk[i];
+        const bool match = (d == 7) || ((key >> (8 * (d + 1))) == (prefix >> (8 * (d + 1))));
+        if (match) atomicAdd(&s_hist[(int)((key >> (8 * d)) & 255)], 1);
+      }
+      __syncthreads();
+      merge_pick_bin(s_hist, d, &s_prefix, &s_remaining);
+      __syncthreads();
+    }
+    const uint64_t T = s_prefix;     // the k-th largest key
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += kMergeThreads) {
+      const uint64_t key = sk[i];
+      if (key >= T) {
+        const int p = atomicAdd(&s_cnt, 1);
+        if (p < kMergeOut) {
+          ok[p] = key;
+          od[p] = sd[i];
+        }
+      }
+    }
+    __syncthreads();
+    m = min(s_cnt, a.k);
+  }
   int P = 1;
-  while (P < n) P <<= 1;
-  for (int i = n + tid; i < P; i += kMergeThreads) {
-    sk[i] = 0;
-    sd[i] = -1;
+  while (P < m) P <<= 1;
+  for (int i = m + tid; i < P; i += kMergeThreads) {
+    ok[i] = 0;
+    od[i] = -1;
   }
   __syncthreads();
-  // bitonic sort, descending
+  // bitonic sort, descending (P <= 2048)
   for (int size = 2; size <= P; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       for (int i = tid; i < (P >> 1); i += kMergeThreads) {
-        const int lo = ((i / stride) * stride * 2) + (i % stride);
+        const int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
         const int hi = lo + stride;
         const bool desc = ((lo & size) == 0);
-        const uint64_t x = sk[lo], y = sk[hi];
+        const uint64_t x = ok[lo], y = ok[hi];
         if ((x < y) == desc) {
-          sk[lo] = y;
-          sk[hi] = x;
-          const int32_t t = sd[lo];
-          sd[lo] = sd[hi];
-          sd[hi] = t;
+          ok[lo] = y;
+          ok[hi] = x;
+          const int32_t t = od[lo];
+          od[lo] = od[hi];
+          od[hi] = t;
         }
       }
       __syncthreads();
     }
   }
-  const int cnt = min(n, a.k);
+  const int cnt = m;
   for (int i = tid; i < a.k; i += kMergeThreads) {
-    const bool ok = i < cnt;
-    const uint64_t key = ok ? sk[i] : 0ull;
+    const bool valid = i < cnt;
+    const uint64_t key = valid ? ok[i] : 0ull;
     const int64_t o = (int64_t)q * a.k + i;
     if (a.out_key) a.out_key[o] = key;
-    if (a.out_dbidx) a.out_dbidx[o] = ok ? sd[i] : -1;
-    if (a.out_score) a.out_score[o] = ok ? key_score(key) : -INFINITY;
-    if (a.out_row) a.out_row[o] = ok ? (int64_t)key_row(key) : -1;
+    if (a.out_dbidx) a.out_dbidx[o] = valid ? od[i] : -1;
+    if (a.out_score) a.out_score[o] = valid ? key_score(key) : -INFINITY;
+    if (a.out_row) a.out_row[o] = valid ? (int64_t)key_row(key) : -1;
   }
   if (tid == 0 && a.out_count) a.out_count[q] = cnt;
 }
@@ -562,12 +638,8 @@ int launch_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_lists, in
                  cudaStream_t st) {
   MergeArgs a{d_keys, d_dbidx, n_lists, list_stride, query_stride, k, d_thr,
               d_out_key, d_out_dbidx, d_out_score, d_out_row, d_out_count};
-  const size_t smem = (size_t)kMergeCap * 12;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SSW_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  const size_t smem = (size_t)(kMergeCap + kMergeOut) * 12;
+  SSW_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   merge_topk_kernel<<<nq, kMergeThreads, smem, st>>>(a);
   SSW_LAUNCHED();
   return SSW_OK;

@@ -8,11 +8,20 @@
 // The database is read from HBM ONCE per batch (arithmetic intensity 64 flop/B would make 64 CUDA-core
 // passes compute-bound; on the tensor pipe the pass stays HBM-bound).  Orientation: queries are the
 // resident A operand in TMEM, database rows are the streamed B operand, so accumulator lane = query
-// and accumulator column = database row: every epilogue thread owns one query and walks the rows of
-// the tile in order — the per-image segmented max is a running max, image boundaries are warp-uniform.
+// and accumulator column = database row: the per-image segmented max is a running max along the
+// columns and image boundaries are warp-uniform.
 // fp32 queries are split into hi + lo fp16 parts after scaling by a power of two (keeps ~22 mantissa
-// bits; exact for fp16-representable queries): lane 32w+j holds the hi part of query 16w+j, lane
-// 32w+16+j its lo part, and the two partial dot products meet with one shfl_xor(16).
+// bits; exact for fp16-representable queries) by a small preparation kernel that writes the TMEM image
+// of the A operand.  TMEM lane layout of a 32-lane quarter q4 (h = 0,1; r = 0..7):
+//   lane 16h + r     : hi part of query 16*q4 + 8h + r
+//   lane 16h + 8 + r : lo part of the same query
+// so a 16x256b tcgen05.ld of half h hands thread (r = lane/4, j = lane%4) BOTH parts of one query for
+// columns 8i+2j, 8i+2j+1 (i = 0..3): hi + lo needs no shuffle and no lane is redundant.
+//
+// Epilogue cost model: per 128-row tile a thread does 64 x (FADD, FSETP, 2 SEL); an image
+// boundary costs one vote, and only when some lane's partial max reaches its query's threshold a quad
+// reduction (8 SHFL) plus the owner's threshold / exclusion / list work.  Everything lives in registers
+// and shared memory: no local memory, no out-of-line calls.
 #include <algorithm>
 
 #include "ssw_db.h"
@@ -21,12 +30,13 @@
 namespace ssw {
 
 struct ScanTcArgs {
-  const float* q;            // [nq, DIM] fp32
+  const uint32_t* a_img;     // [128][DIM/2] packed fp16 pairs: image of the A operand, one row per TMEM lane
+  const float* inv_scale;    // [64] 2^-e of every query slot (scores = accumulator * inv_scale)
   int nq;
   int k;
   const uint32_t* excl;      // [nq, excl_words] or null
   int64_t excl_words;
-  const int32_t* img_of_row; // [n_rows + 1], sentinel -1
+  const uint32_t* last_bits; // bit r set <=> device row r is the last row of its image
   const int64_t* row_ptr;
   const int32_t* img_dbidx;
   const int64_t* orig_row;   // null when identity
@@ -39,43 +49,100 @@ struct ScanTcArgs {
 
 constexpr int kTcMaxK = 64;   // per-query list length the batched epilogue keeps in shared memory
 
-// Per-query epilogue state in SHARED memory (structure of arrays over the 64 query slots).  It used
-// to be a struct in local memory: with 214 KB of the SM carved out as shared memory the L1 left for
-// local memory thrashes and every access cost an L2 round trip (ncu: LDL-dependent stalls, 2.7 us per
-// image boundary).
+// ------------------------------------------------------------------------------------------
+// query preparation: fp32 [nq, DIM] -> hi/lo fp16 image of the A operand, scales, zeroed thresholds
+// one block per TMEM lane (128), DIM/2 threads, thread t converts elements 2t, 2t+1
+// ------------------------------------------------------------------------------------------
+__global__ void scan_tc_prep_kernel(const float* __restrict__ q, int nq, int dim, uint32_t* __restrict__ a_img,
+                                    float* __restrict__ inv_scale, uint64_t* __restrict__ g_thr) {
+  const int L = blockIdx.x;                       // TMEM lane
+  const int q4 = L >> 5, h = (L >> 4) & 1, r = L & 7;
+  const bool is_lo = (L >> 3) & 1;
+  const int qa = q4 * 16 + h * 8 + r;
+  const bool ok = qa < nq;
+  const int t = threadIdx.x;
+  float x0 = 0.f, x1 = 0.f;
+  if (ok) {
+    const float2 v = reinterpret_cast<const float2*>(q + (size_t)qa * dim)[t];
+    x0 = v.x;
+    x1 = v.y;
+  }
+  __shared__ float s_max[32];
+  float mx = fmaxf(fabsf(x0), fabsf(x1));
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+  if ((t & 31) == 0) s_max[t >> 5] = mx;
+  __syncthreads();
+  mx = 0.f;
+  for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) mx = fmaxf(mx, s_max[w]);
+  int e = 0;
+  if (mx > 0.f && mx < INFINITY) {
+    int ex;
+    frexpf(mx, &ex);          // mx = m * 2^ex, m in [0.5, 1)
+    e = 11 - ex;              // mx * 2^e in [1024, 2048): hi keeps 11 bits, lo the next 11
+  }
+  const float scale = ldexpf(1.0f, e);
+  x0 *= scale;
+  x1 *= scale;
+  __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+  if (is_lo) {
+    h0 = __float2half_rn(x0 - __half2float(h0));
+    h1 = __float2half_rn(x1 - __half2float(h1));
+  }
+  a_img[(size_t)L * (dim / 2) + t] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+  if (t == 0 && !is_lo) {
+    inv_scale[qa] = ldexpf(1.0f, -e);
+    if (ok) g_thr[qa] = 0ull;
+  }
+}
+
+// Per-query epilogue state in SHARED memory (structure of arrays over the 64 query slots).
 struct QShared {
   uint64_t* keys;       // [k][64]   candidate keys, slot s of query q at keys[s*64 + q]
   int32_t* img;         // [k][64]   local image index of the candidate
   uint64_t* thr;        // [64] reject keys <= thr: max(own k-th best once full, shared lower bound)
-  uint64_t* pend_key;   // [64] candidate whose exclusion word is still on its way (0 = none)
-  int32_t* pend_img;    // [64]
   int32_t* cnt;         // [64]
   int32_t* minpos;      // [64]
-  float* inv_scale;     // [64]
 };
-__host__ __device__ constexpr size_t qshared_bytes(int k) { return (size_t)k * 64 * 12 + 64 * (8 + 8 + 4 + 4 + 4 + 4); }
+__host__ __device__ constexpr size_t qshared_bytes(int k) { return (size_t)k * 64 * 12 + 64 * (8 + 4 + 4); }
 
 __device__ __forceinline__ QShared qshared_carve(uint8_t* base, int k) {
   QShared q;
   q.keys = reinterpret_cast<uint64_t*>(base);
   q.thr = q.keys + (size_t)k * 64;
-  q.pend_key = q.thr + 64;
-  q.img = reinterpret_cast<int32_t*>(q.pend_key + 64);
-  q.pend_img = q.img + (size_t)k * 64;
-  q.cnt = q.pend_img + 64;
+  q.img = reinterpret_cast<int32_t*>(q.thr + 64);
+  q.cnt = q.img + (size_t)k * 64;
   q.minpos = q.cnt + 64;
-  q.inv_scale = reinterpret_cast<float*>(q.minpos + 64);
   return q;
 }
 
-__device__ __forceinline__ void qlist_insert(const QShared& Q, const ScanTcArgs& a, int q, int k, uint64_t key, int img) {
-  if (key <= Q.thr[q]) return;
+// threshold key -> the accumulator-space score a partial maximum must reach to matter
+__device__ __forceinline__ float thr_to_acc(uint64_t thr, float scale) {
+  return thr == 0 ? -INFINITY : key_score(thr) * scale;
+}
+
+// Owner thread of query q: the finished image `img` peaked at accumulator value `best` in device row
+// `drow`.  Applies the threshold, the exclusion bitmap and the list update; returns the (possibly
+// raised) threshold key of the query.
+__device__ __forceinline__ uint64_t scan_tc_offer(const QShared& Q, const ScanTcArgs& a, int q, float best,
+                                                  float inv_scale, int64_t drow, int img) {
+  const int k = a.k;
+  const uint64_t thr = Q.thr[q];
+  uint64_t key = make_key(best * inv_scale, (uint32_t)drow);
+  if ((key >> 32) < (thr >> 32)) return thr;
+  const int64_t orow = a.orig_row ? a.orig_row[drow] : drow;
+  key = (key & 0xFFFFFFFF00000000ull) | (uint64_t)(0xFFFFFFFFu - (uint32_t)(a.row_base + orow));
+  if (key <= thr) return thr;
+  if (a.excl) {
+    const uint32_t w = __ldg(a.excl + (size_t)q * a.excl_words + (img >> 5));
+    if ((w >> (img & 31)) & 1u) return thr;
+  }
   const int cnt = Q.cnt[q];
   if (cnt < k) {
     Q.keys[cnt * 64 + q] = key;
     Q.img[cnt * 64 + q] = img;
     Q.cnt[q] = cnt + 1;
-    if (cnt + 1 < k) return;
+    if (cnt + 1 < k) return thr;
   } else {
     const int mp = Q.minpos[q];
     Q.keys[mp * 64 + q] = key;
@@ -83,6 +150,7 @@ __device__ __forceinline__ void qlist_insert(const QShared& Q, const ScanTcArgs&
   }
   uint64_t mk = ~0ull;
   int mp = 0;
+#pragma unroll 4
   for (int s = 0; s < k; ++s) {
     const uint64_t x = Q.keys[s * 64 + q];
     if (x < mk) {
@@ -91,97 +159,120 @@ __device__ __forceinline__ void qlist_insert(const QShared& Q, const ScanTcArgs&
     }
   }
   Q.minpos[q] = mp;
-  if (mk > Q.thr[q]) Q.thr[q] = mk;
+  const uint64_t nthr = mk > thr ? mk : thr;
+  Q.thr[q] = nthr;
   atomicMax(reinterpret_cast<unsigned long long*>(a.g_thr + q), (unsigned long long)mk);
+  return nthr;
 }
 
-__device__ __forceinline__ void qlist_resolve_pending(const QShared& Q, const ScanTcArgs& a, int q, int k) {
-  const uint64_t pk = Q.pend_key[q];
-  if (pk == 0) return;
-  const int img = Q.pend_img[q];
-  const uint32_t w = a.excl[(size_t)q * a.excl_words + (img >> 5)];    // prefetched when the candidate was parked
-  Q.pend_key[q] = 0;
-  if (!((w >> (img & 31)) & 1u)) qlist_insert(Q, a, q, k, pk, img);
-}
-
-// Candidate of one finished image (max score, device row holding it, image index) -> the owner's
-// top-k list.  The exclusion test needs one word of a 2 MB table: instead of stalling on it, the
-// candidate is parked with a prefetch and settled at the next call.  Out of line: once per image.
-__device__ __noinline__ void scan_tc_flush(uint8_t* qbase, const ScanTcArgs& a, int q, float smax, int64_t drow, int img) {
-  const int k = a.k;
-  const QShared Q = qshared_carve(qbase, k);
-  if (a.excl) qlist_resolve_pending(Q, a, q, k);
-  const float sc = smax * Q.inv_scale[q];
-  uint64_t key = make_key(sc, (uint32_t)drow);
-  const uint64_t thr = Q.thr[q];
-  if ((key >> 32) < (thr >> 32)) return;
-  const int64_t orow = a.orig_row ? a.orig_row[drow] : drow;
-  key = (key & 0xFFFFFFFF00000000ull) | (uint64_t)(0xFFFFFFFFu - (uint32_t)(a.row_base + orow));
-  if (key <= thr) return;
-  if (a.excl) {
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(a.excl + (size_t)q * a.excl_words + (img >> 5)));
-    Q.pend_key[q] = key;
-    Q.pend_img[q] = img;
-  } else {
-    qlist_insert(Q, a, q, k, key, img);
-  }
-}
-
-// Running (max score, column) of the two queries a thread sees through the 16x256b loads; passed and
-// returned BY VALUE so it stays in registers across the out-of-line call.
-struct Run2 {
-  float m0, m1;
-  int c0, c1;
+// Running state of one epilogue thread: partial maxima (over this thread's columns) of the two
+// queries of its quad for the image being walked, and what they must reach to matter.
+struct EpiState {
+  float m0, m1;       // running max, query A (half 0) / query B (half 1)
+  int c0, c1;         // column (relative to the CTA's first row) of that max
+  float thrA, thrB;   // accumulator-space thresholds
+  int cur_img;        // local image index of the image being walked (warp-uniform)
 };
 
-// One 8-column group that contains at least one image boundary (about 1 group in 5): walk the columns
-// in order; column p belongs to the thread with lane%4 == p/2; at a boundary the four threads of a
-// quad combine their running maxima and the owner flushes the image.  eb: boundary bits of the group,
-// sXY: this thread's column Y of half X, col8: column (relative to r_begin) of p = 0, img_lane: image
-// id of column (32g + lane) held by each lane, sub: 8-column group index within the 32 columns,
-// own_q: query slot this thread owns for half own_h (own_h < 0: none).
-// misc packs sub (bits 0-3), own_h + 1 (bits 4-7) and own_q (bits 8..) to keep the call in registers.
-__device__ __noinline__ Run2 scan_tc_slow_group(Run2 run, uint8_t* qbase, const ScanTcArgs& a, uint32_t eb, float s00,
-                                                float s01, float s10, float s11, int col8, int img_lane, int misc,
-                                                int64_t r_begin) {
-  const int lane = threadIdx.x & 31, j = lane & 3;
-  const int sub = misc & 15, own_h = ((misc >> 4) & 15) - 1, own_q = misc >> 8;
-#pragma unroll 1
-  for (int p = 0; p < 8; ++p) {
-    if ((p >> 1) == j) {
-      const float x0 = (p & 1) ? s01 : s00, x1 = (p & 1) ? s11 : s10;
-      if (x0 > run.m0) {
-        run.m0 = x0;
-        run.c0 = col8 + p;
-      }
-      if (x1 > run.m1) {
-        run.m1 = x1;
-        run.c1 = col8 + p;
+struct EpiCtx {
+  int j;              // lane % 4
+  bool owner;         // this thread owns query own_q (j == 0: query A, j == 1: query B)
+  int own_q;
+  float invA, invB, scaleA, scaleB;
+  int64_t r_begin;
+};
+
+// An image ends here (warp-uniform call).
+__device__ __forceinline__ void scan_tc_boundary(EpiState& st, const EpiCtx& cx, const QShared& Q,
+                                                 const ScanTcArgs& a) {
+  const bool cand = (st.m0 >= st.thrA) | (st.m1 >= st.thrB);
+  if (__any_sync(0xffffffffu, cand)) {
+    // (score desc, column asc) max over the quad for both queries
+    uint64_t k0 = ((uint64_t)f32_ordered(st.m0) << 32) | (uint32_t)(0x7FFFFFFF - st.c0);
+    uint64_t k1 = ((uint64_t)f32_ordered(st.m1) << 32) | (uint32_t)(0x7FFFFFFF - st.c1);
+    uint64_t o0 = shfl_xor_u64(k0, 1), o1 = shfl_xor_u64(k1, 1);
+    k0 = o0 > k0 ? o0 : k0;
+    k1 = o1 > k1 ? o1 : k1;
+    o0 = shfl_xor_u64(k0, 2);
+    o1 = shfl_xor_u64(k1, 2);
+    k0 = o0 > k0 ? o0 : k0;
+    k1 = o1 > k1 ? o1 : k1;
+    if (cx.owner) {
+      const uint64_t kk = cx.j ? k1 : k0;
+      const float best = f32_from_ordered((uint32_t)(kk >> 32));
+      const float mythr = cx.j ? st.thrB : st.thrA;
+      if (best >= mythr) {
+        const int col = 0x7FFFFFFF - (int)(uint32_t)(kk & 0xFFFFFFFFu);
+        const uint64_t nthr = scan_tc_offer(Q, a, cx.own_q, best, cx.j ? cx.invB : cx.invA, cx.r_begin + col, st.cur_img);
+        const float t = thr_to_acc(nthr, cx.j ? cx.scaleB : cx.scaleA);
+        if (cx.j) st.thrB = t; else st.thrA = t;
       }
     }
-    if ((eb >> p) & 1u) {      // warp-uniform
-      const int img = __shfl_sync(0xffffffffu, img_lane, sub * 8 + p);
-      // (score desc, column asc) max over the quad, both halves
-      uint64_t k0 = ((uint64_t)f32_ordered(run.m0) << 32) | (uint32_t)(0x7FFFFFFF - run.c0);
-      uint64_t k1 = ((uint64_t)f32_ordered(run.m1) << 32) | (uint32_t)(0x7FFFFFFF - run.c1);
-      uint64_t o0 = shfl_xor_u64(k0, 1), o1 = shfl_xor_u64(k1, 1);
-      k0 = o0 > k0 ? o0 : k0;
-      k1 = o1 > k1 ? o1 : k1;
-      o0 = shfl_xor_u64(k0, 2);
-      o1 = shfl_xor_u64(k1, 2);
-      k0 = o0 > k0 ? o0 : k0;
-      k1 = o1 > k1 ? o1 : k1;
-      if (own_h >= 0) {
-        const uint64_t kk = own_h ? k1 : k0;
-        const float best = f32_from_ordered((uint32_t)(kk >> 32));
-        const int col = 0x7FFFFFFF - (int)(uint32_t)(kk & 0xFFFFFFFFu);
-        if (best > -INFINITY) scan_tc_flush(qbase, a, own_q, best, r_begin + col, img);
+    __syncwarp();
+  }
+  st.m0 = st.m1 = -INFINITY;
+  st.c0 = st.c1 = 0;
+  ++st.cur_img;
+}
+
+// 32 accumulator columns starting at column `colbase`: v0 / v1 are the 16x256b loads of half 0 / 1,
+// em has bit c set when column colbase + c is the last row of its image.
+__device__ __forceinline__ void scan_tc_group(EpiState& st, const EpiCtx& cx, const QShared& Q, const ScanTcArgs& a,
+                                              const uint32_t* v0, const uint32_t* v1, uint32_t em, int colbase) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float s00 = __uint_as_float(v0[4 * i]) + __uint_as_float(v0[4 * i + 2]);
+    const float s01 = __uint_as_float(v0[4 * i + 1]) + __uint_as_float(v0[4 * i + 3]);
+    const float s10 = __uint_as_float(v1[4 * i]) + __uint_as_float(v1[4 * i + 2]);
+    const float s11 = __uint_as_float(v1[4 * i + 1]) + __uint_as_float(v1[4 * i + 3]);
+    const uint32_t eb = (em >> (8 * i)) & 0xFFu;
+    const int ca = colbase + 8 * i + 2 * cx.j;
+    if (eb == 0) {            // warp-uniform fast path: no image ends inside these 8 columns
+      if (s00 > st.m0) { st.m0 = s00; st.c0 = ca; }
+      if (s01 > st.m0) { st.m0 = s01; st.c0 = ca + 1; }
+      if (s10 > st.m1) { st.m1 = s10; st.c1 = ca; }
+      if (s11 > st.m1) { st.m1 = s11; st.c1 = ca + 1; }
+    } else {
+      // walk the boundaries of the group in order; this thread's columns are 2j and 2j+1
+      const int pa = 2 * cx.j, pb = pa + 1;
+      int lo = 0;
+      uint32_t e = eb;
+      do {
+        const int p = __ffs(e) - 1;
+        e &= e - 1;
+        if (pa >= lo && pa <= p) {
+          if (s00 > st.m0) { st.m0 = s00; st.c0 = ca; }
+          if (s10 > st.m1) { st.m1 = s10; st.c1 = ca; }
+        }
+        if (pb >= lo && pb <= p) {
+          if (s01 > st.m0) { st.m0 = s01; st.c0 = ca + 1; }
+          if (s11 > st.m1) { st.m1 = s11; st.c1 = ca + 1; }
+        }
+        scan_tc_boundary(st, cx, Q, a);
+        lo = p + 1;
+      } while (e);
+      if (pa >= lo) {
+        if (s00 > st.m0) { st.m0 = s00; st.c0 = ca; }
+        if (s10 > st.m1) { st.m1 = s10; st.c1 = ca; }
       }
-      run.m0 = run.m1 = -INFINITY;
-      run.c0 = run.c1 = 0;
+      if (pb >= lo) {
+        if (s01 > st.m0) { st.m0 = s01; st.c0 = ca + 1; }
+        if (s11 > st.m1) { st.m1 = s11; st.c1 = ca + 1; }
+      }
     }
   }
-  return run;
+}
+
+// tcgen05.wait::ld that also names the destination registers, so no use of them can be scheduled
+// above the wait.
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t* x, uint32_t* y) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]),
+                 "+r"(x[8]), "+r"(x[9]), "+r"(x[10]), "+r"(x[11]), "+r"(x[12]), "+r"(x[13]), "+r"(x[14]), "+r"(x[15]),
+                 "+r"(y[0]), "+r"(y[1]), "+r"(y[2]), "+r"(y[3]), "+r"(y[4]), "+r"(y[5]), "+r"(y[6]), "+r"(y[7]),
+                 "+r"(y[8]), "+r"(y[9]), "+r"(y[10]), "+r"(y[11]), "+r"(y[12]), "+r"(y[13]), "+r"(y[14]), "+r"(y[15])
+               :
+               : "memory");
 }
 
 template <int DIM, int NT, int NS>
@@ -240,143 +331,119 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
       __syncwarp();
     }
   } else {
-    // ===== epilogue warps.  TMEM lane layout of quarter q4 (lanes 32*q4 ..):
-    //   lane 16h + r      (r < 8): hi part of query 16*q4 + 8h + r
-    //   lane 16h + 8 + r          : lo part of the same query
-    // so a 16x256b load of half h hands thread (r = lane/4, j = lane%4) BOTH parts of query 16*q4+8h+r
-    // for columns 8i+2j, 8i+2j+1: the hi+lo sum needs no shuffle and no lane is redundant.
+    // ===== epilogue warps (warp w may touch TMEM lanes 32*(w%4) .. +31)
     const int q4 = warp & 3;
     const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
     const int k = a.k;
 
-    // ---- A operand (thread t writes TMEM lane 32*q4 + t)
+    // ---- A operand: thread t copies the prepared row of TMEM lane 32*q4 + t
     {
-      const int h = lane >> 4, r = lane & 7;
-      const bool is_lo = (lane >> 3) & 1;
-      const int qa = q4 * 16 + h * 8 + r;
-      const bool qa_ok = qa < a.nq;
-      const float* qp = a.q + (size_t)(qa_ok ? qa : 0) * DIM;
-      float mx = 0.f;
-      if (qa_ok)
-        for (int i = 0; i < DIM; ++i) mx = fmaxf(mx, fabsf(__ldg(qp + i)));
-      int e = 0;
-      if (mx > 0.f && mx < INFINITY) {
-        int ex;
-        frexpf(mx, &ex);          // mx = m * 2^ex, m in [0.5, 1)
-        e = 11 - ex;              // mx * 2^e in [1024, 2048): hi keeps 11 bits, lo the next 11
-      }
-      const float scale = ldexpf(1.0f, e);
-      if (!is_lo) {
-        Q.inv_scale[qa] = ldexpf(1.0f, -e);
-        Q.thr[qa] = 0;
-        Q.pend_key[qa] = 0;
-        Q.pend_img[qa] = 0;
-        Q.cnt[qa] = 0;
-        Q.minpos[qa] = 0;
-      }
+      const uint4* src = reinterpret_cast<const uint4*>(a.a_img + (size_t)(q4 * 32 + lane) * (DIM / 2));
 #pragma unroll 1
       for (int c = 0; c < Cfg::A_COLS / 32; ++c) {
         uint32_t rr[32];
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          float x0 = 0.f, x1 = 0.f;
-          if (qa_ok) {
-            x0 = __ldg(qp + c * 64 + 2 * jj) * scale;
-            x1 = __ldg(qp + c * 64 + 2 * jj + 1) * scale;
-          }
-          __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-          if (is_lo) {
-            h0 = __float2half_rn(x0 - __half2float(h0));
-            h1 = __float2half_rn(x1 - __half2float(h1));
-          }
-          rr[jj] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        for (int x = 0; x < 8; ++x) {
+          const uint4 w = __ldg(src + c * 8 + x);
+          rr[4 * x] = w.x;
+          rr[4 * x + 1] = w.y;
+          rr[4 * x + 2] = w.z;
+          rr[4 * x + 3] = w.w;
         }
         tmem_st32(lane_addr + Cfg::A_BASE + c * 32, rr);
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(S.a_ready);
-      __syncwarp();            // the state of this warp's 16 query slots is visible below
+      if (lane < 16) {           // this warp's 16 query slots
+        const int qs = q4 * 16 + lane;
+        Q.thr[qs] = 0;
+        Q.cnt[qs] = 0;
+        Q.minpos[qs] = 0;
+      }
+      __syncwarp();
     }
 
-    const int j = lane & 3, r = lane >> 2;
-    const int own_h = j < 2 ? j : -1;                  // thread j==h of a quad owns the quad's half-h query
-    const int qi = q4 * 16 + (own_h < 0 ? 0 : own_h) * 8 + r;
-    const bool owner = own_h >= 0 && qi < a.nq;
-    const int my_own_h = owner ? own_h : -1;
-    Run2 run{-INFINITY, -INFINITY, 0, 0};
+    EpiCtx cx;
+    cx.j = lane & 3;
+    const int r = lane >> 2;
+    const int qA = q4 * 16 + r, qB = qA + 8;
+    cx.own_q = cx.j == 0 ? qA : qB;
+    cx.owner = cx.j < 2 && cx.own_q < a.nq;
+    cx.invA = __ldg(a.inv_scale + qA);
+    cx.invB = __ldg(a.inv_scale + qB);
+    cx.scaleA = 1.0f / cx.invA;      // powers of two: exact
+    cx.scaleB = 1.0f / cx.invB;
+    cx.r_begin = r_begin;
+    EpiState st;
+    st.m0 = st.m1 = -INFINITY;
+    st.c0 = st.c1 = 0;
+    st.thrA = st.thrB = -INFINITY;
+    st.cur_img = img0;
 
-    // Image ids of this lane's columns (lane, lane+32, ...) and of their right neighbours, fetched one
-    // tile AHEAD (consumed right after the load they cost a loaded-HBM latency per 32 columns).
     constexpr int NG = NT / 32;
-    int img_a[NG], img_b[NG];
-    auto fetch_imgs = [&](int t) {
-      const int64_t row0 = r_begin + (int64_t)t * NT;
-      const int valid = (int)min((int64_t)NT, r_end - row0);
+    static_assert(NG == 2 || NG == 4, "tile must be 64 or 128 rows");
+    // image-boundary bits of the next tile, fetched one tile ahead (NG + 1 words cover any alignment)
+    uint32_t wb[NG + 1];
+    auto fetch_bits = [&](int t) {
+      const uint32_t* p = a.last_bits + ((r_begin + (int64_t)t * NT) >> 5);
 #pragma unroll
-      for (int g = 0; g < NG; ++g) {
-        const int c = g * 32 + lane;
-        img_a[g] = c < valid ? a.img_of_row[row0 + c] : 0;
-        img_b[g] = c < valid ? a.img_of_row[row0 + c + 1] : 0;
-      }
+      for (int i = 0; i <= NG; ++i) wb[i] = __ldg(p + i);
     };
-    if (ntiles > 0) fetch_imgs(0);
+    if (ntiles > 0) fetch_bits(0);
     for (int t = 0; t < ntiles; ++t) {
       const uint32_t as = t & 1;
       const int64_t row0 = r_begin + (int64_t)t * NT;
-      // bit i of ends[g] set <=> row0 + 32g + i is the last row of its image (0 for columns past r_end)
+      const int sh = (int)(row0 & 31);
+      const int valid = (int)min((int64_t)NT, r_end - row0);
       uint32_t ends[NG];
-      int img_now[NG];
 #pragma unroll
       for (int g = 0; g < NG; ++g) {
-        ends[g] = __ballot_sync(0xffffffffu, img_a[g] != img_b[g]);
-        img_now[g] = img_a[g];
+        const int rem = valid - 32 * g;
+        const uint32_t keep = rem >= 32 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+        ends[g] = __funnelshift_r(wb[g], wb[g + 1], sh) & keep;
       }
-      if (t + 1 < ntiles) fetch_imgs(t + 1);
-      uint64_t gshared = 0;
-      if (owner) gshared = ld_relaxed_u64(a.g_thr + qi);
+      if (t + 1 < ntiles) fetch_bits(t + 1);
+      // refresh the thresholds: shared lower bound from the other CTAs, then the quad's register copies
+      if (cx.owner) {
+        const uint64_t gshared = ld_relaxed_u64(a.g_thr + cx.own_q);
+        if (gshared > Q.thr[cx.own_q]) Q.thr[cx.own_q] = gshared;
+      }
+      __syncwarp();
+      st.thrA = thr_to_acc(Q.thr[qA], cx.scaleA);
+      st.thrB = thr_to_acc(Q.thr[qB], cx.scaleB);
       mbar_wait(S.tmem_full + 8 * as, (t >> 1) & 1);
       tc_fence_after();
-      if (owner && gshared > Q.thr[qi]) Q.thr[qi] = gshared;
-#pragma unroll 1
-      for (int g = 0; g < NG; ++g) {
-        uint32_t em = ends[0];
-        int img_lane = img_now[0];
-#pragma unroll
-        for (int gg = 1; gg < NG; ++gg) {
-          em = (g == gg) ? ends[gg] : em;
-          img_lane = (g == gg) ? img_now[gg] : img_lane;
-        }
-        uint32_t v0[16], v1[16];
-        tmem_ld_16x256b_x4(lane_addr + Cfg::ACC_BASE + as * NT + g * 32, v0);
-        tmem_ld_16x256b_x4(lane_addr + (16u << 16) + Cfg::ACC_BASE + as * NT + g * 32, v1);
-        tmem_ld_wait();
-        const int colbase = (int)(row0 - r_begin) + g * 32;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float s00 = __uint_as_float(v0[4 * i]) + __uint_as_float(v0[4 * i + 2]);
-          const float s01 = __uint_as_float(v0[4 * i + 1]) + __uint_as_float(v0[4 * i + 3]);
-          const float s10 = __uint_as_float(v1[4 * i]) + __uint_as_float(v1[4 * i + 2]);
-          const float s11 = __uint_as_float(v1[4 * i + 1]) + __uint_as_float(v1[4 * i + 3]);
-          const uint32_t eb = (em >> (8 * i)) & 0xFFu;
-          const int c0 = colbase + 8 * i + 2 * j;
-          if (eb == 0) {          // warp-uniform fast path: no image ends inside these 8 columns
-            if (s00 > run.m0) { run.m0 = s00; run.c0 = c0; }
-            if (s01 > run.m0) { run.m0 = s01; run.c0 = c0 + 1; }
-            if (s10 > run.m1) { run.m1 = s10; run.c1 = c0; }
-            if (s11 > run.m1) { run.m1 = s11; run.c1 = c0 + 1; }
-          } else {
-            run = scan_tc_slow_group(run, after, a, eb, s00, s01, s10, s11, colbase + 8 * i, img_lane,
-                                     i | ((my_own_h + 1) << 4) | (qi << 8), r_begin);
-          }
-        }
+      const uint32_t acc = lane_addr + Cfg::ACC_BASE + as * NT;
+      const int colbase = (int)(row0 - r_begin);
+      uint32_t va0[16], va1[16], vb0[16], vb1[16];
+      tmem_ld_16x256b_x4(acc, va0);
+      tmem_ld_16x256b_x4(acc + (16u << 16), va1);
+      tmem_ld_wait_regs(va0, va1);
+      tmem_ld_16x256b_x4(acc + 32, vb0);
+      tmem_ld_16x256b_x4(acc + (16u << 16) + 32, vb1);
+      scan_tc_group(st, cx, Q, a, va0, va1, ends[0], colbase);
+      tmem_ld_wait_regs(vb0, vb1);
+      if constexpr (NG == 4) {
+        tmem_ld_16x256b_x4(acc + 64, va0);
+        tmem_ld_16x256b_x4(acc + (16u << 16) + 64, va1);
+      }
+      scan_tc_group(st, cx, Q, a, vb0, vb1, ends[1], colbase + 32);
+      if constexpr (NG == 4) {
+        tmem_ld_wait_regs(va0, va1);
+        tmem_ld_16x256b_x4(acc + 96, vb0);
+        tmem_ld_16x256b_x4(acc + (16u << 16) + 96, vb1);
+        scan_tc_group(st, cx, Q, a, va0, va1, ends[2], colbase + 64);
+        tmem_ld_wait_regs(vb0, vb1);
+        scan_tc_group(st, cx, Q, a, vb0, vb1, ends[3], colbase + 96);
       }
       tc_fence_before();
       mbar_arrive(S.tmem_empty + 8 * as);
     }
-    // ---- settle the parked candidate and publish this CTA's list of every query
-    if (owner) {
-      if (a.excl) qlist_resolve_pending(Q, a, qi, k);
+    // ---- publish this CTA's list of every query
+    __syncwarp();
+    if (cx.owner) {
+      const int qi = cx.own_q;
       const int cnt = Q.cnt[qi];
       const int64_t o = ((int64_t)qi * gridDim.x + blockIdx.x) * k;
       for (int s = 0; s < k; ++s) {
@@ -400,7 +467,9 @@ static int launch_scan_tc_t(ssw_db* db, const ScanTcArgs& a, cudaStream_t st) {
                       tc_smem_slack;
   auto kern = scan_tc_kernel<DIM, NT, NS>;
   SSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  prof_begin(db, st);      // times the scan kernel alone (not the query preparation)
   kern<<<db->scan_grid, kTcThreads, smem, st>>>(tmap, a);
+  prof_end(db, st);
   SSW_LAUNCHED();
   return SSW_OK;
 }
@@ -409,16 +478,24 @@ bool scan_tc_supported(const ssw_db* db, int k) {
   return db->dtype == SSW_F16 && (db->dim == 256 || db->dim == 512 || db->dim == 768) && k <= kTcMaxK;
 }
 
-// One pass over the database for queries [0, nq), nq <= 64.
+size_t scan_tc_workspace_bytes(int dim) { return (size_t)128 * (dim / 2) * 4 + 64 * 4; }
+
+// One pass over the database for queries [0, nq), nq <= 64.  `workspace` holds the prepared A operand
+// (scan_tc_workspace_bytes); the preparation kernel also zeroes the queries' shared thresholds.
 int launch_scan_tc(ssw_db* db, const float* d_queries, int nq, int k, const uint32_t* d_excl, uint64_t* d_list_keys,
-                   int32_t* d_list_dbidx, uint64_t* d_gthr, cudaStream_t st) {
+                   int32_t* d_list_dbidx, uint64_t* d_gthr, void* workspace, cudaStream_t st) {
+  uint32_t* a_img = static_cast<uint32_t*>(workspace);
+  float* inv_scale = reinterpret_cast<float*>(a_img + (size_t)128 * (db->dim / 2));
+  scan_tc_prep_kernel<<<128, db->dim / 2, 0, st>>>(d_queries, nq, db->dim, a_img, inv_scale, d_gthr);
+  SSW_LAUNCHED();
   ScanTcArgs a{};
-  a.q = d_queries;
+  a.a_img = a_img;
+  a.inv_scale = inv_scale;
   a.nq = nq;
   a.k = k;
   a.excl = d_excl;
   a.excl_words = db->excl_words;
-  a.img_of_row = db->d_img_of_row;
+  a.last_bits = db->d_last_bits;
   a.row_ptr = db->d_row_ptr;
   a.img_dbidx = db->d_img_dbidx;
   a.orig_row = db->d_orig_row;
@@ -427,7 +504,7 @@ int launch_scan_tc(ssw_db* db, const float* d_queries, int nq, int k, const uint
   a.list_dbidx = d_list_dbidx;
   a.g_thr = d_gthr;
   a.row_base = db->row_base;
-  // shared memory: NS stages of NT*128 B + 64 lists of k (key, dbidx) pairs (k <= 64 -> <= 48 KB)
+  // shared memory: NS stages of NT*128 B + 64 lists of k (key, image) pairs (k <= 64 -> <= 48 KB)
   switch (db->dim) {
     case 256: return launch_scan_tc_t<256, 128, 10>(db, a, st);
     case 512: return launch_scan_tc_t<512, 128, 10>(db, a, st);

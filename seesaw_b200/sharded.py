@@ -37,6 +37,16 @@ def merge_candidates_host(keys, dbidx, k):
     return out_k, out_d.astype(np.int32)
 
 
+def encode_keys(score, row):
+    """(score fp32, global row) -> uint64 keys, the host statement of make_key (csrc/ssw_common.cuh):
+    order-preserving score bits in the high word, ~row in the low word, so a larger key is a better
+    candidate (higher score, then lower row); -0.0 ties with +0.0."""
+    s = np.asarray(score, dtype=np.float32) + np.float32(0.0)
+    b = s.view(np.uint32)
+    u = np.where(b & np.uint32(0x80000000), ~b, b | np.uint32(0x80000000)).astype(np.uint64)
+    return (u << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - np.asarray(row).astype(np.uint64))
+
+
 def decode_keys(keys):
     """uint64 keys -> (score fp32, global row int64); empty slots -> (-inf, -1)."""
     keys = np.asarray(keys, dtype=np.uint64)
@@ -85,10 +95,12 @@ class ShardedPatchDatabase:
         if self.world_size == 1 and self._merge is None:
             from .engine import merge_topk_device
             return merge_topk_device(keys.unsqueeze(0), dbidx.unsqueeze(0), k)
-        all_k = torch.empty((self.world_size,) + tuple(keys.shape), dtype=keys.dtype, device=keys.device)
-        all_d = torch.empty((self.world_size,) + tuple(dbidx.shape), dtype=dbidx.dtype, device=dbidx.device)
+        w = self.world_size
+        all_k = torch.empty((w * nq, k), dtype=keys.dtype, device=keys.device)
+        all_d = torch.empty((w * nq, k), dtype=dbidx.dtype, device=dbidx.device)
         dist.all_gather_into_tensor(all_k, keys.contiguous(), group=self.group)
         dist.all_gather_into_tensor(all_d, dbidx.contiguous(), group=self.group)
+        all_k, all_d = all_k.view(w, nq, k), all_d.view(w, nq, k)
         if self._merge is not None:
             return self._merge(all_k, all_d, k)
         from .engine import merge_topk_device

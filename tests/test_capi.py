@@ -1,0 +1,67 @@
+"""CPU checks of the drop-in boundary: the shared library loads, exports every function that
+include/seesaw_b200.h declares, the ctypes table binds each of them, and — with no GPU — every
+compute entry point fails loudly instead of falling back to a CPU path."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "seesaw_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ssw_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound():
+    from seesaw_b200 import _lib
+    names = header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(_lib.lib, n), f"{n} is declared in the header but not exported by the library"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == names, "ctypes table and header disagree"
+    assert _lib.lib.ssw_version() >= 100
+
+
+def test_constants_match_header():
+    from seesaw_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "seesaw_b200.h")).read()
+    for name in ("SSW_MAX_TOPK", "SSW_MAX_BATCH", "SSW_MAX_KNN_K1"):
+        assert int(re.search(rf"#define {name} (\d+)", text).group(1)) == getattr(_lib, name)
+
+
+def test_no_cpu_fallback():
+    """Without an sm_100 device the product must raise (SSW_ERR_NO_DEVICE), never compute on the CPU."""
+    from seesaw_b200 import _lib, engine, knn_graph
+    if _lib.device_count() > 0:
+        pytest.skip("a B200 is present")
+    v = np.zeros((8, 512), np.float32)
+    with pytest.raises(_lib.SeesawB200Error) as e:
+        engine.PatchDatabase.from_arrays(v, np.arange(8))
+    assert e.value.code == 2
+    with pytest.raises(_lib.SeesawB200Error):
+        knn_graph.knn_candidates(v, 3)
+
+
+def test_argument_validation_needs_no_device():
+    from seesaw_b200 import _lib
+    h = C.c_void_p()
+    # unsupported dim / null handle are rejected before any CUDA call
+    rc = _lib.lib.ssw_db_create(C.byref(h), 0, None, 0, 1, 4, 100, None, 0)
+    assert rc == 1 and b"null" in _lib.lib.ssw_last_error()
+    assert _lib.lib.ssw_set_scan_mode(None, 0) == 1
+    assert _lib.lib.ssw_db_destroy(None) == 0
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under seesaw_b200/ may import it."""
+    pkg = os.path.join(ROOT, "seesaw_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "seesaw_oracle" not in src and "refstubs" not in src and "import oracle" not in src, fn

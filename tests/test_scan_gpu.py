@@ -235,3 +235,34 @@ def test_batched_matches_streaming_kernel(eng):
     mism = (a["dbidx"] != b["dbidx"]).sum()
     assert mism <= 4, mism      # only adjacent near-ties may swap
     db.close()
+
+
+# ------------------------------------------------------------------ K4: merge of candidate lists
+@pytest.mark.parametrize("n_lists,nq,k", [(1, 3, 50), (8, 64, 50), (148, 2, 64), (40, 3, 2048), (5, 1, 1), (300, 2, 700)])
+def test_merge_kernel_vs_host_statement(eng, n_lists, nq, k):
+    """ssw_merge_topk_device against the numpy statement of the merge (all three size regimes: survivors
+    fit the sort buffer, need the shared-memory radix select, need the global radix select)."""
+    import torch
+    from seesaw_b200 import sharded
+    rng = np.random.default_rng(n_lists * 1000 + k)
+    score = rng.standard_normal((n_lists, nq, k)).astype(np.float32)
+    score[rng.random(score.shape) < 0.3] = np.float32(0.25)            # exact score ties -> row order decides
+    rows = rng.permutation(n_lists * nq * k).reshape(n_lists, nq, k)
+    keys = sharded.encode_keys(score, rows)
+    ids = rng.integers(0, 10 ** 6, size=keys.shape).astype(np.int32)
+    empty = rng.random(keys.shape) < 0.2
+    keys[empty] = 0
+    ids[empty] = -1
+    if n_lists == 5:
+        keys[:] = 0                                                     # nothing at all
+        ids[:] = -1
+    out = eng.merge_topk_device(torch.from_numpy(keys.view(np.int64)).cuda(), torch.from_numpy(ids).cuda(), k)
+    hk, hd = sharded.merge_candidates_host(keys, ids, k)
+    gk = out["key"].cpu().numpy().view(np.uint64)
+    assert (gk == hk).all()
+    assert (out["dbidx"].cpu().numpy() == hd).all()
+    s, r = sharded.decode_keys(hk)
+    assert (out["row"].cpu().numpy() == r).all()
+    assert (out["count"].cpu().numpy() == (hk != 0).sum(axis=1)).all()
+    got = out["score"].cpu().numpy()
+    assert ((got == s) | (np.isinf(got) & np.isinf(s))).all()
