@@ -442,7 +442,7 @@ static int scan_topk_impl(ssw_db* db, const float* d_queries, int nq, int k, con
   }
   const bool use_tc = db->scan_mode == 2 || (db->scan_mode == 0 && tc_ok && nq >= 8);
   if (use_tc) {
-    if (!db->d_tc_ws) SSW_CUDA(cudaMalloc(&db->d_tc_ws, scan_tc_workspace_bytes(db->dim)));
+    if (!db->d_tc_ws) SSW_CUDA(cudaMalloc(&db->d_tc_ws, scan_tc_workspace_bytes(db->dim, db->scan_grid)));
     for (int q0 = 0; q0 < nq; q0 += SSW_MAX_BATCH) {
       const int nb = std::min(SSW_MAX_BATCH, nq - q0);
       rc = launch_scan_tc(db, d_queries + (size_t)q0 * db->dim, nb, k,

@@ -63,7 +63,7 @@ int launch_scan1(ssw_db* db, const float* d_query, int k, const uint32_t* d_excl
 int launch_score_all(ssw_db* db, const float* d_query, float* d_out, cudaStream_t st);
 // tcgen05 batched scan (K2): one pass for up to 64 queries; fp16 storage, dim 256/512/768, k <= 64
 bool scan_tc_supported(const ssw_db* db, int k);
-size_t scan_tc_workspace_bytes(int dim);
+size_t scan_tc_workspace_bytes(int dim, int grid);
 int launch_scan_tc(ssw_db* db, const float* d_queries, int nq, int k, const uint32_t* d_excl, uint64_t* d_list_keys,
                    int32_t* d_list_dbidx, uint64_t* d_gthr, void* workspace, cudaStream_t st);
 // merge kernel (K4)

@@ -44,6 +44,7 @@ struct ScanTcArgs {
   uint64_t* list_keys;       // [nq][grid][k]
   int32_t* list_dbidx;
   uint64_t* g_thr;           // [nq]
+  uint32_t* pub;             // [64][grid] best score (order-preserving bits) every CTA holds per query
   int64_t row_base;
 };
 
@@ -54,7 +55,9 @@ constexpr int kTcMaxK = 64;   // per-query list length the batched epilogue keep
 // one block per TMEM lane (128), DIM/2 threads, thread t converts elements 2t, 2t+1
 // ------------------------------------------------------------------------------------------
 __global__ void scan_tc_prep_kernel(const float* __restrict__ q, int nq, int dim, uint32_t* __restrict__ a_img,
-                                    float* __restrict__ inv_scale, uint64_t* __restrict__ g_thr) {
+                                    float* __restrict__ inv_scale, uint64_t* __restrict__ g_thr,
+                                    uint32_t* __restrict__ pub, int n_pub) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pub; i += gridDim.x * blockDim.x) pub[i] = 0u;
   const int L = blockIdx.x;                       // TMEM lane
   const int q4 = L >> 5, h = (L >> 4) & 1, r = L & 7;
   const bool is_lo = (L >> 3) & 1;
@@ -103,8 +106,10 @@ struct QShared {
   uint64_t* thr;        // [64] reject keys <= thr: max(own k-th best once full, shared lower bound)
   int32_t* cnt;         // [64]
   int32_t* minpos;      // [64]
+  uint32_t* best;       // [64] order-preserving score bits of the best candidate held (published to the other CTAs)
+  int* done;            // epilogue warps that have finished (the threshold warp leaves at 4)
 };
-__host__ __device__ constexpr size_t qshared_bytes(int k) { return (size_t)k * 64 * 12 + 64 * (8 + 4 + 4); }
+__host__ __device__ constexpr size_t qshared_bytes(int k) { return (size_t)k * 64 * 12 + 64 * (8 + 4 + 4 + 4) + 16; }
 
 __device__ __forceinline__ QShared qshared_carve(uint8_t* base, int k) {
   QShared q;
@@ -113,6 +118,8 @@ __device__ __forceinline__ QShared qshared_carve(uint8_t* base, int k) {
   q.img = reinterpret_cast<int32_t*>(q.thr + 64);
   q.cnt = q.img + (size_t)k * 64;
   q.minpos = q.cnt + 64;
+  q.best = reinterpret_cast<uint32_t*>(q.minpos + 64);
+  q.done = reinterpret_cast<int*>(q.best + 64);
   return q;
 }
 
@@ -137,6 +144,11 @@ __device__ __forceinline__ uint64_t scan_tc_offer(const QShared& Q, const ScanTc
     const uint32_t w = __ldg(a.excl + (size_t)q * a.excl_words + (img >> 5));
     if ((w >> (img & 31)) & 1u) return thr;
   }
+  if ((uint32_t)(key >> 32) > Q.best[q]) {      // a new best of this CTA: let the other CTAs see it
+    Q.best[q] = (uint32_t)(key >> 32);
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(a.pub + (size_t)q * gridDim.x + blockIdx.x),
+                 "r"((uint32_t)(key >> 32)) : "memory");
+  }
   const int cnt = Q.cnt[q];
   if (cnt < k) {
     Q.keys[cnt * 64 + q] = key;
@@ -150,7 +162,7 @@ __device__ __forceinline__ uint64_t scan_tc_offer(const QShared& Q, const ScanTc
   }
   uint64_t mk = ~0ull;
   int mp = 0;
-#pragma unroll 4
+#pragma unroll 2
   for (int s = 0; s < k; ++s) {
     const uint64_t x = Q.keys[s * 64 + q];
     if (x < mk) {
@@ -159,10 +171,10 @@ __device__ __forceinline__ uint64_t scan_tc_offer(const QShared& Q, const ScanTc
     }
   }
   Q.minpos[q] = mp;
-  const uint64_t nthr = mk > thr ? mk : thr;
-  Q.thr[q] = nthr;
+  // the threshold warp raises Q.thr concurrently: merge with an atomic max
+  const uint64_t old = atomicMax(reinterpret_cast<unsigned long long*>(Q.thr + q), (unsigned long long)mk);
   atomicMax(reinterpret_cast<unsigned long long*>(a.g_thr + q), (unsigned long long)mk);
-  return nthr;
+  return mk > old ? mk : old;
 }
 
 // Running state of one epilogue thread: partial maxima (over this thread's columns) of the two
@@ -215,51 +227,96 @@ __device__ __forceinline__ void scan_tc_boundary(EpiState& st, const EpiCtx& cx,
   ++st.cur_img;
 }
 
+// Threshold warp.  Every CTA publishes the best score it holds per query (a.pub).  Split the G CTAs into
+// NGP >= k groups (CTA c in group c mod NGP): the smallest of the group maxima is a score that at least
+// k distinct images reach, hence a valid lower bound of the final k-th best — far tighter than a single
+// CTA's own k-th best early in the scan, when almost every image would otherwise enter its CTA's list
+// (expected list updates per query and CTA drop from k*ln(n/k) to a handful).  One warp per CTA sweeps
+// the queries for the whole life of the kernel and raises the thresholds the epilogue warps read each
+// tile; it never touches the epilogue's critical path.
+__device__ __forceinline__ void scan_tc_threshold_warp(const QShared& Q, const ScanTcArgs& a, int lane) {
+  constexpr int VMAX = 6;                       // up to 192 CTAs
+  const int G = gridDim.x;
+  int ngp = 1;
+  while (ngp < a.k) ngp <<= 1;                  // k <= 64
+  const bool pooled = G >= ngp && G <= 32 * VMAX;
+  volatile int* done = Q.done;
+  while (*done < 4) {
+#pragma unroll 2
+    for (int q = 0; q < a.nq; ++q) {
+      uint32_t t = 0;
+      if (pooled) {
+        uint32_t v[VMAX];
+#pragma unroll
+        for (int m = 0; m < VMAX; ++m) {
+          const int c = lane + 32 * m;
+          v[m] = 0u;
+          if (c < G)
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v[m]) : "l"(a.pub + (size_t)q * G + c) : "memory");
+        }
+        if (ngp == 64) {                        // groups lane and lane + 32
+          const uint32_t ga = max(max(v[0], v[2]), v[4]), gb = max(max(v[1], v[3]), v[5]);
+          t = min(ga, gb);
+        } else {                                // group lane % ngp
+          t = max(max(max(v[0], v[1]), max(v[2], v[3])), max(v[4], v[5]));
+          for (int sft = 16; sft >= ngp; sft >>= 1) t = max(t, __shfl_xor_sync(0xffffffffu, t, sft));
+        }
+        t = __reduce_min_sync(0xffffffffu, t);
+      }
+      if (lane == 0) {
+        const uint64_t g = ld_relaxed_u64(a.g_thr + q);
+        const uint64_t tkey = (uint64_t)t << 32;
+        if (blockIdx.x == 0 && tkey > g) atomicMax(reinterpret_cast<unsigned long long*>(a.g_thr + q), (unsigned long long)tkey);
+        const uint64_t best = tkey > g ? tkey : g;
+        if (best != 0) atomicMax(reinterpret_cast<unsigned long long*>(Q.thr + q), (unsigned long long)best);
+      }
+    }
+    __nanosleep(2000);
+  }
+}
+
 // 32 accumulator columns starting at column `colbase`: v0 / v1 are the 16x256b loads of half 0 / 1,
 // em has bit c set when column colbase + c is the last row of its image.
 __device__ __forceinline__ void scan_tc_group(EpiState& st, const EpiCtx& cx, const QShared& Q, const ScanTcArgs& a,
                                               const uint32_t* v0, const uint32_t* v1, uint32_t em, int colbase) {
+  float sa[8], sb[8];       // query A / B at this thread's columns 8i + 2j + e  (index 2i + e)
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float s00 = __uint_as_float(v0[4 * i]) + __uint_as_float(v0[4 * i + 2]);
-    const float s01 = __uint_as_float(v0[4 * i + 1]) + __uint_as_float(v0[4 * i + 3]);
-    const float s10 = __uint_as_float(v1[4 * i]) + __uint_as_float(v1[4 * i + 2]);
-    const float s11 = __uint_as_float(v1[4 * i + 1]) + __uint_as_float(v1[4 * i + 3]);
-    const uint32_t eb = (em >> (8 * i)) & 0xFFu;
-    const int ca = colbase + 8 * i + 2 * cx.j;
-    if (eb == 0) {            // warp-uniform fast path: no image ends inside these 8 columns
-      if (s00 > st.m0) { st.m0 = s00; st.c0 = ca; }
-      if (s01 > st.m0) { st.m0 = s01; st.c0 = ca + 1; }
-      if (s10 > st.m1) { st.m1 = s10; st.c1 = ca; }
-      if (s11 > st.m1) { st.m1 = s11; st.c1 = ca + 1; }
-    } else {
-      // walk the boundaries of the group in order; this thread's columns are 2j and 2j+1
-      const int pa = 2 * cx.j, pb = pa + 1;
-      int lo = 0;
-      uint32_t e = eb;
-      do {
-        const int p = __ffs(e) - 1;
-        e &= e - 1;
-        if (pa >= lo && pa <= p) {
-          if (s00 > st.m0) { st.m0 = s00; st.c0 = ca; }
-          if (s10 > st.m1) { st.m1 = s10; st.c1 = ca; }
-        }
-        if (pb >= lo && pb <= p) {
-          if (s01 > st.m0) { st.m0 = s01; st.c0 = ca + 1; }
-          if (s11 > st.m1) { st.m1 = s11; st.c1 = ca + 1; }
-        }
-        scan_tc_boundary(st, cx, Q, a);
-        lo = p + 1;
-      } while (e);
-      if (pa >= lo) {
-        if (s00 > st.m0) { st.m0 = s00; st.c0 = ca; }
-        if (s10 > st.m1) { st.m1 = s10; st.c1 = ca; }
+    sa[2 * i] = __uint_as_float(v0[4 * i]) + __uint_as_float(v0[4 * i + 2]);
+    sa[2 * i + 1] = __uint_as_float(v0[4 * i + 1]) + __uint_as_float(v0[4 * i + 3]);
+    sb[2 * i] = __uint_as_float(v1[4 * i]) + __uint_as_float(v1[4 * i + 2]);
+    sb[2 * i + 1] = __uint_as_float(v1[4 * i + 1]) + __uint_as_float(v1[4 * i + 3]);
+  }
+  const int cb = colbase + 2 * cx.j;
+  if (em == 0) {            // warp-uniform fast path: no image ends inside these 32 columns
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (sa[2 * i + e] > st.m0) { st.m0 = sa[2 * i + e]; st.c0 = cb + 8 * i + e; }
+        if (sb[2 * i + e] > st.m1) { st.m1 = sb[2 * i + e]; st.c1 = cb + 8 * i + e; }
       }
-      if (pb >= lo) {
-        if (s01 > st.m0) { st.m0 = s01; st.c0 = ca + 1; }
-        if (s11 > st.m1) { st.m1 = s11; st.c1 = ca + 1; }
-      }
-    }
+    return;
+  }
+  // walk the image boundaries in order (warp-uniform loop); fold in this thread's columns of each segment
+  int lo = 0;
+  for (;;) {
+    const int p = em ? __ffs(em) - 1 : 31;
+    const uint32_t seg = (0xFFFFFFFFu >> (31 - p)) & (0xFFFFFFFFu << lo);   // columns lo..p
+    const uint32_t mine = seg >> (2 * cx.j);                                // bit 8i+e <-> my column 8i+2j+e
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        if ((mine >> (8 * i + e)) & 1u) {
+          if (sa[2 * i + e] > st.m0) { st.m0 = sa[2 * i + e]; st.c0 = cb + 8 * i + e; }
+          if (sb[2 * i + e] > st.m1) { st.m1 = sb[2 * i + e]; st.c1 = cb + 8 * i + e; }
+        }
+    if (em == 0) break;
+    em &= em - 1;
+    scan_tc_boundary(st, cx, Q, a);
+    lo = p + 1;
+    if (lo == 32) break;
   }
 }
 
@@ -275,8 +332,10 @@ __device__ __forceinline__ void tmem_ld_wait_regs(uint32_t* x, uint32_t* y) {
                : "memory");
 }
 
+constexpr int kScanTcThreads = kTcThreads + 32;     // + the threshold warp
+
 template <int DIM, int NT, int NS>
-__global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(kScanTcThreads, 1) scan_tc_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                  const ScanTcArgs a) {
   using Cfg = TcCfg<DIM, NT>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -284,6 +343,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
   const TcSmem S = tc_carve(smem_raw, NS, Cfg::STAGE_BYTES, &smem);
   uint8_t* after = smem + NS * Cfg::STAGE_BYTES + ((tc_bar_bytes(NS) + 15) / 16) * 16;
   const QShared Q = qshared_carve(after, a.k);
+  if (threadIdx.x < 64) {      // per-query list state (before the barrier inside tc_setup)
+    Q.thr[threadIdx.x] = 0;
+    Q.cnt[threadIdx.x] = 0;
+    Q.minpos[threadIdx.x] = 0;
+    Q.best[threadIdx.x] = 0;
+    if (threadIdx.x == 0) *Q.done = 0;
+  }
   const uint32_t tmem = tc_setup(S, NS, Cfg::TMEM_ALLOC, &tmap);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -330,6 +396,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
       if (lane == 0) tc_commit(S.tmem_full + 8 * as);
       __syncwarp();
     }
+  } else if (warp == 6) {
+    scan_tc_threshold_warp(Q, a, lane);
   } else {
     // ===== epilogue warps (warp w may touch TMEM lanes 32*(w%4) .. +31)
     const int q4 = warp & 3;
@@ -355,13 +423,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(S.a_ready);
-      if (lane < 16) {           // this warp's 16 query slots
-        const int qs = q4 * 16 + lane;
-        Q.thr[qs] = 0;
-        Q.cnt[qs] = 0;
-        Q.minpos[qs] = 0;
-      }
-      __syncwarp();
     }
 
     EpiCtx cx;
@@ -404,12 +465,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
         ends[g] = __funnelshift_r(wb[g], wb[g + 1], sh) & keep;
       }
       if (t + 1 < ntiles) fetch_bits(t + 1);
-      // refresh the thresholds: shared lower bound from the other CTAs, then the quad's register copies
-      if (cx.owner) {
-        const uint64_t gshared = ld_relaxed_u64(a.g_thr + cx.own_q);
-        if (gshared > Q.thr[cx.own_q]) Q.thr[cx.own_q] = gshared;
-      }
-      __syncwarp();
+      // the quad's register copies of the thresholds (raised by the owners and by the threshold warp)
       st.thrA = thr_to_acc(Q.thr[qA], cx.scaleA);
       st.thrB = thr_to_acc(Q.thr[qB], cx.scaleB);
       mbar_wait(S.tmem_full + 8 * as, (t >> 1) & 1);
@@ -420,28 +476,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tc_kernel(const __grid_con
       tmem_ld_16x256b_x4(acc, va0);
       tmem_ld_16x256b_x4(acc + (16u << 16), va1);
       tmem_ld_wait_regs(va0, va1);
-      tmem_ld_16x256b_x4(acc + 32, vb0);
-      tmem_ld_16x256b_x4(acc + (16u << 16) + 32, vb1);
-      scan_tc_group(st, cx, Q, a, va0, va1, ends[0], colbase);
-      tmem_ld_wait_regs(vb0, vb1);
-      if constexpr (NG == 4) {
-        tmem_ld_16x256b_x4(acc + 64, va0);
-        tmem_ld_16x256b_x4(acc + (16u << 16) + 64, va1);
-      }
-      scan_tc_group(st, cx, Q, a, vb0, vb1, ends[1], colbase + 32);
-      if constexpr (NG == 4) {
-        tmem_ld_wait_regs(va0, va1);
-        tmem_ld_16x256b_x4(acc + 96, vb0);
-        tmem_ld_16x256b_x4(acc + (16u << 16) + 96, vb1);
-        scan_tc_group(st, cx, Q, a, va0, va1, ends[2], colbase + 64);
+#pragma unroll 1
+      for (int gp = 0; gp < NG; gp += 2) {
+        uint32_t eA = ends[0], eB = ends[1];
+        if constexpr (NG == 4) {
+          eA = gp ? ends[2] : eA;
+          eB = gp ? ends[3] : eB;
+        }
+        tmem_ld_16x256b_x4(acc + 32 * (gp + 1), vb0);
+        tmem_ld_16x256b_x4(acc + (16u << 16) + 32 * (gp + 1), vb1);
+        scan_tc_group(st, cx, Q, a, va0, va1, eA, colbase + 32 * gp);
         tmem_ld_wait_regs(vb0, vb1);
-        scan_tc_group(st, cx, Q, a, vb0, vb1, ends[3], colbase + 96);
+        if (gp + 2 < NG) {
+          tmem_ld_16x256b_x4(acc + 32 * (gp + 2), va0);
+          tmem_ld_16x256b_x4(acc + (16u << 16) + 32 * (gp + 2), va1);
+        }
+        scan_tc_group(st, cx, Q, a, vb0, vb1, eB, colbase + 32 * (gp + 1));
+        if (gp + 2 < NG) tmem_ld_wait_regs(va0, va1);
       }
       tc_fence_before();
       mbar_arrive(S.tmem_empty + 8 * as);
     }
     // ---- publish this CTA's list of every query
     __syncwarp();
+    if (lane == 0) atomicAdd(Q.done, 1);
     if (cx.owner) {
       const int qi = cx.own_q;
       const int cnt = Q.cnt[qi];
@@ -468,7 +526,7 @@ static int launch_scan_tc_t(ssw_db* db, const ScanTcArgs& a, cudaStream_t st) {
   auto kern = scan_tc_kernel<DIM, NT, NS>;
   SSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prof_begin(db, st);      // times the scan kernel alone (not the query preparation)
-  kern<<<db->scan_grid, kTcThreads, smem, st>>>(tmap, a);
+  kern<<<db->scan_grid, kScanTcThreads, smem, st>>>(tmap, a);
   prof_end(db, st);
   SSW_LAUNCHED();
   return SSW_OK;
@@ -478,7 +536,7 @@ bool scan_tc_supported(const ssw_db* db, int k) {
   return db->dtype == SSW_F16 && (db->dim == 256 || db->dim == 512 || db->dim == 768) && k <= kTcMaxK;
 }
 
-size_t scan_tc_workspace_bytes(int dim) { return (size_t)128 * (dim / 2) * 4 + 64 * 4; }
+size_t scan_tc_workspace_bytes(int dim, int grid) { return (size_t)128 * (dim / 2) * 4 + 64 * 4 + (size_t)64 * grid * 4; }
 
 // One pass over the database for queries [0, nq), nq <= 64.  `workspace` holds the prepared A operand
 // (scan_tc_workspace_bytes); the preparation kernel also zeroes the queries' shared thresholds.
@@ -486,7 +544,9 @@ int launch_scan_tc(ssw_db* db, const float* d_queries, int nq, int k, const uint
                    int32_t* d_list_dbidx, uint64_t* d_gthr, void* workspace, cudaStream_t st) {
   uint32_t* a_img = static_cast<uint32_t*>(workspace);
   float* inv_scale = reinterpret_cast<float*>(a_img + (size_t)128 * (db->dim / 2));
-  scan_tc_prep_kernel<<<128, db->dim / 2, 0, st>>>(d_queries, nq, db->dim, a_img, inv_scale, d_gthr);
+  uint32_t* pub = reinterpret_cast<uint32_t*>(inv_scale + 64);
+  scan_tc_prep_kernel<<<128, db->dim / 2, 0, st>>>(d_queries, nq, db->dim, a_img, inv_scale, d_gthr, pub,
+                                                     64 * db->scan_grid);
   SSW_LAUNCHED();
   ScanTcArgs a{};
   a.a_img = a_img;
@@ -503,6 +563,7 @@ int launch_scan_tc(ssw_db* db, const float* d_queries, int nq, int k, const uint
   a.list_keys = d_list_keys;
   a.list_dbidx = d_list_dbidx;
   a.g_thr = d_gthr;
+  a.pub = pub;
   a.row_base = db->row_base;
   // shared memory: NS stages of NT*128 B + 64 lists of k (key, image) pairs (k <= 64 -> <= 48 KB)
   switch (db->dim) {
