@@ -93,7 +93,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                          "-lms", "20", "-i", str(self.gpu_index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -121,15 +121,19 @@ class ClockSampler:
             for name, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        # samples taken while the GPU was busy: the sampler runs from the first warm-up step to the end of
+        # the timed steps (idle samples before the first launch sit at a lower clock and are dropped)
+        busy = [c for c in sm if c >= 0.6 * max(sm)] if sm else []
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(busy),
+                "window": "first warm-up step .. last timed step of the HBM-resident leg"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-knn", action="store_true")
@@ -196,7 +200,9 @@ def main():
         out = sdb.scan_topk_device(dq, TOPK, d_exclude_bits=bits)
         return {k: v.cpu() for k, v in out.items() if k in ("dbidx", "score", "row", "count")}
 
-    def timed(fn, steps, profile=False):
+    def timed(fn, steps, profile=False, before=None):
+        if before is not None:
+            before()
         for _ in range(warmup):
             fn()
         barrier()
@@ -224,11 +230,10 @@ def main():
         return float(t[0]), float(t[1]), launches, kern
 
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    dev_ms, wall_ms, launches, (kern_ms, kern_n) = timed(step_resident, args.steps, profile=True)
+    dev_ms, wall_ms, launches, (kern_ms, kern_n) = timed(step_resident, args.steps, profile=True,
+                                                        before=sampler.start if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 50))
     _, e2e_wall_ms, _, _ = timed(step_e2e, e2e_steps)
 
     # parity spot check inside the bench: shard-merged result == single-call result of rank 0's view
