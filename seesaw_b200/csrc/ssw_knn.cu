@@ -27,25 +27,29 @@ struct KnnArgs {
   float* out_dist;
 };
 
+// Per-row list state in shared memory (one 16-byte record per epilogue thread), so the out-of-line
+// insert takes scalar arguments only and nothing spills to local memory.
 struct KnnRowState {
+  uint64_t maxkey;   // worst (largest) key held once the list is full
   int cnt, maxpos;
-  uint64_t maxkey;
 };
 
-// Slow path of the epilogue (rare after warm-up): offer (d, col) to the row's list of the k1
-// smallest keys.  Columns arrive in ascending order, so on a tie with the current worst entry the
-// newcomer (larger column) loses through the key compare.  Returns the new distance threshold.
-__device__ __noinline__ float knn_offer(KnnRowState& st, uint64_t* mylist, int k1, float d, int64_t col, int64_t n,
-                                        float thr) {
-  if (col >= n) return thr;      // zero-filled out-of-range columns of the last tile
+// Rare path of the epilogue: offer (d, col) to the row's list of the k1 smallest keys.  Columns arrive
+// in ascending order, so on a tie with the current worst entry the newcomer (larger column) loses
+// through the key compare.  Returns the row's distance threshold (inf until the list is full).
+__device__ __noinline__ float knn_offer(KnnRowState* st, uint64_t* mylist, int k1, float d, int64_t col, int64_t n) {
+  int cnt = st->cnt;
+  const float cur = cnt < k1 ? INFINITY : key_score(st->maxkey);
+  if (col >= n) return cur;      // zero-filled out-of-range columns of the last tile
   const uint64_t key = ((uint64_t)f32_ordered(d) << 32) | (uint32_t)col;
-  if (st.cnt < k1) {
-    mylist[st.cnt * 128] = key;
-    if (++st.cnt < k1) return thr;
-  } else if (key < st.maxkey) {
-    mylist[st.maxpos * 128] = key;
+  if (cnt < k1) {
+    mylist[cnt * 128] = key;
+    st->cnt = ++cnt;
+    if (cnt < k1) return INFINITY;
+  } else if (key < st->maxkey) {
+    mylist[st->maxpos * 128] = key;
   } else {
-    return thr;
+    return cur;
   }
   uint64_t mk = 0;
   int mp = 0;
@@ -56,9 +60,58 @@ __device__ __noinline__ float knn_offer(KnnRowState& st, uint64_t* mylist, int k
       mp = s;
     }
   }
-  st.maxkey = mk;
-  st.maxpos = mp;
+  st->maxkey = mk;
+  st->maxpos = mp;
   return key_score(mk);
+}
+
+// Dot-product value every column that can still enter the list must reach: d = fl(1 - x) <= thr holds
+// for every x >= 1 - thr, and rounding can pull in x at most one ulp of the distance (< 2^-22) below
+// that; the margin makes the cheap test conservative, the exact test on d follows in the rare path.
+__device__ __forceinline__ float knn_thr_dot(float thr) {
+  return thr == INFINITY ? -INFINITY : (1.0f - thr) - 4.8e-7f;
+}
+
+// 32 accumulator columns (dots of this thread's row with columns col0 .. col0+31).  Common case: one
+// max tree (FMNMX3) and one compare for the whole group.
+__device__ __forceinline__ void knn_group(const uint32_t* v, float& thr, float& thr_dot, KnnRowState* st,
+                                          uint64_t* mylist, int k1, int64_t col0, int64_t n) {
+  float m8[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const float a = fmaxf(fmaxf(__uint_as_float(v[8 * s]), __uint_as_float(v[8 * s + 1])), __uint_as_float(v[8 * s + 2]));
+    const float b = fmaxf(fmaxf(__uint_as_float(v[8 * s + 3]), __uint_as_float(v[8 * s + 4])), __uint_as_float(v[8 * s + 5]));
+    m8[s] = fmaxf(fmaxf(a, b), fmaxf(__uint_as_float(v[8 * s + 6]), __uint_as_float(v[8 * s + 7])));
+  }
+  const float mx = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+  if (mx >= thr_dot) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      if (m8[s] >= thr_dot) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float x = __uint_as_float(v[8 * s + e]);
+          if (x >= thr_dot) {
+            const float d = __fsub_rn(1.0f, x);
+            if (d <= thr) {
+              thr = knn_offer(st, mylist, k1, d, col0 + 8 * s + e, n);
+              thr_dot = knn_thr_dot(thr);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void tmem_ld_wait_regs32(uint32_t* x) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]),
+                 "+r"(x[8]), "+r"(x[9]), "+r"(x[10]), "+r"(x[11]), "+r"(x[12]), "+r"(x[13]), "+r"(x[14]), "+r"(x[15]),
+                 "+r"(x[16]), "+r"(x[17]), "+r"(x[18]), "+r"(x[19]), "+r"(x[20]), "+r"(x[21]), "+r"(x[22]), "+r"(x[23]),
+                 "+r"(x[24]), "+r"(x[25]), "+r"(x[26]), "+r"(x[27]), "+r"(x[28]), "+r"(x[29]), "+r"(x[30]), "+r"(x[31])
+               :
+               : "memory");
 }
 
 template <int DIM, int NT, int NS>
@@ -67,8 +120,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_kernel(const __grid_constan
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem;
   const TcSmem S = tc_carve(smem_raw, NS, Cfg::STAGE_BYTES, &smem);
-  // per-row candidate lists after the barrier block: keys[k1][128]
+  // after the barrier block: per-row candidate lists keys[k1][128], then the 128 row-state records
   uint64_t* lists = reinterpret_cast<uint64_t*>(smem + NS * Cfg::STAGE_BYTES + ((tc_bar_bytes(NS) + 15) / 16) * 16);
+  KnnRowState* states = reinterpret_cast<KnnRowState*>(lists + (size_t)a.k1 * 128);
   const uint32_t tmem = tc_setup(S, NS, Cfg::TMEM_ALLOC, &tmap);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -126,12 +180,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_kernel(const __grid_constan
     const int lrow = q4 * 32 + lane;                     // TMEM lane == row within the block
     const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
     uint64_t* mylist = lists + lrow;                      // slot s at mylist[s * 128]
+    KnnRowState* st = states + lrow;
     const int k1 = a.k1;
     uint32_t it = 0;
     for (int64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
       const int64_t row = a.row_begin + b * 128 + lrow;
       const bool row_ok = row < a.row_end;
-      // ---- A operand: this thread's row of V into its TMEM lane (fp16 pairs are already packed)
+      // ---- A operand: this thread's row of V into its TMEM lane (fp16 pairs are already packed).
+      // The previous block's MMAs have all completed: its last accumulator was drained below.
       {
         const uint4* src = reinterpret_cast<const uint4*>(a.v + (row_ok ? row : 0) * (int64_t)DIM);
 #pragma unroll 1
@@ -151,28 +207,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_kernel(const __grid_constan
         tc_fence_before();
         mbar_arrive(S.a_ready);
       }
-      KnnRowState stt{0, 0, ~0ull};
-      float thr = INFINITY;
+      st->cnt = 0;
+      st->maxpos = 0;
+      st->maxkey = ~0ull;
+      float thr = INFINITY, thr_dot = -INFINITY;
       for (int t = 0; t < ntiles; ++t, ++it) {
         const uint32_t as = it & 1;
         mbar_wait(S.tmem_full + 8 * as, (it >> 1) & 1);
         tc_fence_after();
         const int64_t col0 = (int64_t)t * NT;
+        const uint32_t acc = lane_addr + Cfg::ACC_BASE + as * NT;
+        uint32_t va[32], vb[32];
+        tmem_ld32(acc, va);
+        tmem_ld_wait_regs32(va);
 #pragma unroll 1
-        for (int c0 = 0; c0 < NT; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(lane_addr + Cfg::ACC_BASE + as * NT + c0, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float d = __fsub_rn(1.0f, __uint_as_float(v[i]));
-            if (d <= thr) thr = knn_offer(stt, mylist, k1, d, col0 + c0 + i, a.n, thr);
-          }
+        for (int c0 = 0; c0 < NT; c0 += 64) {
+          tmem_ld32(acc + c0 + 32, vb);
+          knn_group(va, thr, thr_dot, st, mylist, k1, col0 + c0, a.n);
+          tmem_ld_wait_regs32(vb);
+          if (c0 + 64 < NT) tmem_ld32(acc + c0 + 64, va);
+          knn_group(vb, thr, thr_dot, st, mylist, k1, col0 + c0 + 32, a.n);
+          if (c0 + 64 < NT) tmem_ld_wait_regs32(va);
         }
         tc_fence_before();
         mbar_arrive(S.tmem_empty + 8 * as);
       }
-      const int cnt = stt.cnt;
+      const int cnt = st->cnt;
       // ---- sort the row's k1 candidates ascending by (d, col) and write them out
       if (row_ok) {
         for (int i = 1; i < cnt; ++i) {
@@ -230,7 +290,7 @@ int make_tmap_f16_rows(CUtensorMap* out, const void* base, int64_t n_rows, int d
 template <int DIM, int NT>
 static int launch_knn_t(int sm_count, const KnnArgs& a, cudaStream_t st) {
   using Cfg = TcCfg<DIM, NT>;
-  const size_t list_bytes = (size_t)a.k1 * 128 * 8;
+  const size_t list_bytes = (size_t)a.k1 * 128 * 8 + 128 * sizeof(KnnRowState);
   CUtensorMap tmap;
   int rc = make_tmap_f16_rows(&tmap, a.v, a.n, DIM, NT);
   if (rc) return rc;
