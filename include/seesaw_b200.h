@@ -41,6 +41,7 @@ enum ssw_status {
 #define SSW_MAX_TOPK 2048      /* largest k of the fused scan epilogue                        */
 #define SSW_MAX_BATCH 64       /* queries per tensor-core batched pass (larger nq is looped)  */
 #define SSW_MAX_KNN_K1 64      /* largest n_neighbors+1 of the fused kNN epilogue             */
+#define SSW_MAX_WORLD 8        /* GPUs of one NVSwitch box a database can be sharded over     */
 
 const char* ssw_last_error(void);
 int ssw_version(void);
@@ -102,6 +103,27 @@ int ssw_exclude_build_device(ssw_db* db, const int32_t* d_exclude_dbidx, const i
 int ssw_merge_topk_device(int device, const uint64_t* d_keys, const int32_t* d_dbidx, int n_lists,
                           int nq, int k, uint64_t* d_out_key, int32_t* d_out_dbidx,
                           float* d_out_score, int64_t* d_out_row, int32_t* d_out_count, void* stream);
+
+/* ---- row-sharded database: one process per GPU ------------------------------------------
+ * The reference has no multi-device path: images are split into contiguous ranges,
+ * one shard (ssw_db with global_row_base) per GPU.  ssw_scan_topk_sharded_device scans this rank's
+ * shard and finishes the step in ONE kernel: merge of the shard's lists, stores of the shard's top-k
+ * into every rank's exchange buffer over NVLink, flag hand-shake, merge of the world's lists — every
+ * rank ends with the same global top-k (outputs as ssw_merge_topk_device).  All ranks must call it
+ * with the same nq, k, capacities and `epoch` (non-zero, +1 per call).  nq <= min(nq_cap, #SMs).
+ * Exchange buffers: ssw_xchg_create allocates and zeroes this rank's buffer and returns its 64-byte
+ * CUDA IPC handle; the host layer exchanges handles (any transport) and maps each peer's buffer with
+ * ssw_xchg_open; peer_bufs[r] is rank r's buffer as seen from this device (peer_bufs[rank] = own). */
+int ssw_xchg_create(int device, int world, int nq_cap, int k_cap, void** d_buf, void* ipc_handle_out,
+                    int64_t* bytes);
+int ssw_xchg_open(int device, const void* ipc_handle, void** d_peer);
+int ssw_xchg_close(int device, void* d_peer);
+int ssw_xchg_destroy(int device, void* d_buf);
+int ssw_scan_topk_sharded_device(ssw_db* db, const float* d_queries, int nq, int k,
+                                 const uint32_t* d_exclude_bits, void* const* peer_bufs, int world, int rank,
+                                 int nq_cap, int k_cap, uint32_t epoch, uint64_t* d_out_key,
+                                 int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row,
+                                 int32_t* d_out_count, void* stream);
 
 /* Kernel selection for ssw_scan_topk*: 0 = auto (streaming SIMT kernel for nq < 8 queries,
  * tcgen05 batched kernel otherwise), 1 = force streaming kernel, 2 = force tcgen05 kernel. */

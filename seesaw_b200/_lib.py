@@ -14,6 +14,7 @@ SSW_F32, SSW_F16 = 0, 1
 SSW_MAX_TOPK = 2048
 SSW_MAX_BATCH = 64
 SSW_MAX_KNN_K1 = 64
+SSW_MAX_WORLD = 8
 
 
 class SeesawB200Error(RuntimeError):
@@ -50,6 +51,12 @@ SIGNATURES = {
     "ssw_exclude_words": (C.c_int, [_p, _i64p]),
     "ssw_exclude_build_device": (C.c_int, [_p, _p, _p, C.c_int, C.c_int64, _p, _p]),
     "ssw_merge_topk_device": (C.c_int, [C.c_int, _p, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p]),
+    "ssw_xchg_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_p), _p, _i64p]),
+    "ssw_xchg_open": (C.c_int, [C.c_int, _p, C.POINTER(_p)]),
+    "ssw_xchg_close": (C.c_int, [C.c_int, _p]),
+    "ssw_xchg_destroy": (C.c_int, [C.c_int, _p]),
+    "ssw_scan_topk_sharded_device": (C.c_int, [_p, _p, C.c_int, C.c_int, _p, C.POINTER(_p), C.c_int, C.c_int, C.c_int,
+                                               C.c_int, C.c_uint32, _p, _p, _p, _p, _p, _p]),
     "ssw_set_scan_mode": (C.c_int, [_p, C.c_int]),
     "ssw_score_all": (C.c_int, [_p, _p, _p]),
     "ssw_score_all_device": (C.c_int, [_p, _p, _p, _p]),

@@ -429,9 +429,15 @@ int ssw_exclude_build_device(ssw_db* db, const int32_t* d_exclude_dbidx, const i
   return launch_exclude_build(db, d_exclude_dbidx, d_exclude_offsets, nq, d_bits_out, (cudaStream_t)stream);
 }
 
+struct XchgCtx {
+  void* const* peers;
+  int world, rank, nq_cap, k_cap;
+  uint32_t epoch;
+};
+
 static int scan_topk_impl(ssw_db* db, const float* d_queries, int nq, int k, const uint32_t* d_exclude_bits,
                           uint64_t* d_out_key, int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row,
-                          int32_t* d_out_count, cudaStream_t st) {
+                          int32_t* d_out_count, cudaStream_t st, const XchgCtx* xc = nullptr) {
   const int lists = db->scan_grid;
   int rc = ensure_lists(db, nq, lists, k);
   if (rc) return rc;
@@ -463,8 +469,73 @@ static int scan_topk_impl(ssw_db* db, const float* d_queries, int nq, int k, con
       if (rc) return rc;
     }
   }
+  if (xc)
+    return launch_exchange_merge(db->d_list_keys, db->d_list_dbidx, lists, k, (int64_t)lists * k, nq, k, db->d_gthr,
+                                 xc->peers, xc->world, xc->rank, xc->nq_cap, xc->k_cap, xc->epoch, d_out_key,
+                                 d_out_dbidx, d_out_score, d_out_row, d_out_count, st);
   return launch_merge(db->d_list_keys, db->d_list_dbidx, lists, k, (int64_t)lists * k, nq, k, db->d_gthr,
                       d_out_key, d_out_dbidx, d_out_score, d_out_row, d_out_count, st);
+}
+
+int ssw_scan_topk_sharded_device(ssw_db* db, const float* d_queries, int nq, int k, const uint32_t* d_exclude_bits,
+                                 void* const* peer_bufs, int world, int rank, int nq_cap, int k_cap, uint32_t epoch,
+                                 uint64_t* d_out_key, int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row,
+                                 int32_t* d_out_count, void* stream) {
+  SSW_REQUIRE(db != nullptr && d_queries != nullptr && peer_bufs != nullptr, "null argument");
+  SSW_REQUIRE(world >= 1 && world <= SSW_MAX_WORLD && rank >= 0 && rank < world, "bad world/rank");
+  SSW_REQUIRE(nq > 0 && nq <= nq_cap && nq <= db->sm_count, "nq must be in [1, min(nq_cap, SM count)]");
+  SSW_REQUIRE(k > 0 && k <= k_cap && k <= SSW_MAX_TOPK, "k must be in [1, min(k_cap, SSW_MAX_TOPK)]");
+  SSW_REQUIRE(epoch != 0, "epoch must be non-zero and increase by one per call");
+  for (int i = 0; i < world; ++i) SSW_REQUIRE(peer_bufs[i] != nullptr, "peer buffer is null");
+  SSW_CUDA(cudaSetDevice(db->device));
+  XchgCtx xc{peer_bufs, world, rank, nq_cap, k_cap, epoch};
+  return scan_topk_impl(db, d_queries, nq, k, d_exclude_bits, d_out_key, d_out_dbidx, d_out_score, d_out_row,
+                        d_out_count, (cudaStream_t)stream, &xc);
+}
+
+int ssw_xchg_create(int device, int world, int nq_cap, int k_cap, void** d_buf, void* ipc_handle_out, int64_t* bytes) {
+  SSW_REQUIRE(d_buf != nullptr, "d_buf is null");
+  SSW_REQUIRE(world >= 1 && world <= SSW_MAX_WORLD && nq_cap >= 1 && k_cap >= 1 && k_cap <= SSW_MAX_TOPK, "bad capacity");
+  int rc = ensure_device(device, nullptr);
+  if (rc) return rc;
+  const size_t n = xchg_bytes(world, nq_cap, k_cap);
+  SSW_CUDA(cudaMalloc(d_buf, n));
+  SSW_CUDA(cudaMemset(*d_buf, 0, n));
+  SSW_CUDA(cudaDeviceSynchronize());
+  if (ipc_handle_out) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    SSW_CUDA(cudaIpcGetMemHandle(&h, *d_buf));
+    memcpy(ipc_handle_out, &h, sizeof(h));
+  }
+  if (bytes) *bytes = (int64_t)n;
+  return SSW_OK;
+}
+
+int ssw_xchg_open(int device, const void* ipc_handle, void** d_peer) {
+  SSW_REQUIRE(ipc_handle != nullptr && d_peer != nullptr, "null argument");
+  int rc = ensure_device(device, nullptr);
+  if (rc) return rc;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle, sizeof(h));
+  SSW_CUDA(cudaIpcOpenMemHandle(d_peer, h, cudaIpcMemLazyEnablePeerAccess));
+  return SSW_OK;
+}
+
+int ssw_xchg_close(int device, void* d_peer) {
+  if (!d_peer) return SSW_OK;
+  int rc = ensure_device(device, nullptr);
+  if (rc) return rc;
+  SSW_CUDA(cudaIpcCloseMemHandle(d_peer));
+  return SSW_OK;
+}
+
+int ssw_xchg_destroy(int device, void* d_buf) {
+  if (!d_buf) return SSW_OK;
+  int rc = ensure_device(device, nullptr);
+  if (rc) return rc;
+  SSW_CUDA(cudaFree(d_buf));
+  return SSW_OK;
 }
 
 int ssw_scan_topk_device(ssw_db* db, const float* d_queries, int nq, int k, const uint32_t* d_exclude_bits,

@@ -71,6 +71,12 @@ int launch_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_lists, in
                  int64_t query_stride, int nq, int k, const uint64_t* d_thr, uint64_t* d_out_key,
                  int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row, int32_t* d_out_count,
                  cudaStream_t st);
+// fused shard merge + peer exchange + world merge (multi-GPU); peers[] are peer-mapped exchange buffers
+size_t xchg_bytes(int world, int nq_cap, int k_cap);
+int launch_exchange_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_lists, int64_t list_stride,
+                          int64_t query_stride, int nq, int k, const uint64_t* d_thr, void* const* peers, int world,
+                          int rank, int nq_cap, int k_cap, uint32_t epoch, uint64_t* d_out_key, int32_t* d_out_dbidx,
+                          float* d_out_score, int64_t* d_out_row, int32_t* d_out_count, cudaStream_t st);
 int launch_exclude_build(ssw_db* db, const int32_t* d_ids, const int64_t* d_offsets, int nq, uint32_t* d_bits,
                          cudaStream_t st);
 int launch_synth(void* d_out, int dtype, int64_t n_rows, int dim, int64_t global_row0, uint64_t seed, int kind,

@@ -487,117 +487,123 @@ __device__ __forceinline__ void merge_pick_bin(const int* hist, int d, uint64_t*
   }
 }
 
-__global__ void __launch_bounds__(kMergeThreads, 1) merge_topk_kernel(const MergeArgs a) {
-  extern __shared__ __align__(16) uint8_t msmem[];
-  uint64_t* sk = reinterpret_cast<uint64_t*>(msmem);                 // [kMergeCap] survivors
-  uint64_t* ok = sk + kMergeCap;                                     // [kMergeOut] selected top-k
-  int32_t* sd = reinterpret_cast<int32_t*>(ok + kMergeOut);          // [kMergeCap]
-  int32_t* od = sd + kMergeCap;                                      // [kMergeOut]
-  __shared__ int s_cnt;
-  __shared__ int s_hist[256];
-  __shared__ uint64_t s_prefix;
-  __shared__ int s_remaining;
+// Scratch of one merge block (dynamic shared memory + a few words of static state).
+struct MergeSmem {
+  uint64_t* sk;   // [kMergeCap] survivors
+  int32_t* sd;
+  uint64_t* ok;   // [kMergeOut] selected, then sorted, top-k
+  int32_t* od;
+  int* cnt;
+  int* hist;      // [256]
+  uint64_t* prefix;
+  int* remaining;
+};
 
-  const int q = blockIdx.x, tid = threadIdx.x;
-  const uint32_t k = (uint32_t)a.k;
-  const uint32_t total = (uint32_t)a.n_lists * k;
-  const uint64_t* kq = a.keys + (int64_t)q * a.query_stride;
-  const int32_t* dq = a.dbidx + (int64_t)q * a.query_stride;
-  uint64_t thr = a.thr ? a.thr[q] : 0ull;
+// Candidate lists (n_lists x k, list l at keys + l*list_stride) -> the entries with key >= thr gathered in
+// shared memory; returns their number (<= kMergeCap).  When more survive than fit, the exact k-th largest
+// key is found by radix select over the lists in global memory and only keys >= it are gathered (exactly k:
+// every key embeds a distinct row).  `cg`: read through L2 (lists written by a peer GPU).
+template <bool CG>
+__device__ __forceinline__ int merge_gather(const MergeSmem& M, const uint64_t* kq, const int32_t* dq, int n_lists,
+                                            int64_t list_stride, uint32_t k, uint64_t thr) {
+  const int tid = threadIdx.x;
+  const uint32_t total = (uint32_t)n_lists * k;
   if (thr == 0) thr = 1;   // key 0 == empty slot
-
+  auto ldk = [&](int64_t off) { return CG ? __ldcg(kq + off) : kq[off]; };
+  auto ldd = [&](int64_t off) { return CG ? __ldcg(dq + off) : dq[off]; };
   auto gather = [&](uint64_t lo) {
-    if (tid == 0) s_cnt = 0;
+    if (tid == 0) *M.cnt = 0;
     __syncthreads();
     for (uint32_t e = tid; e < total; e += kMergeThreads) {
-      const int64_t off = (int64_t)(e / k) * a.list_stride + (e % k);
-      const uint64_t key = kq[off];
+      const int64_t off = (int64_t)(e / k) * list_stride + (e % k);
+      const uint64_t key = ldk(off);
       if (key >= lo) {
-        const int p = atomicAdd(&s_cnt, 1);
+        const int p = atomicAdd(M.cnt, 1);
         if (p < kMergeCap) {
-          sk[p] = key;
-          sd[p] = dq[off];
+          M.sk[p] = key;
+          M.sd[p] = ldd(off);
         }
       }
     }
     __syncthreads();
-    return s_cnt;
+    return *M.cnt;
   };
-
   int n = gather(thr);
   if (n > kMergeCap) {
-    // Too many survivors for shared memory: exact k-th largest key by radix select over the global
-    // lists, then gather the >= T set (exactly k keys: every key embeds a distinct row).
     if (tid == 0) {
-      s_prefix = 0;
-      s_remaining = a.k;
+      *M.prefix = 0;
+      *M.remaining = (int)k;
     }
     for (int d = 7; d >= 0; --d) {
-      for (int i = tid; i < 256; i += kMergeThreads) s_hist[i] = 0;
+      for (int i = tid; i < 256; i += kMergeThreads) M.hist[i] = 0;
       __syncthreads();
-      const uint64_t prefix = s_prefix;
+      const uint64_t prefix = *M.prefix;
       for (uint32_t e = tid; e < total; e += kMergeThreads) {
-        const int64_t off = (int64_t)(e / k) * a.list_stride + (e % k);
-        const uint64_t key = kq[off];
+        const int64_t off = (int64_t)(e / k) * list_stride + (e % k);
+        const uint64_t key = ldk(off);
         if (key < thr) continue;
         const bool match = (d == 7) || ((key >> (8 * (d + 1))) == (prefix >> (8 * (d + 1))));
-        if (match) atomicAdd(&s_hist[(int)((key >> (8 * d)) & 255)], 1);
+        if (match) atomicAdd(&M.hist[(int)((key >> (8 * d)) & 255)], 1);
       }
       __syncthreads();
-      merge_pick_bin(s_hist, d, &s_prefix, &s_remaining);
+      merge_pick_bin(M.hist, d, M.prefix, M.remaining);
       __syncthreads();
     }
-    n = gather(s_prefix);
+    n = gather(*M.prefix);
   }
-  n = min(n, kMergeCap);
-  // ---- select the top min(n, k) survivors into (ok, od)
+  return min(n, kMergeCap);
+}
+
+// The n gathered survivors -> their best min(n, k), sorted best-first in (ok, od); returns that count.
+__device__ __forceinline__ int merge_select_sort(const MergeSmem& M, int n, int k) {
+  const int tid = threadIdx.x;
   int m;
-  if (n <= a.k) {
+  if (n <= k) {
     m = n;
     for (int i = tid; i < n; i += kMergeThreads) {
-      ok[i] = sk[i];
-      od[i] = sd[i];
+      M.ok[i] = M.sk[i];
+      M.od[i] = M.sd[i];
     }
     __syncthreads();
   } else {
     if (tid == 0) {
-      s_prefix = 0;
-      s_remaining = a.k;
+      *M.prefix = 0;
+      *M.remaining = k;
     }
     for (int d = 7; d >= 0; --d) {
-      for (int i = tid; i < 256; i += kMergeThreads) s_hist[i] = 0;
+      for (int i = tid; i < 256; i += kMergeThreads) M.hist[i] = 0;
       __syncthreads();
-      const uint64_t prefix = s_prefix;
+      const uint64_t prefix = *M.prefix;
       for (int i = tid; i < n; i += kMergeThreads) {
-        const uint64_t key = sk[i];
+        const uint64_t key = M.sk[i];
         const bool match = (d == 7) || ((key >> (8 * (d + 1))) == (prefix >> (8 * (d + 1))));
-        if (match) atomicAdd(&s_hist[(int)((key >> (8 * d)) & 255)], 1);
+        if (match) atomicAdd(&M.hist[(int)((key >> (8 * d)) & 255)], 1);
       }
       __syncthreads();
-      merge_pick_bin(s_hist, d, &s_prefix, &s_remaining);
+      merge_pick_bin(M.hist, d, M.prefix, M.remaining);
       __syncthreads();
     }
-    const uint64_t T = s_prefix;     // the k-th largest key
-    if (tid == 0) s_cnt = 0;
+    const uint64_t T = *M.prefix;     // the k-th largest key
+    if (tid == 0) *M.cnt = 0;
     __syncthreads();
     for (int i = tid; i < n; i += kMergeThreads) {
-      const uint64_t key = sk[i];
+      const uint64_t key = M.sk[i];
       if (key >= T) {
-        const int p = atomicAdd(&s_cnt, 1);
+        const int p = atomicAdd(M.cnt, 1);
         if (p < kMergeOut) {
-          ok[p] = key;
-          od[p] = sd[i];
+          M.ok[p] = key;
+          M.od[p] = M.sd[i];
         }
       }
     }
     __syncthreads();
-    m = min(s_cnt, a.k);
+    m = min(*M.cnt, k);
   }
   int P = 1;
   while (P < m) P <<= 1;
   for (int i = m + tid; i < P; i += kMergeThreads) {
-    ok[i] = 0;
-    od[i] = -1;
+    M.ok[i] = 0;
+    M.od[i] = -1;
   }
   __syncthreads();
   // bitonic sort, descending (P <= 2048)
@@ -607,29 +613,56 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_topk_kernel(const Merg
         const int lo = ((i & ~(stride - 1)) << 1) | (i & (stride - 1));
         const int hi = lo + stride;
         const bool desc = ((lo & size) == 0);
-        const uint64_t x = ok[lo], y = ok[hi];
+        const uint64_t x = M.ok[lo], y = M.ok[hi];
         if ((x < y) == desc) {
-          ok[lo] = y;
-          ok[hi] = x;
-          const int32_t t = od[lo];
-          od[lo] = od[hi];
-          od[hi] = t;
+          M.ok[lo] = y;
+          M.ok[hi] = x;
+          const int32_t t = M.od[lo];
+          M.od[lo] = M.od[hi];
+          M.od[hi] = t;
         }
       }
       __syncthreads();
     }
   }
-  const int cnt = m;
+  return m;
+}
+
+__device__ __forceinline__ void merge_write(const MergeSmem& M, const MergeArgs& a, int q, int cnt) {
+  const int tid = threadIdx.x;
   for (int i = tid; i < a.k; i += kMergeThreads) {
     const bool valid = i < cnt;
-    const uint64_t key = valid ? ok[i] : 0ull;
+    const uint64_t key = valid ? M.ok[i] : 0ull;
     const int64_t o = (int64_t)q * a.k + i;
     if (a.out_key) a.out_key[o] = key;
-    if (a.out_dbidx) a.out_dbidx[o] = valid ? od[i] : -1;
+    if (a.out_dbidx) a.out_dbidx[o] = valid ? M.od[i] : -1;
     if (a.out_score) a.out_score[o] = valid ? key_score(key) : -INFINITY;
     if (a.out_row) a.out_row[o] = valid ? (int64_t)key_row(key) : -1;
   }
   if (tid == 0 && a.out_count) a.out_count[q] = cnt;
+}
+
+#define SSW_MERGE_SMEM(M)                                                                   \
+  extern __shared__ __align__(16) uint8_t msmem[];                                          \
+  __shared__ int s_cnt, s_remaining, s_hist[256];                                           \
+  __shared__ uint64_t s_prefix;                                                             \
+  MergeSmem M;                                                                              \
+  M.sk = reinterpret_cast<uint64_t*>(msmem);                                                \
+  M.ok = M.sk + kMergeCap;                                                                  \
+  M.sd = reinterpret_cast<int32_t*>(M.ok + kMergeOut);                                      \
+  M.od = M.sd + kMergeCap;                                                                  \
+  M.cnt = &s_cnt;                                                                           \
+  M.hist = s_hist;                                                                          \
+  M.prefix = &s_prefix;                                                                     \
+  M.remaining = &s_remaining
+
+__global__ void __launch_bounds__(kMergeThreads, 1) merge_topk_kernel(const MergeArgs a) {
+  SSW_MERGE_SMEM(M);
+  const int q = blockIdx.x;
+  const int n = merge_gather<false>(M, a.keys + (int64_t)q * a.query_stride, a.dbidx + (int64_t)q * a.query_stride,
+                                    a.n_lists, a.list_stride, (uint32_t)a.k, a.thr ? a.thr[q] : 0ull);
+  const int m = merge_select_sort(M, n, a.k);
+  merge_write(M, a, q, m);
 }
 
 int launch_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_lists, int64_t list_stride,
@@ -641,6 +674,97 @@ int launch_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_lists, in
   const size_t smem = (size_t)(kMergeCap + kMergeOut) * 12;
   SSW_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   merge_topk_kernel<<<nq, kMergeThreads, smem, st>>>(a);
+  SSW_LAUNCHED();
+  return SSW_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// K4x: the multi-GPU step in ONE kernel — merge this shard's per-CTA lists, store the shard's top-k
+// into every peer's exchange buffer over NVLink (peer-mapped pointers), signal, wait for the peers'
+// signals, merge the world's lists.  One block per query; block q of a rank depends only on block q
+// of the other ranks, and nq <= 148 blocks are all co-resident, so the spin-wait cannot deadlock.
+// Exchange buffer of a rank (identical layout everywhere; two parities so a fast rank's next step
+// never overwrites what a slow rank still reads):
+//   keys  [2][world][nq_cap][k_cap] u64 | dbidx [2][world][nq_cap][k_cap] i32 | flags [2][world][nq_cap] u32
+// ------------------------------------------------------------------------------------------
+struct XchgArgs {
+  MergeArgs m;                 // local lists in, final outputs out
+  void* peers[8];              // exchange buffer of every rank, as mapped on this device
+  int world, rank, nq_cap, k_cap;
+  uint32_t epoch;              // strictly increasing per call, same on all ranks
+};
+
+__host__ __device__ inline size_t xchg_keys_bytes(int world, int nq_cap, int k_cap) { return (size_t)2 * world * nq_cap * k_cap * 8; }
+__host__ __device__ inline size_t xchg_dbidx_bytes(int world, int nq_cap, int k_cap) { return (size_t)2 * world * nq_cap * k_cap * 4; }
+size_t xchg_bytes(int world, int nq_cap, int k_cap) {
+  return xchg_keys_bytes(world, nq_cap, k_cap) + xchg_dbidx_bytes(world, nq_cap, k_cap) + (size_t)2 * world * nq_cap * 4;
+}
+
+__global__ void __launch_bounds__(kMergeThreads, 1) exchange_merge_kernel(const XchgArgs x) {
+  SSW_MERGE_SMEM(M);
+  const MergeArgs& a = x.m;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const int par = (int)(x.epoch & 1u);
+  // ---- 1. this shard's top-k
+  int n = merge_gather<false>(M, a.keys + (int64_t)q * a.query_stride, a.dbidx + (int64_t)q * a.query_stride,
+                              a.n_lists, a.list_stride, (uint32_t)a.k, a.thr ? a.thr[q] : 0ull);
+  int m = merge_select_sort(M, n, a.k);
+  // ---- 2. store it into slot `rank` of every rank's buffer (own included), then raise the flags
+  const size_t slot = (((size_t)par * x.world + x.rank) * x.nq_cap + q);
+  for (int p = 0; p < x.world; ++p) {
+    uint8_t* base = static_cast<uint8_t*>(x.peers[p]);
+    uint64_t* pk = reinterpret_cast<uint64_t*>(base) + slot * x.k_cap;
+    int32_t* pd = reinterpret_cast<int32_t*>(base + xchg_keys_bytes(x.world, x.nq_cap, x.k_cap)) + slot * x.k_cap;
+    for (int i = tid; i < a.k; i += kMergeThreads) {
+      pk[i] = i < m ? M.ok[i] : 0ull;
+      pd[i] = i < m ? M.od[i] : -1;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < x.world) {
+    uint8_t* base = static_cast<uint8_t*>(x.peers[tid]);
+    uint32_t* flag = reinterpret_cast<uint32_t*>(base + xchg_keys_bytes(x.world, x.nq_cap, x.k_cap) +
+                                                 xchg_dbidx_bytes(x.world, x.nq_cap, x.k_cap)) + slot;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(x.epoch) : "memory");
+  }
+  // ---- 3. wait until every rank's slot of THIS rank's buffer carries this epoch
+  uint8_t* mine = static_cast<uint8_t*>(x.peers[x.rank]);
+  if (tid < x.world) {
+    const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine + xchg_keys_bytes(x.world, x.nq_cap, x.k_cap) +
+                                                             xchg_dbidx_bytes(x.world, x.nq_cap, x.k_cap)) +
+                           (((size_t)par * x.world + tid) * x.nq_cap + q);
+    uint32_t v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    } while (v != x.epoch);
+  }
+  __syncthreads();
+  // ---- 4. merge the world's lists (read through L2: they were written by other GPUs)
+  const size_t q0 = ((size_t)par * x.world) * x.nq_cap + q;
+  const uint64_t* wk = reinterpret_cast<const uint64_t*>(mine) + q0 * x.k_cap;
+  const int32_t* wd = reinterpret_cast<const int32_t*>(mine + xchg_keys_bytes(x.world, x.nq_cap, x.k_cap)) + q0 * x.k_cap;
+  n = merge_gather<true>(M, wk, wd, x.world, (int64_t)x.nq_cap * x.k_cap, (uint32_t)a.k, 0ull);
+  m = merge_select_sort(M, n, a.k);
+  merge_write(M, a, q, m);
+}
+
+int launch_exchange_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_lists, int64_t list_stride,
+                          int64_t query_stride, int nq, int k, const uint64_t* d_thr, void* const* peers, int world,
+                          int rank, int nq_cap, int k_cap, uint32_t epoch, uint64_t* d_out_key, int32_t* d_out_dbidx,
+                          float* d_out_score, int64_t* d_out_row, int32_t* d_out_count, cudaStream_t st) {
+  XchgArgs x{};
+  x.m = MergeArgs{d_keys, d_dbidx, n_lists, list_stride, query_stride, k, d_thr,
+                  d_out_key, d_out_dbidx, d_out_score, d_out_row, d_out_count};
+  for (int i = 0; i < world; ++i) x.peers[i] = peers[i];
+  x.world = world;
+  x.rank = rank;
+  x.nq_cap = nq_cap;
+  x.k_cap = k_cap;
+  x.epoch = epoch;
+  const size_t smem = (size_t)(kMergeCap + kMergeOut) * 12;
+  SSW_CUDA(cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  exchange_merge_kernel<<<nq, kMergeThreads, smem, st>>>(x);
   SSW_LAUNCHED();
   return SSW_OK;
 }

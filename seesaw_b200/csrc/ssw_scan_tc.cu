@@ -23,6 +23,7 @@
 // reduction (8 SHFL) plus the owner's threshold / exclusion / list work.  Everything lives in registers
 // and shared memory: no local memory, no out-of-line calls.
 #include <algorithm>
+#include <cstdlib>
 
 #include "ssw_db.h"
 #include "ssw_tc.cuh"
@@ -334,10 +335,10 @@ __device__ __forceinline__ void tmem_ld_wait_regs(uint32_t* x, uint32_t* y) {
 
 constexpr int kScanTcThreads = kTcThreads + 32;     // + the threshold warp
 
-template <int DIM, int NT, int NS>
+template <int DIM, int NT, int NS, int NACC>
 __global__ void __launch_bounds__(kScanTcThreads, 1) scan_tc_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                  const ScanTcArgs a) {
-  using Cfg = TcCfg<DIM, NT>;
+  using Cfg = TcCfg<DIM, NT, NACC>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem;
   const TcSmem S = tc_carve(smem_raw, NS, Cfg::STAGE_BYTES, &smem);
@@ -376,8 +377,8 @@ __global__ void __launch_bounds__(kScanTcThreads, 1) scan_tc_kernel(const __grid
     mbar_wait_parked(S.a_ready, 0);
     tc_fence_after();
     for (int t = 0; t < ntiles; ++t) {
-      const uint32_t as = t & 1;
-      mbar_wait_parked(S.tmem_empty + 8 * as, ((t >> 1) & 1) ^ 1);
+      const uint32_t as = NACC == 2 ? (t & 1) : 0;
+      mbar_wait_parked(S.tmem_empty + 8 * as, ((NACC == 2 ? (t >> 1) : t) & 1) ^ 1);
       tc_fence_after();
       for (int kc = 0; kc < Cfg::KC; ++kc) {
         mbar_wait_parked(S.full + 8 * p.stage, p.phase);
@@ -453,7 +454,7 @@ __global__ void __launch_bounds__(kScanTcThreads, 1) scan_tc_kernel(const __grid
     };
     if (ntiles > 0) fetch_bits(0);
     for (int t = 0; t < ntiles; ++t) {
-      const uint32_t as = t & 1;
+      const uint32_t as = NACC == 2 ? (t & 1) : 0;
       const int64_t row0 = r_begin + (int64_t)t * NT;
       const int sh = (int)(row0 & 31);
       const int valid = (int)min((int64_t)NT, r_end - row0);
@@ -468,7 +469,7 @@ __global__ void __launch_bounds__(kScanTcThreads, 1) scan_tc_kernel(const __grid
       // the quad's register copies of the thresholds (raised by the owners and by the threshold warp)
       st.thrA = thr_to_acc(Q.thr[qA], cx.scaleA);
       st.thrB = thr_to_acc(Q.thr[qB], cx.scaleB);
-      mbar_wait(S.tmem_full + 8 * as, (t >> 1) & 1);
+      mbar_wait(S.tmem_full + 8 * as, (NACC == 2 ? (t >> 1) : t) & 1);
       tc_fence_after();
       const uint32_t acc = lane_addr + Cfg::ACC_BASE + as * NT;
       const int colbase = (int)(row0 - r_begin);
@@ -515,15 +516,15 @@ __global__ void __launch_bounds__(kScanTcThreads, 1) scan_tc_kernel(const __grid
   if (warp == 1) tmem_dealloc(tmem, Cfg::TMEM_ALLOC);
 }
 
-template <int DIM, int NT, int NS>
+template <int DIM, int NT, int NS, int NACC>
 static int launch_scan_tc_t(ssw_db* db, const ScanTcArgs& a, cudaStream_t st) {
-  using Cfg = TcCfg<DIM, NT>;
+  using Cfg = TcCfg<DIM, NT, NACC>;
   CUtensorMap tmap;
   int rc = make_tmap_f16_rows(&tmap, db->d_vecs, db->n_rows, DIM, NT);
   if (rc) return rc;
   const size_t smem = (size_t)NS * Cfg::STAGE_BYTES + ((tc_bar_bytes(NS) + 15) / 16) * 16 + qshared_bytes(a.k) +
                       tc_smem_slack;
-  auto kern = scan_tc_kernel<DIM, NT, NS>;
+  auto kern = scan_tc_kernel<DIM, NT, NS, NACC>;
   SSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prof_begin(db, st);      // times the scan kernel alone (not the query preparation)
   kern<<<db->scan_grid, kScanTcThreads, smem, st>>>(tmap, a);
@@ -567,9 +568,12 @@ int launch_scan_tc(ssw_db* db, const float* d_queries, int nq, int k, const uint
   a.row_base = db->row_base;
   // shared memory: NS stages of NT*128 B + 64 lists of k (key, image) pairs (k <= 64 -> <= 48 KB)
   switch (db->dim) {
-    case 256: return launch_scan_tc_t<256, 128, 10>(db, a, st);
-    case 512: return launch_scan_tc_t<512, 128, 10>(db, a, st);
-    case 768: return launch_scan_tc_t<768, 64, 20>(db, a, st);
+    case 256: return launch_scan_tc_t<256, 128, 10, 2>(db, a, st);
+    case 512: return launch_scan_tc_t<512, 128, 10, 2>(db, a, st);
+    // 768: A takes 384 of the 512 TMEM columns; one 128-column accumulator (MMA and epilogue alternate,
+    // together well under the tile's HBM time) beats two 64-column ones (twice the per-tile overhead)
+    case 768: return getenv("SSW_TC768_NT64") ? launch_scan_tc_t<768, 64, 20, 2>(db, a, st)
+                                              : launch_scan_tc_t<768, 128, 10, 1>(db, a, st);
   }
   set_error("batched scan supports dim 256, 512 or 768");
   return SSW_ERR_INVALID;

@@ -114,13 +114,13 @@ __device__ __forceinline__ uint64_t make_bdesc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
-template <int DIM, int NT>
+template <int DIM, int NT, int NACC = 2>
 struct TcCfg {
   static_assert(DIM % kTcKChunk == 0, "DIM must be a multiple of 64");
   static constexpr int KC = DIM / kTcKChunk;            // stages (TMA boxes) per tile
   static constexpr int A_COLS = DIM / 2;                // TMEM columns of the resident A operand
   static constexpr int ACC_BASE = 0;
-  static constexpr int A_BASE = 2 * NT;
+  static constexpr int A_BASE = NACC * NT;          // NACC accumulator buffers of NT columns, then A
   static constexpr int TMEM_USED = A_BASE + A_COLS;
   static constexpr int TMEM_ALLOC = TMEM_USED <= 32 ? 32 : TMEM_USED <= 64 ? 64 : TMEM_USED <= 128 ? 128
                                     : TMEM_USED <= 256 ? 256 : 512;

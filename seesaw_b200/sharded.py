@@ -69,6 +69,72 @@ class ShardedPatchDatabase:
     def __init__(self, local, *, rank, world_size, group=None, merge=None):
         self.local, self.rank, self.world_size, self.group = local, rank, world_size, group
         self._merge = merge
+        self._xchg = None            # fused peer-memory exchange (enable_fused_exchange)
+
+    # ---- fused exchange over peer memory --------------------------------------------------
+    def enable_fused_exchange(self, nq_cap=64, k_cap=64):
+        """Replace [local merge -> NCCL all-gather -> merge] by ONE kernel per step that merges the shard's
+        lists, stores them into every rank's exchange buffer over NVLink and merges the world's lists
+        (C ABI ``ssw_scan_topk_sharded_device``).  Collective: every rank must call it.  The buffers are
+        plain cudaMalloc memory shared through CUDA IPC handles, which travel over the process group."""
+        import ctypes as C
+
+        import torch.distributed as dist
+
+        from ._lib import check, lib
+        dev = self.local.device
+        buf, nbytes = C.c_void_p(), C.c_int64()
+        handle = C.create_string_buffer(64)
+        check(lib.ssw_xchg_create(dev, self.world_size, nq_cap, k_cap, C.byref(buf), handle, C.byref(nbytes)))
+        handles = [None] * self.world_size
+        if self.world_size > 1:
+            dist.all_gather_object(handles, handle.raw, group=self.group)
+        peers = (C.c_void_p * self.world_size)()
+        for r in range(self.world_size):
+            if r == self.rank:
+                peers[r] = buf.value
+            else:
+                p = C.c_void_p()
+                check(lib.ssw_xchg_open(dev, C.create_string_buffer(handles[r], 64), C.byref(p)))
+                peers[r] = p.value
+        if self.world_size > 1:
+            dist.barrier(group=self.group)
+        self._xchg = dict(buf=buf, peers=peers, nq_cap=nq_cap, k_cap=k_cap, epoch=0)
+
+    def close(self):
+        if self._xchg is not None:
+            from ._lib import lib
+            dev = self.local.device
+            for r in range(self.world_size):
+                if r != self.rank:
+                    lib.ssw_xchg_close(dev, self._xchg["peers"][r])
+            lib.ssw_xchg_destroy(dev, self._xchg["buf"])
+            self._xchg = None
+        self.local.close()
+
+    def _scan_fused(self, d_queries, k, d_exclude_bits, stream=None):
+        import ctypes as C
+
+        import torch
+
+        from ._lib import check, lib
+        x = self._xchg
+        nq = d_queries.shape[0]
+        dev = d_queries.device
+        out = dict(key=torch.empty((nq, k), dtype=torch.int64, device=dev),
+                   dbidx=torch.empty((nq, k), dtype=torch.int32, device=dev),
+                   score=torch.empty((nq, k), dtype=torch.float32, device=dev),
+                   row=torch.empty((nq, k), dtype=torch.int64, device=dev),
+                   count=torch.empty((nq,), dtype=torch.int32, device=dev))
+        x["epoch"] += 1
+        s = torch.cuda.current_stream(dev) if stream is None else stream
+        bits = None if d_exclude_bits is None else C.c_void_p(d_exclude_bits.data_ptr())
+        check(lib.ssw_scan_topk_sharded_device(
+            self.local._h, C.c_void_p(d_queries.data_ptr()), nq, int(k), bits, x["peers"], self.world_size, self.rank,
+            x["nq_cap"], x["k_cap"], x["epoch"], C.c_void_p(out["key"].data_ptr()), C.c_void_p(out["dbidx"].data_ptr()),
+            C.c_void_p(out["score"].data_ptr()), C.c_void_p(out["row"].data_ptr()), C.c_void_p(out["count"].data_ptr()),
+            C.c_void_p(s.cuda_stream)))
+        return out
 
     @classmethod
     def synthetic(cls, rows_per_image, dim, *, seed, rank, world_size, device, kind="tri", store="f16", group=None):
@@ -91,6 +157,8 @@ class ShardedPatchDatabase:
         nq = d_queries.shape[0]
         if d_exclude_bits is None and exclude is not None:
             d_exclude_bits = self.local.build_exclude_bits(exclude, nq)
+        if self._xchg is not None and nq <= self._xchg["nq_cap"] and k <= self._xchg["k_cap"]:
+            return self._scan_fused(d_queries, k, d_exclude_bits)
         keys, dbidx = self.local.scan_topk_device(d_queries, k, d_exclude_bits)
         if self.world_size == 1 and self._merge is None:
             from .engine import merge_topk_device

@@ -1,0 +1,87 @@
+"""GPU tests of the row-sharded scan: world size 1 always; world size 2 over NCCL when the box has two GPUs
+(the driver's 1-GPU box skips that one; `gpurun --gpus 2 -- pytest tests/test_sharded_gpu.py -m gpu` runs it)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import seesaw_oracle as orc
+from seesaw_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem():
+    counts = synth.patches_per_image(6000, 1, 40, 8)
+    dbidx = synth.dbidx_of_rows(counts)
+    n = int(counts.sum())
+    qs = synth.lattice_queries(20, 512, 9)
+    ids = np.unique(dbidx)
+    rng = np.random.default_rng(3)
+    excl = [rng.choice(ids, size=int(s), replace=False) for s in rng.choice([0, 5, 300], size=len(qs))]
+    return counts, dbidx, n, qs, excl
+
+
+def _check(res, counts, dbidx, n, qs, excl, k):
+    vecs = synth.synth_rows(0, n, 512, 23, "lattice", np.float32)
+    got = {name: t.cpu().numpy() for name, t in res.items()}
+    for i in range(len(qs)):
+        o = orc.query_prelim(vecs, dbidx, qs[i], k, exclude=excl[i])
+        m = len(o["dbidx"])
+        assert got["count"][i] == m
+        assert (got["dbidx"][i, :m] == o["dbidx"]).all(), i
+        assert (got["row"][i, :m] == o["best_row"]).all(), i
+        assert (got["score"][i, :m] == o["max_score"]).all(), i
+
+
+def test_sharded_world1():
+    import torch
+    from seesaw_b200.sharded import ShardedPatchDatabase
+    counts, dbidx, n, qs, excl = _problem()
+    sdb = ShardedPatchDatabase.synthetic(counts, 512, seed=23, rank=0, world_size=1, device=0, kind="lattice")
+    for fused in (False, True):
+        if fused:
+            sdb.enable_fused_exchange(nq_cap=32, k_cap=64)
+        for k in (50, 3):
+            res = sdb.scan_topk_device(torch.from_numpy(qs).cuda(), k, exclude=excl)
+            torch.cuda.synchronize()
+            _check(res, counts, dbidx, n, qs, excl, k)
+    sdb.close()
+
+
+def _worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    from seesaw_b200.sharded import ShardedPatchDatabase
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    counts, dbidx, n, qs, excl = _problem()
+    sdb = ShardedPatchDatabase.synthetic(counts, 512, seed=23, rank=rank, world_size=world, device=rank, kind="lattice")
+    for fused in (False, True):
+        if fused:
+            sdb.enable_fused_exchange(nq_cap=32, k_cap=64)
+        for rep in range(3):                      # several epochs: both buffer parities are reused
+            for k in (50, 3):
+                res = sdb.scan_topk_device(torch.from_numpy(qs).cuda(), k, exclude=excl)
+                torch.cuda.synchronize()
+                _check(res, counts, dbidx, n, qs, excl, k)
+    dist.barrier()
+    sdb.close()
+    dist.destroy_process_group()
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+
+
+def test_sharded_world2_nccl(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    world = min(torch.cuda.device_count(), 4)
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
