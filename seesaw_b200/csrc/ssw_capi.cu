@@ -172,6 +172,9 @@ static int build_layout(ssw_db* db, const int32_t* dbidx_per_row, std::vector<in
   }
   part[0] = 0;
   part[G] = (int32_t)db->n_images;
+  db->max_cta_images = 0;
+  for (int c = 0; c < db->scan_grid; ++c)
+    db->max_cta_images = std::max<int64_t>(db->max_cta_images, part[(c + 1) * kScanWarps] - part[c * kScanWarps]);
 
   int rc;
   if ((rc = dev_alloc(&db->d_img_of_row, (size_t)n + 1))) return rc;

@@ -23,6 +23,7 @@ struct ssw_db {
   int64_t* d_orig_row = nullptr;   // [n_rows] device row -> original local row; NULL when identity
   int32_t* d_part = nullptr;       // [scan_warps + 1] image range of every scan warp
   int scan_grid = 0;               // CTAs of the streaming scan (one per SM)
+  int64_t max_cta_images = 0;      // most images any CTA's range holds
   uint32_t* d_last_bits = nullptr; // [n_rows/32 + pad] bit r set <=> device row r is the last row of its image
   void* d_tc_ws = nullptr;         // prepared A operand of the tcgen05 batched scan (one batch)
 

@@ -37,6 +37,7 @@ struct ScanTcArgs {
   int k;
   const uint32_t* excl;      // [nq, excl_words] or null
   int64_t excl_words;
+  int excl_slice_words;      // > 0: every CTA keeps its image range's slice of the bitmaps in shared memory
   const uint32_t* last_bits; // bit r set <=> device row r is the last row of its image
   const int64_t* row_ptr;
   const int32_t* img_dbidx;
@@ -109,6 +110,7 @@ struct QShared {
   int32_t* minpos;      // [64]
   uint32_t* best;       // [64] order-preserving score bits of the best candidate held (published to the other CTAs)
   int* done;            // epilogue warps that have finished (the threshold warp leaves at 4)
+  uint32_t* excl;       // [64][slice_words] this CTA's slice of the exclusion bitmaps (optional)
 };
 __host__ __device__ constexpr size_t qshared_bytes(int k) { return (size_t)k * 64 * 12 + 64 * (8 + 4 + 4 + 4) + 16; }
 
@@ -121,6 +123,7 @@ __device__ __forceinline__ QShared qshared_carve(uint8_t* base, int k) {
   q.minpos = q.cnt + 64;
   q.best = reinterpret_cast<uint32_t*>(q.minpos + 64);
   q.done = reinterpret_cast<int*>(q.best + 64);
+  q.excl = reinterpret_cast<uint32_t*>(q.done + 4);
   return q;
 }
 
@@ -133,24 +136,29 @@ __device__ __forceinline__ float thr_to_acc(uint64_t thr, float scale) {
 // `drow`.  Applies the threshold, the exclusion bitmap and the list update; returns the (possibly
 // raised) threshold key of the query.
 __device__ __forceinline__ uint64_t scan_tc_offer(const QShared& Q, const ScanTcArgs& a, int q, float best,
-                                                  float inv_scale, int64_t drow, int img) {
+                                                  float inv_scale, int64_t drow, int img, int slice_base) {
   const int k = a.k;
+  // every shared-memory word the common (append) path needs is loaded up front: one LDS latency instead of
+  // a chain of five dependent ones — this path runs for every image until the first pooled threshold arrives
   const uint64_t thr = Q.thr[q];
+  const int cnt = Q.cnt[q];
+  const uint32_t best_seen = Q.best[q];
+  uint32_t xw = 0;
+  if (a.excl && a.excl_slice_words > 0) xw = Q.excl[q * a.excl_slice_words + (img >> 5) - slice_base];
   uint64_t key = make_key(best * inv_scale, (uint32_t)drow);
   if ((key >> 32) < (thr >> 32)) return thr;
   const int64_t orow = a.orig_row ? a.orig_row[drow] : drow;
   key = (key & 0xFFFFFFFF00000000ull) | (uint64_t)(0xFFFFFFFFu - (uint32_t)(a.row_base + orow));
   if (key <= thr) return thr;
   if (a.excl) {
-    const uint32_t w = __ldg(a.excl + (size_t)q * a.excl_words + (img >> 5));
-    if ((w >> (img & 31)) & 1u) return thr;
+    if (a.excl_slice_words == 0) xw = __ldg(a.excl + (size_t)q * a.excl_words + (img >> 5));
+    if ((xw >> (img & 31)) & 1u) return thr;
   }
-  if ((uint32_t)(key >> 32) > Q.best[q]) {      // a new best of this CTA: let the other CTAs see it
+  if ((uint32_t)(key >> 32) > best_seen) {      // a new best of this CTA: let the other CTAs see it
     Q.best[q] = (uint32_t)(key >> 32);
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(a.pub + (size_t)q * gridDim.x + blockIdx.x),
                  "r"((uint32_t)(key >> 32)) : "memory");
   }
-  const int cnt = Q.cnt[q];
   if (cnt < k) {
     Q.keys[cnt * 64 + q] = key;
     Q.img[cnt * 64 + q] = img;
@@ -193,6 +201,7 @@ struct EpiCtx {
   int own_q;
   float invA, invB, scaleA, scaleB;
   int64_t r_begin;
+  int slice_base;     // first bitmap word of the CTA's exclusion slice
 };
 
 // An image ends here (warp-uniform call).
@@ -216,7 +225,8 @@ __device__ __forceinline__ void scan_tc_boundary(EpiState& st, const EpiCtx& cx,
       const float mythr = cx.j ? st.thrB : st.thrA;
       if (best >= mythr) {
         const int col = 0x7FFFFFFF - (int)(uint32_t)(kk & 0xFFFFFFFFu);
-        const uint64_t nthr = scan_tc_offer(Q, a, cx.own_q, best, cx.j ? cx.invB : cx.invA, cx.r_begin + col, st.cur_img);
+        const uint64_t nthr = scan_tc_offer(Q, a, cx.own_q, best, cx.j ? cx.invB : cx.invA, cx.r_begin + col, st.cur_img,
+                                            cx.slice_base);
         const float t = thr_to_acc(nthr, cx.j ? cx.scaleB : cx.scaleA);
         if (cx.j) st.thrB = t; else st.thrA = t;
       }
@@ -242,34 +252,46 @@ __device__ __forceinline__ void scan_tc_threshold_warp(const QShared& Q, const S
   while (ngp < a.k) ngp <<= 1;                  // k <= 64
   const bool pooled = G >= ngp && G <= 32 * VMAX;
   volatile int* done = Q.done;
+  constexpr int QB = 8;                         // queries whose loads are in flight together
   while (*done < 4) {
-#pragma unroll 2
-    for (int q = 0; q < a.nq; ++q) {
-      uint32_t t = 0;
-      if (pooled) {
-        uint32_t v[VMAX];
+#pragma unroll 1
+    for (int q0 = 0; q0 < a.nq; q0 += QB) {
+      uint32_t v[QB][VMAX];
+      uint64_t g[QB];
+#pragma unroll
+      for (int u = 0; u < QB; ++u) {
+        const int q = q0 + u;
 #pragma unroll
         for (int m = 0; m < VMAX; ++m) {
           const int c = lane + 32 * m;
-          v[m] = 0u;
-          if (c < G)
-            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v[m]) : "l"(a.pub + (size_t)q * G + c) : "memory");
+          v[u][m] = 0u;
+          if (pooled && q < a.nq && c < G)
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v[u][m]) : "l"(a.pub + (size_t)q * G + c) : "memory");
         }
-        if (ngp == 64) {                        // groups lane and lane + 32
-          const uint32_t ga = max(max(v[0], v[2]), v[4]), gb = max(max(v[1], v[3]), v[5]);
-          t = min(ga, gb);
-        } else {                                // group lane % ngp
-          t = max(max(max(v[0], v[1]), max(v[2], v[3])), max(v[4], v[5]));
-          for (int sft = 16; sft >= ngp; sft >>= 1) t = max(t, __shfl_xor_sync(0xffffffffu, t, sft));
-        }
-        t = __reduce_min_sync(0xffffffffu, t);
+        g[u] = 0;
+        if (lane == 0 && q < a.nq) g[u] = ld_relaxed_u64(a.g_thr + q);
       }
-      if (lane == 0) {
-        const uint64_t g = ld_relaxed_u64(a.g_thr + q);
-        const uint64_t tkey = (uint64_t)t << 32;
-        if (blockIdx.x == 0 && tkey > g) atomicMax(reinterpret_cast<unsigned long long*>(a.g_thr + q), (unsigned long long)tkey);
-        const uint64_t best = tkey > g ? tkey : g;
-        if (best != 0) atomicMax(reinterpret_cast<unsigned long long*>(Q.thr + q), (unsigned long long)best);
+#pragma unroll
+      for (int u = 0; u < QB; ++u) {
+        const int q = q0 + u;
+        if (q >= a.nq) break;
+        uint32_t t = 0;
+        if (pooled) {
+          if (ngp == 64) {                        // groups lane and lane + 32
+            const uint32_t ga = max(max(v[u][0], v[u][2]), v[u][4]), gb = max(max(v[u][1], v[u][3]), v[u][5]);
+            t = min(ga, gb);
+          } else {                                // group lane % ngp
+            t = max(max(max(v[u][0], v[u][1]), max(v[u][2], v[u][3])), max(v[u][4], v[u][5]));
+            for (int sft = 16; sft >= ngp; sft >>= 1) t = max(t, __shfl_xor_sync(0xffffffffu, t, sft));
+          }
+          t = __reduce_min_sync(0xffffffffu, t);
+        }
+        if (lane == 0) {
+          const uint64_t tkey = (uint64_t)t << 32;
+          if (blockIdx.x == 0 && tkey > g[u]) atomicMax(reinterpret_cast<unsigned long long*>(a.g_thr + q), (unsigned long long)tkey);
+          const uint64_t best = tkey > g[u] ? tkey : g[u];
+          if (best != 0) atomicMax(reinterpret_cast<unsigned long long*>(Q.thr + q), (unsigned long long)best);
+        }
       }
     }
     __nanosleep(2000);
@@ -426,7 +448,21 @@ __global__ void __launch_bounds__(kScanTcThreads, 1) scan_tc_kernel(const __grid
       mbar_arrive(S.a_ready);
     }
 
+    // ---- this CTA's slice of the warp's 16 exclusion bitmaps -> shared memory
+    const int slice_base = img0 >> 5;
+    if (a.excl && a.excl_slice_words > 0 && img1 > img0) {
+      const int nw = ((img1 - 1) >> 5) - slice_base + 1;
+      for (int i = 0; i < 16; ++i) {
+        const int qs = q4 * 16 + i;
+        if (qs >= a.nq) break;
+        for (int w = lane; w < nw; w += 32)
+          Q.excl[qs * a.excl_slice_words + w] = __ldg(a.excl + (size_t)qs * a.excl_words + slice_base + w);
+      }
+      __syncwarp();
+    }
+
     EpiCtx cx;
+    cx.slice_base = slice_base;
     cx.j = lane & 3;
     const int r = lane >> 2;
     const int qA = q4 * 16 + r, qB = qA + 8;
@@ -501,13 +537,16 @@ __global__ void __launch_bounds__(kScanTcThreads, 1) scan_tc_kernel(const __grid
     // ---- publish this CTA's list of every query
     __syncwarp();
     if (lane == 0) atomicAdd(Q.done, 1);
-    if (cx.owner) {
-      const int qi = cx.own_q;
-      const int cnt = Q.cnt[qi];
-      const int64_t o = ((int64_t)qi * gridDim.x + blockIdx.x) * k;
-      for (int s = 0; s < k; ++s) {
-        a.list_keys[o + s] = s < cnt ? Q.keys[s * 64 + qi] : 0ull;
-        a.list_dbidx[o + s] = s < cnt ? a.img_dbidx[Q.img[s * 64 + qi]] : -1;
+    // (the warp's 16 queries x k slots spread over its 32 lanes: independent loads and stores)
+    {
+      const int nqw = min(16, a.nq - q4 * 16);
+#pragma unroll 4
+      for (int e = lane; e < nqw * k; e += 32) {
+        const int qi = q4 * 16 + e / k, sl = e % k;
+        const bool ok = sl < Q.cnt[qi];
+        const int64_t o = ((int64_t)qi * gridDim.x + blockIdx.x) * k + sl;
+        a.list_keys[o] = ok ? Q.keys[sl * 64 + qi] : 0ull;
+        a.list_dbidx[o] = ok ? __ldg(a.img_dbidx + Q.img[sl * 64 + qi]) : -1;
       }
     }
   }
@@ -522,12 +561,20 @@ static int launch_scan_tc_t(ssw_db* db, const ScanTcArgs& a, cudaStream_t st) {
   CUtensorMap tmap;
   int rc = make_tmap_f16_rows(&tmap, db->d_vecs, db->n_rows, DIM, NT);
   if (rc) return rc;
-  const size_t smem = (size_t)NS * Cfg::STAGE_BYTES + ((tc_bar_bytes(NS) + 15) / 16) * 16 + qshared_bytes(a.k) +
-                      tc_smem_slack;
+  size_t smem = (size_t)NS * Cfg::STAGE_BYTES + ((tc_bar_bytes(NS) + 15) / 16) * 16 + qshared_bytes(a.k) + tc_smem_slack;
+  ScanTcArgs a2 = a;
+  a2.excl_slice_words = 0;
+  if (a.excl) {   // keep the CTA's slice of the bitmaps in shared memory when it fits (227 KB per CTA)
+    const int words = (int)(db->max_cta_images / 32) + 2;
+    if (smem + (size_t)64 * words * 4 <= 232448) {
+      a2.excl_slice_words = words;
+      smem += (size_t)64 * words * 4;
+    }
+  }
   auto kern = scan_tc_kernel<DIM, NT, NS, NACC>;
   SSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prof_begin(db, st);      // times the scan kernel alone (not the query preparation)
-  kern<<<db->scan_grid, kScanTcThreads, smem, st>>>(tmap, a);
+  kern<<<db->scan_grid, kScanTcThreads, smem, st>>>(tmap, a2);
   prof_end(db, st);
   SSW_LAUNCHED();
   return SSW_OK;
