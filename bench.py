@@ -258,16 +258,16 @@ def main():
     torch.cuda.synchronize()
 
     line = None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         esz = 2
-        bytes_per_launch = db.n_rows * (DIM * esz + 4)              # vectors + 4-byte image id per row (this shard)
+        bytes_per_launch = db.n_rows * DIM * esz + db.n_rows // 8   # vectors + 1 boundary bit per row (this rank's shard)
         kern_avg_ms = kern_ms / max(kern_n, 1)
         achieved = bytes_per_launch / (kern_avg_ms * 1e-3) / 1e9 if kern_n else None
         ms_per_step = dev_ms / args.steps
@@ -314,33 +314,43 @@ def main():
                                 "queries_per_s": 1e3 / step_ms, "kernel_ms_avg": k1_ms / max(k1_n, 1),
                                 "achieved_gbs": bytes1 / (k1_ms / max(k1_n, 1) * 1e-3) / 1e9,
                                 "frac_of_peak": bytes1 / (k1_ms / max(k1_n, 1) * 1e-3) / 1e9 / line["roofline"]["peak"]}
-        if not args.no_knn:
-            from seesaw_b200.knn_graph import knn_candidates_device
-            n_knn = 1_000_000                     # BASELINE config 4: k=10 exact graph over 1M x 512
-            g = torch.Generator(device=dev).manual_seed(5)
-            v = torch.randn(n_knn, DIM, device=dev, generator=g)
-            v = (v / v.norm(dim=1, keepdim=True)).half().contiguous()
-            knn_candidates_device(v, 10, rows=(0, 148 * 128))          # warm-up: one wave of row blocks
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            knn_candidates_device(v, 10)
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1)
+    # ---- kNN-graph build (BASELINE config 4): k=10 exact graph over 1M x 512, output rows split over the ranks
+    if not args.no_knn:
+        from seesaw_b200.knn_graph import knn_candidates_device
+        from seesaw_b200.sharded import knn_candidates_sharded, knn_row_ranges
+        n_knn = 1_000_000
+        g = torch.Generator(device=dev).manual_seed(5)             # same seed on every rank: V is replicated
+        v = torch.randn(n_knn, DIM, device=dev, generator=g)
+        v = (v / v.norm(dim=1, keepdim=True)).half().contiguous()
+        lo = int(knn_row_ranges(n_knn, world)[rank])
+        knn_candidates_device(v, 10, rows=(lo, min(lo + 148 * 128, n_knn)))     # warm-up: one wave of row blocks
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        idx, _ = knn_candidates_sharded(v, 10, rank=rank, world_size=world)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        self_ok = bool((idx[::9973, 0].cpu() == torch.arange(0, n_knn, 9973, dtype=torch.int32)).all())
+        if rank == 0:
             tf = 2.0 * n_knn * n_knn * DIM / (ms * 1e-3) / 1e12
-            tpeak = float(peaks.get("bf16_tflops", 1590.0))
+            tpeak = float(peaks.get("bf16_tflops", 1590.0)) * world
             line["knn_build"] = {"kernel": "ssw::knn_kernel<512,128,12> (K3, tcgen05 + fused row top-11)", "n": n_knn,
                                  "dim": DIM, "k": 10, "seconds": ms * 1e-3, "flops": 2.0 * n_knn * n_knn * DIM,
                                  "roofline": {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s",
                                               "frac": tf / tpeak,
-                                              "frac_of_sustained": tf / float(peaks.get("bf16_tflops_sustained", tpeak))},
-                                 "note": "one launch, all 1M rows on one GPU, vectors resident in HBM"}
-            del v
-        if not args.no_cpu_baseline:
-            sdb.local.close()
-            torch.cuda.empty_cache()
-            line["cpu_baseline"] = cpu_reference_arm(steps=4, warmup=1)
+                                              "frac_of_sustained": tf / (float(peaks.get("bf16_tflops_sustained", tpeak / world)) * world)},
+                                 "sharding": f"output rows over {world} GPU(s), V replicated, final all-gather of [N,11] ids+distances included",
+                                 "self_is_nearest_spot_check": self_ok}
+        del v, idx
+        torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sdb.close()
+        torch.cuda.empty_cache()
+        line["cpu_baseline"] = cpu_reference_arm(steps=4, warmup=1)
     if rank == 0:
         line.setdefault("cpu_baseline", None)
         emit(line)

@@ -173,3 +173,41 @@ class ShardedPatchDatabase:
             return self._merge(all_k, all_d, k)
         from .engine import merge_topk_device
         return merge_topk_device(all_k, all_d, k)
+
+
+# ---------------------------------------------------------------------------------------------
+# exact kNN graph across ranks: V replicated on every GPU, rank r computes output rows
+# [lo_r, hi_r) against all columns, no communication until the final all-gather of [N, k1] (idx, dist)
+# ---------------------------------------------------------------------------------------------
+def knn_row_ranges(n, world_size, block=128):
+    """Row range of every rank, aligned to the kernel's 128-row blocks: int64 [world_size+1]."""
+    blocks = -(-n // block)
+    per = -(-blocks // world_size)
+    return np.minimum(np.arange(world_size + 1, dtype=np.int64) * per * block, n)
+
+
+def knn_candidates_sharded(d_vectors, n_neighbors, *, rank, world_size, group=None, candidates=None):
+    """Every rank passes the SAME [N, dim] tensor (fp16 CUDA tensor on GPUs) and receives the full
+    candidate table (idx int32 [N,k1], dist fp32 [N,k1]) — compute_exact_knn's matmul + argsort
+    (seesaw/knn_graph.py:170-182) split by output rows.  ``candidates(vectors, k, rows=(lo, hi))`` is the
+    per-rank builder (default: the tcgen05 kernel); injected on CPU for the gloo test."""
+    import torch
+    import torch.distributed as dist
+    if candidates is None:
+        from .knn_graph import knn_candidates_device as candidates
+    n = d_vectors.shape[0]
+    k1 = min(int(n_neighbors) + 1, n)
+    bounds = knn_row_ranges(n, world_size)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    idx, dist_ = candidates(d_vectors, n_neighbors, rows=(lo, hi))
+    if world_size == 1:
+        return idx, dist_
+    per = int(bounds[1] - bounds[0])                          # equal-size slots, the last ones may be partly empty
+    pad_i = torch.full((per, k1), -1, dtype=idx.dtype, device=idx.device)
+    pad_d = torch.full((per, k1), float("inf"), dtype=dist_.dtype, device=dist_.device)
+    pad_i[: hi - lo], pad_d[: hi - lo] = idx, dist_
+    all_i = torch.empty((world_size * per, k1), dtype=idx.dtype, device=idx.device)
+    all_d = torch.empty((world_size * per, k1), dtype=dist_.dtype, device=dist_.device)
+    dist.all_gather_into_tensor(all_i, pad_i, group=group)
+    dist.all_gather_into_tensor(all_d, pad_d, group=group)
+    return all_i[:n], all_d[:n]

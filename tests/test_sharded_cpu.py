@@ -24,6 +24,13 @@ def test_shard_image_ranges_are_balanced_and_aligned():
     assert b[0] == 0 and b[-1] == 2 and (np.diff(b) >= 0).all()
 
 
+def test_knn_row_ranges():
+    for n, w in ((1000, 3), (128, 8), (1, 2), (100000, 8)):
+        b = sharded.knn_row_ranges(n, w)
+        assert b[0] == 0 and b[-1] == n and (np.diff(b) >= 0).all()
+        assert all(x % 128 == 0 or x == n for x in b)
+
+
 def test_key_roundtrip_and_order():
     rng = np.random.default_rng(0)
     s = np.concatenate([rng.standard_normal(1000).astype(np.float32), np.float32([0.0, -0.0, 1.0, -1.0])])
@@ -93,6 +100,16 @@ def _worker(rank, world, port, out_dir):
             assert (res["row"][i, :m] == o["best_row"]).all(), (k, i)
             assert (res["score"][i, :m] == o["max_score"]).all(), (k, i)
             assert (res["dbidx"][i, m:] == -1).all()
+    # kNN graph split by output rows + all-gather (the oracle's blockwise builder plays the kernel's part)
+    v = synth.synth_rows(0, 333, 256, 19, "lattice", np.float32) * np.float32(0.25)
+
+    def cand(vec, k, rows):
+        i, d = orc.exact_knn_candidates_blockwise(vec.numpy(), k, block=64, rows=rows)
+        return torch.from_numpy(i), torch.from_numpy(d)
+
+    gi, gd = sharded.knn_candidates_sharded(torch.from_numpy(v), 10, rank=rank, world_size=world, candidates=cand)
+    oi, od = orc.exact_knn_candidates(v, 10)
+    assert (gi.numpy() == oi).all() and (gd.numpy() == od).all()
     dist.barrier()
     dist.destroy_process_group()
     open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
