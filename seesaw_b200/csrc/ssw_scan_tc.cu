@@ -331,10 +331,12 @@ __device__ __forceinline__ void scan_tc_group(EpiState& st, const EpiCtx& cx, co
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int e = 0; e < 2; ++e)
-        if ((mine >> (8 * i + e)) & 1u) {
-          if (sa[2 * i + e] > st.m0) { st.m0 = sa[2 * i + e]; st.c0 = cb + 8 * i + e; }
-          if (sb[2 * i + e] > st.m1) { st.m1 = sb[2 * i + e]; st.c1 = cb + 8 * i + e; }
-        }
+      {                       // branch-free: a column outside the segment competes with -inf
+        const bool on = (mine >> (8 * i + e)) & 1u;
+        const float xa = on ? sa[2 * i + e] : -INFINITY, xb = on ? sb[2 * i + e] : -INFINITY;
+        if (xa > st.m0) { st.m0 = xa; st.c0 = cb + 8 * i + e; }
+        if (xb > st.m1) { st.m1 = xb; st.c1 = cb + 8 * i + e; }
+      }
     if (em == 0) break;
     em &= em - 1;
     scan_tc_boundary(st, cx, Q, a);
