@@ -338,7 +338,7 @@ def main():
         if rank == 0:
             tf = 2.0 * n_knn * n_knn * DIM / (ms * 1e-3) / 1e12
             tpeak = float(peaks.get("bf16_tflops", 1590.0)) * world
-            line["knn_build"] = {"kernel": "ssw::knn_kernel<512,128,12> (K3, tcgen05 + fused row top-11)", "n": n_knn,
+            line["knn_build"] = {"kernel": "ssw::knn3_kernel<512> (K3: tcgen05 cta_group::2, M256 x N256 SS MMAs, fused row top-11)", "n": n_knn,
                                  "dim": DIM, "k": 10, "seconds": ms * 1e-3, "flops": 2.0 * n_knn * n_knn * DIM,
                                  "roofline": {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s",
                                               "frac": tf / tpeak,

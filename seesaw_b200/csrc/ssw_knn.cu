@@ -448,6 +448,192 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
   if (warp == 1) tmem_dealloc_2sm(tmem, 512);
 }
 
+// ------------------------------------------------------------------------------------------
+// K3, full-rate variant: CTA pairs + N = 256 MMAs.  Measured with the epilogue switched off, N = 128
+// instructions cap the tensor pipe at ~1200 TFLOP/s while N = 256 reach ~1480 (per-instruction
+// overhead).  Two 256-column accumulators fill tensor memory, so A moves to shared memory (SS form):
+// a pair owns 256 output rows; each CTA keeps its 128 rows of A resident (DIM*256 bytes, loaded by TMA
+// once per row block) and streams its 128-row half of every 256-row B tile; per MMA a CTA reads 4 KB
+// of A and 4 KB of B from shared memory in 128 cycles — half the shared-memory bandwidth.
+// ------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+    knn3_kernel(const __grid_constant__ CUtensorMap tmap, const KnnArgs a, const int NS) {
+  constexpr int NT = 256;                         // B tile rows per MMA (128 per CTA)
+  constexpr int KC = DIM / kTcKChunk;
+  constexpr int CHUNK_BYTES = 128 * 128;          // 128 rows x 64 fp16: one TMA box, one SWIZZLE_128B operand tile
+  constexpr int A_BYTES = KC * CHUNK_BYTES;
+  constexpr uint32_t IDESC = make_idesc_f16(256, NT);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t a_smem = (raw + 1023u) & ~1023u;                 // resident A: KC chunks
+  const uint32_t stages = a_smem + A_BYTES;                       // NS chunks of B
+  const uint32_t bars = stages + (uint32_t)NS * CHUNK_BYTES;
+  const uint32_t full = bars, empty = bars + 8 * NS, tmem_full = bars + 16 * NS, tmem_empty = tmem_full + 16;
+  const uint32_t a_ready = tmem_empty + 16, a_empty = a_ready + 8, tmem_ptr = a_empty + 8;
+  uint8_t* after = smem_raw + (a_smem - raw) + A_BYTES + NS * CHUNK_BYTES + ((16 * NS + 16 + 16 + 8 + 8 + 8 + 15) / 16) * 16;
+  uint64_t* lists = reinterpret_cast<uint64_t*>(after);
+  KnnRowState* states = reinterpret_cast<KnnRowState*>(lists + (size_t)a.k1 * 128);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(full + 8 * i, 1);
+      mbar_init(empty + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tmem_full + 8 * i, 1);
+      mbar_init(tmem_empty + 8 * i, 256);
+    }
+    mbar_init(a_ready, 1);
+    mbar_init(a_empty, 1);
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_ptr, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tmem_ptr));
+
+  const int64_t npairs = gridDim.x / 2, pair = blockIdx.x / 2;
+  const int64_t nblocks2 = (a.row_end - a.row_begin + 255) / 256;
+  const int ntiles = (int)((a.n + NT - 1) / NT);
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, blk = 0;
+      for (int64_t b = pair; b < nblocks2; b += npairs, ++blk) {
+        // this CTA's 128 rows of A, once the previous block's MMAs have all completed
+        if (blk > 0) mbar_wait_parked(a_empty, (blk - 1) & 1);
+        if (leader) mbar_expect_tx(a_ready, 2 * A_BYTES);
+        const int arow = (int)(a.row_begin + b * 256 + (int64_t)rank * 128);
+        for (int kc = 0; kc < KC; ++kc)
+          tma_load_2d_2sm(a_smem + kc * CHUNK_BYTES, &tmap, kc * kTcKChunk, arow, a_ready);
+        for (int t = 0; t < ntiles; ++t) {
+          for (int kc = 0; kc < KC; ++kc) {
+            mbar_wait_parked(empty + 8 * stage, phase ^ 1);
+            if (leader) mbar_expect_tx(full + 8 * stage, 2 * CHUNK_BYTES);
+            tma_load_2d_2sm(stages + stage * CHUNK_BYTES, &tmap, kc * kTcKChunk, t * NT + (int)rank * (NT / 2),
+                            full + 8 * stage);
+            if (++stage == NS) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (even CTA only) =====
+    if (leader) {
+      int stage = 0;
+      uint32_t phase = 0, it = 0, blk = 0;
+      for (int64_t b = pair; b < nblocks2; b += npairs, ++blk) {
+        mbar_wait_parked(a_ready, blk & 1);
+        tc_fence_after();
+        for (int t = 0; t < ntiles; ++t, ++it) {
+          const uint32_t as = it & 1;
+          mbar_wait_parked(tmem_empty + 8 * as, ((it >> 1) & 1) ^ 1);
+          tc_fence_after();
+          for (int kc = 0; kc < KC; ++kc) {
+            mbar_wait_parked(full + 8 * stage, phase);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint64_t adesc = make_bdesc_sw128(a_smem + kc * CHUNK_BYTES);
+              const uint64_t bdesc = make_bdesc_sw128(stages + stage * CHUNK_BYTES);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                mma_f16_ss_2sm(tmem + as * NT, adesc + 2 * k, bdesc + 2 * k, IDESC, (kc | k) != 0);
+              tc_commit_2sm(empty + 8 * stage);
+            }
+            __syncwarp();
+            if (++stage == NS) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          if (lane == 0) {
+            tc_commit_2sm(tmem_full + 8 * as);
+            if (t == ntiles - 1) tc_commit_2sm(a_empty);       // A may be replaced once these MMAs are done
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: one thread per output row (both CTAs) =====
+    const int q4 = warp & 3;
+    const int lrow = q4 * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
+    uint64_t* mylist = lists + lrow;
+    KnnRowState* st = states + lrow;
+    const int k1 = a.k1;
+    uint32_t it = 0;
+    for (int64_t b = pair; b < nblocks2; b += npairs) {
+      const int64_t row = a.row_begin + b * 256 + (int64_t)rank * 128 + lrow;
+      const bool row_ok = row < a.row_end;
+      st->cnt = 0;
+      st->maxpos = 0;
+      st->maxkey = ~0ull;
+      float thr = INFINITY, thr_dot = -INFINITY;
+      for (int t = 0; t < ntiles; ++t, ++it) {
+        const uint32_t as = it & 1;
+        mbar_wait(tmem_full + 8 * as, (it >> 1) & 1);
+        tc_fence_after();
+        const int64_t col0 = (int64_t)t * NT;
+        const uint32_t acc = lane_addr + as * NT;
+        uint32_t va[32], vb[32];
+        if (a.debug & 1) {
+          tc_fence_before();
+          mbar_arrive_leader(tmem_empty + 8 * as);
+          continue;
+        }
+        tmem_ld32(acc, va);
+        tmem_ld_wait_regs32(va);
+#pragma unroll 1
+        for (int c0 = 0; c0 < NT; c0 += 64) {
+          tmem_ld32(acc + c0 + 32, vb);
+          knn_group(va, thr, thr_dot, st, mylist, k1, col0 + c0, a.n);
+          tmem_ld_wait_regs32(vb);
+          if (c0 + 64 < NT) tmem_ld32(acc + c0 + 64, va);
+          knn_group(vb, thr, thr_dot, st, mylist, k1, col0 + c0 + 32, a.n);
+          if (c0 + 64 < NT) tmem_ld_wait_regs32(va);
+        }
+        tc_fence_before();
+        mbar_arrive_leader(tmem_empty + 8 * as);
+      }
+      const int cnt = st->cnt;
+      if (row_ok) {
+        for (int i = 1; i < cnt; ++i) {
+          const uint64_t x = mylist[i * 128];
+          int j = i - 1;
+          while (j >= 0 && mylist[j * 128] > x) {
+            mylist[(j + 1) * 128] = mylist[j * 128];
+            --j;
+          }
+          mylist[(j + 1) * 128] = x;
+        }
+        const int64_t o = (row - a.row_begin) * k1;
+        for (int i = 0; i < k1; ++i) {
+          const uint64_t x = i < cnt ? mylist[i * 128] : 0;
+          a.out_idx[o + i] = i < cnt ? (int32_t)(x & 0xFFFFFFFFu) : -1;
+          a.out_dist[o + i] = i < cnt ? f32_from_ordered((uint32_t)(x >> 32)) : INFINITY;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2sm(tmem, 512);
+}
+
 int make_tmap_f16_rows(CUtensorMap* out, const void* base, int64_t n_rows, int dim, int box_rows) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -515,10 +701,38 @@ static int launch_knn2_t(int sm_count, const KnnArgs& a, cudaStream_t st) {
   return SSW_OK;
 }
 
+// SS / N = 256 variant: needs >= 3 B stages next to the resident A block and the candidate lists
+template <int DIM>
+static int launch_knn3_t(int sm_count, const KnnArgs& a, cudaStream_t st, bool* launched) {
+  *launched = false;
+  const size_t list_bytes = (size_t)a.k1 * 128 * 8 + 128 * sizeof(KnnRowState);
+  const size_t fixed = (size_t)(DIM / 64) * 16384 + list_bytes + tc_smem_slack + 512;
+  if (fixed + 3 * 16384 > 232448) return SSW_OK;
+  const int NS = (int)std::min<size_t>((232448 - fixed) / 16384, 8);
+  CUtensorMap tmap;
+  int rc = make_tmap_f16_rows(&tmap, a.v, a.n, DIM, 128);      // box = 128 rows x 64 fp16 (A block chunk / B half tile)
+  if (rc) return rc;
+  const int64_t nblocks2 = (a.row_end - a.row_begin + 255) / 256;
+  const int grid = 2 * (int)std::min<int64_t>(sm_count / 2, nblocks2);
+  const size_t smem = fixed + (size_t)NS * 16384;
+  auto kern = knn3_kernel<DIM>;
+  SSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kTcThreads, smem, st>>>(tmap, a, NS);
+  SSW_LAUNCHED();
+  *launched = true;
+  return SSW_OK;
+}
+
 static int launch_knn(int sm_count, const KnnArgs& a, int dim, cudaStream_t st) {
   // CTA pairs (tcgen05 cta_group::2) for the dims whose A block leaves room for two 128-column accumulators;
   // SSW_KNN_1CTA=1 selects the single-CTA kernel (kept for dim 768 and as a cross-check)
   static const bool one_cta = [] { const char* e = getenv("SSW_KNN_1CTA"); return e && e[0] == '1'; }();
+  static const bool ts_pairs = [] { const char* e = getenv("SSW_KNN_TS"); return e && e[0] == '1'; }();
+  if (!one_cta && !ts_pairs && (dim == 256 || dim == 512)) {
+    bool launched = false;
+    const int rc = dim == 256 ? launch_knn3_t<256>(sm_count, a, st, &launched) : launch_knn3_t<512>(sm_count, a, st, &launched);
+    if (rc || launched) return rc;
+  }
   if (!one_cta) {
     if (dim == 256) return launch_knn2_t<256>(sm_count, a, st);
     if (dim == 512) return launch_knn2_t<512>(sm_count, a, st);
