@@ -44,10 +44,11 @@ q = torch.from_numpy(synth.unit_queries(64, 512, 1)).cuda()
 rng = np.random.default_rng(0)
 bits = db.build_exclude_bits([rng.choice(250000, size=50, replace=False) for _ in range(64)], 64)
 gb = db.n_rows * 512 * 2 / 1e9
-db.set_scan_mode(1)
 q1, b1 = q[:1].contiguous(), bits[:1]
-if "K1" in WHAT:
-    run("K1", lambda: db.scan_topk_device(q1, 50, b1), gb)
-db.set_scan_mode(2)
-if "K2" in WHAT:
-    run("K2", lambda: db.scan_topk_device(q, 50, bits), gb, iters=600)
+for what in WHAT:
+    if what == "K1":
+        db.set_scan_mode(1)
+        run("K1", lambda: db.scan_topk_device(q1, 50, b1), gb, iters=400)
+    elif what == "K2":
+        db.set_scan_mode(2)
+        run("K2", lambda: db.scan_topk_device(q, 50, bits), gb, iters=600)

@@ -137,7 +137,6 @@ static int build_layout(ssw_db* db, const int32_t* dbidx_per_row, std::vector<in
     std::stable_sort(perm.begin(), perm.end(),
                      [&](int64_t x, int64_t y) { return dbidx_per_row[x] < dbidx_per_row[y]; });
   }
-  std::vector<int32_t> img_of_row(n + 1);
   std::vector<int32_t> img_dbidx;
   std::vector<int64_t> row_ptr;
   int32_t prev = 0;
@@ -148,9 +147,7 @@ static int build_layout(ssw_db* db, const int32_t* dbidx_per_row, std::vector<in
       row_ptr.push_back(i);
       prev = d;
     }
-    img_of_row[i] = (int32_t)img_dbidx.size() - 1;
   }
-  img_of_row[n] = -1;
   row_ptr.push_back(n);
   // one bit per device row: last row of its image (read by the batched scan instead of the 4-byte ids)
   std::vector<uint32_t> last_bits((size_t)(n / 32) + 8, 0u);
@@ -177,13 +174,11 @@ static int build_layout(ssw_db* db, const int32_t* dbidx_per_row, std::vector<in
     db->max_cta_images = std::max<int64_t>(db->max_cta_images, part[(c + 1) * kScanWarps] - part[c * kScanWarps]);
 
   int rc;
-  if ((rc = dev_alloc(&db->d_img_of_row, (size_t)n + 1))) return rc;
   if ((rc = dev_alloc(&db->d_row_ptr, row_ptr.size()))) return rc;
   if ((rc = dev_alloc(&db->d_img_dbidx, img_dbidx.size()))) return rc;
   if ((rc = dev_alloc(&db->d_part, part.size()))) return rc;
   if ((rc = dev_alloc(&db->d_last_bits, last_bits.size()))) return rc;
   SSW_CUDA(cudaMemcpy(db->d_last_bits, last_bits.data(), last_bits.size() * 4, cudaMemcpyHostToDevice));
-  SSW_CUDA(cudaMemcpy(db->d_img_of_row, img_of_row.data(), (n + 1) * 4, cudaMemcpyHostToDevice));
   SSW_CUDA(cudaMemcpy(db->d_row_ptr, row_ptr.data(), row_ptr.size() * 8, cudaMemcpyHostToDevice));
   if (!img_dbidx.empty())
     SSW_CUDA(cudaMemcpy(db->d_img_dbidx, img_dbidx.data(), img_dbidx.size() * 4, cudaMemcpyHostToDevice));
@@ -254,7 +249,6 @@ int ssw_db_destroy(ssw_db* db) {
   cudaSetDevice(db->device);
   if (db->stream) cudaStreamSynchronize(db->stream);
   cudaFree(db->d_vecs);
-  cudaFree(db->d_img_of_row);
   cudaFree(db->d_row_ptr);
   cudaFree(db->d_img_dbidx);
   cudaFree(db->d_orig_row);

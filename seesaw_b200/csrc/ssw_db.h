@@ -17,7 +17,6 @@ struct ssw_db {
 
   // HBM layout (SURVEY.md §7 "row order is not guaranteed grouped by image"):
   void* d_vecs = nullptr;          // [n_rows, dim] stored type, rows STABLY grouped by image
-  int32_t* d_img_of_row = nullptr; // [n_rows + 1] local image index of each device row (+ sentinel -1)
   int64_t* d_row_ptr = nullptr;    // [n_images + 1] CSR over device rows
   int32_t* d_img_dbidx = nullptr;  // [n_images] dbidx of each local image, ascending
   int64_t* d_orig_row = nullptr;   // [n_rows] device row -> original local row; NULL when identity

@@ -26,7 +26,7 @@ namespace ssw {
 
 struct Scan1Args {
   const void* vecs;
-  const int32_t* img_of_row;
+  const uint32_t* last_bits;  // bit r set <=> device row r is the last row of its image
   const int64_t* row_ptr;
   const int32_t* img_dbidx;
   const int64_t* orig_row;   // may be null (identity)
@@ -257,16 +257,21 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scan1_kernel(const Scan1Ar
     for (int64_t t = 0; t < (ntiles < (int64_t)kStages ? ntiles : (int64_t)kStages); ++t) issue(t);
   }
 
-  int cur_img = -1;
-  uint64_t cur_key = 0;
+  // Segmented max without per-row broadcasts: after the butterfly the 32/RT lanes of group r all hold
+  // row r's score; every lane keeps the running (max, row) of ITS group's rows of the image being
+  // walked, and only when an image ends (warp-uniform, from the boundary bitmap) and some lane's
+  // running max reaches the threshold are the groups combined (3 shuffle rounds) and the image offered.
+  constexpr int LPR = Cfg::LANES_PER_ROW;
+  const int my_r = lane / LPR;                 // row of the tile this lane's group holds
+  float run_m = -INFINITY;
+  uint32_t run_row = 0;                        // device row of run_m
+  int cur_img = img0;
   uint64_t g_cached = 0;
 
   auto emit = [&](int img, uint64_t key) {
-
-    // key carries the LOCAL device row; quick reject on the score half first
-    // Lanes may arrive here at different times (no reconvergence guarantee after the lane-0
-    // blocks above), and *L.thr changes under other warps' inserts: take lane 0's view so the
-    // whole warp makes ONE decision before the warp-collective insert.
+    // key carries the LOCAL device row; quick reject on the score half first.
+    // *L.thr changes under other warps' inserts: take lane 0's view so the whole warp makes ONE
+    // decision before the warp-collective insert.
     uint64_t thr = *L.thr;
     thr = thr > g_cached ? thr : g_cached;
     thr = shfl_u64(thr, 0);
@@ -279,15 +284,33 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scan1_kernel(const Scan1Ar
     list_insert(L, a.k, lane, key, a.img_dbidx[img], a.g_thr);
   };
 
+  // boundary bits of the next tile, fetched one tile ahead (2 words cover any alignment of 8 rows)
+  uint32_t wb0 = 0, wb1 = 0;
+  if (MODE == 0 && ntiles > 0) {
+    const uint32_t* p = a.last_bits + (r_begin >> 5);
+    wb0 = __ldg(p);
+    wb1 = __ldg(p + 1);
+  }
+
   for (int64_t t = 0; t < ntiles; ++t) {
     const int s = (int)(t % kStages);
     const uint32_t parity = (uint32_t)((t / kStages) & 1);
     const int64_t row0 = r_begin + t * RT;                 // device row of the tile's first row
     const int rows_here = (int)(nrows - t * RT < (int64_t)RT ? nrows - t * RT : (int64_t)RT);
-    int my_img = -1;
+    uint32_t ends = 0;
+    float thr_f = -INFINITY;
     if (MODE == 0) {
-      if (lane < rows_here) my_img = a.img_of_row[row0 + lane];
+      ends = __funnelshift_r(wb0, wb1, (int)(row0 & 31)) & ((1u << rows_here) - 1u);
+      if (t + 1 < ntiles) {
+        const uint32_t* p = a.last_bits + ((row0 + RT) >> 5);
+        wb0 = __ldg(p);
+        wb1 = __ldg(p + 1);
+      }
       if ((t & 7) == 0) g_cached = ld_relaxed_u64(a.g_thr);
+      // score an image must reach to matter (possibly stale, i.e. low: the exact test is in emit)
+      uint64_t th = *L.thr;
+      th = th > g_cached ? th : g_cached;
+      thr_f = th == 0 ? -INFINITY : key_score(th);
     }
     mbar_wait(bar0 + 8 * s, parity);
 
@@ -331,25 +354,46 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scan1_kernel(const Scan1Ar
         a.scores_out[orow] = total;
       }
     } else {
-#pragma unroll
-      for (int r = 0; r < RT; ++r) {
-        if (r < rows_here) {     // warp-uniform
-          const float sc = __shfl_sync(0xffffffffu, total, r * Cfg::LANES_PER_ROW);
-          const int img = __shfl_sync(0xffffffffu, my_img, r);
-          const uint64_t key = make_key(sc, (uint32_t)(row0 + r));
-          if (img != cur_img) {
-            if (cur_img >= 0) emit(cur_img, cur_key);
-            cur_img = img;
-            cur_key = key;
-          } else {
-            cur_key = key > cur_key ? key : cur_key;
+      const bool valid = my_r < rows_here;
+      const uint32_t my_row = (uint32_t)(row0 + my_r);
+      if (ends == 0) {            // warp-uniform fast path: no image ends inside this tile
+        if (valid && total > run_m) {
+          run_m = total;
+          run_row = my_row;
+        }
+      } else {
+        int lo = 0;
+        uint32_t e = ends;
+        do {                      // warp-uniform walk over the image ends of the tile
+          const int p = __ffs(e) - 1;
+          e &= e - 1;
+          const float x = (valid && my_r >= lo && my_r <= p) ? total : -INFINITY;
+          if (x > run_m) {
+            run_m = x;
+            run_row = my_row;
           }
+          if (__any_sync(0xffffffffu, run_m >= thr_f)) {
+            // (score desc, row asc) max over the RT groups; empty groups carry key 0
+            uint64_t key = run_m > -INFINITY ? make_key(run_m, run_row) : 0ull;
+#pragma unroll
+            for (int m = LPR; m < 32; m <<= 1) {
+              const uint64_t o = shfl_xor_u64(key, m);
+              key = o > key ? o : key;
+            }
+            if (key != 0) emit(cur_img, key);
+          }
+          run_m = -INFINITY;
+          ++cur_img;
+          lo = p + 1;
+        } while (e);
+        if (valid && my_r >= lo && total > run_m) {
+          run_m = total;
+          run_row = my_row;
         }
       }
     }
   }
   if (MODE == 0) {
-    if (cur_img >= 0) emit(cur_img, cur_key);
     __syncthreads();
     const int cnt = s_ctrl[0];
     for (int i = threadIdx.x; i < a.k; i += blockDim.x) {
@@ -397,7 +441,7 @@ int launch_scan1(ssw_db* db, const float* d_query, int k, const uint32_t* d_excl
                  int32_t* d_list_dbidx, uint64_t* d_gthr, cudaStream_t st) {
   Scan1Args a{};
   a.vecs = db->d_vecs;
-  a.img_of_row = db->d_img_of_row;
+  a.last_bits = db->d_last_bits;
   a.row_ptr = db->d_row_ptr;
   a.img_dbidx = db->d_img_dbidx;
   a.orig_row = db->d_orig_row;
@@ -416,7 +460,7 @@ int launch_scan1(ssw_db* db, const float* d_query, int k, const uint32_t* d_excl
 int launch_score_all(ssw_db* db, const float* d_query, float* d_out, cudaStream_t st) {
   Scan1Args a{};
   a.vecs = db->d_vecs;
-  a.img_of_row = db->d_img_of_row;
+  a.last_bits = db->d_last_bits;
   a.row_ptr = db->d_row_ptr;
   a.img_dbidx = db->d_img_dbidx;
   a.orig_row = db->d_orig_row;
