@@ -89,10 +89,11 @@ int ssw_scan_topk(ssw_db* db, const float* queries, int nq, int k,
  * All pointers are DEVICE pointers on db's device; `stream` is a cudaStream_t (0 = default).
  * exclude_bits: [nq, ssw_exclude_words(db)] uint32 bitmaps over LOCAL image indices, or NULL.
  * out_key [nq,k] uint64 = (order-preserving score bits << 32) | ~global_row, 0 for empty slots,
- * out_dbidx [nq,k] int32.  Asynchronous: returns after enqueueing. */
+ * out_dbidx [nq,k] int32; optional decoded outputs d_out_score / d_out_row [nq,k], d_out_count [nq]
+ * (each may be NULL).  Asynchronous: returns after enqueueing. */
 int ssw_scan_topk_device(ssw_db* db, const float* d_queries, int nq, int k,
                          const uint32_t* d_exclude_bits, uint64_t* d_out_key, int32_t* d_out_dbidx,
-                         void* stream);
+                         float* d_out_score, int64_t* d_out_row, int32_t* d_out_count, void* stream);
 int ssw_exclude_words(const ssw_db* db, int64_t* words_per_query);
 /* Build the bitmaps on the device from id lists already in device memory. */
 int ssw_exclude_build_device(ssw_db* db, const int32_t* d_exclude_dbidx, const int64_t* d_exclude_offsets,

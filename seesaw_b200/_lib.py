@@ -47,7 +47,7 @@ SIGNATURES = {
     "ssw_db_info": (C.c_int, [_p, _i64p, _i64p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ssw_db_vectors_device": (C.c_int, [_p, C.POINTER(_p)]),
     "ssw_scan_topk": (C.c_int, [_p, _p, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p]),
-    "ssw_scan_topk_device": (C.c_int, [_p, _p, C.c_int, C.c_int, _p, _p, _p, _p]),
+    "ssw_scan_topk_device": (C.c_int, [_p, _p, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p, _p]),
     "ssw_exclude_words": (C.c_int, [_p, _i64p]),
     "ssw_exclude_build_device": (C.c_int, [_p, _p, _p, C.c_int, C.c_int64, _p, _p]),
     "ssw_merge_topk_device": (C.c_int, [C.c_int, _p, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p]),

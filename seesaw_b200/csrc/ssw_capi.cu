@@ -536,13 +536,14 @@ int ssw_xchg_destroy(int device, void* d_buf) {
 }
 
 int ssw_scan_topk_device(ssw_db* db, const float* d_queries, int nq, int k, const uint32_t* d_exclude_bits,
-                         uint64_t* d_out_key, int32_t* d_out_dbidx, void* stream) {
+                         uint64_t* d_out_key, int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row,
+                         int32_t* d_out_count, void* stream) {
   SSW_REQUIRE(db != nullptr && d_queries != nullptr, "null argument");
   SSW_REQUIRE(nq > 0, "nq must be positive");
   SSW_REQUIRE(k > 0 && k <= SSW_MAX_TOPK, "k must be in [1, SSW_MAX_TOPK]");
   SSW_CUDA(cudaSetDevice(db->device));
-  return scan_topk_impl(db, d_queries, nq, k, d_exclude_bits, d_out_key, d_out_dbidx, nullptr, nullptr, nullptr,
-                        (cudaStream_t)stream);
+  return scan_topk_impl(db, d_queries, nq, k, d_exclude_bits, d_out_key, d_out_dbidx, d_out_score, d_out_row,
+                        d_out_count, (cudaStream_t)stream);
 }
 
 int ssw_merge_topk_device(int device, const uint64_t* d_keys, const int32_t* d_dbidx, int n_lists, int nq, int k,

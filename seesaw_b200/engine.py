@@ -141,20 +141,30 @@ class PatchDatabase:
                                            int(offsets[-1]), C.c_void_p(bits.data_ptr()), self._stream(stream)))
         return bits
 
-    def scan_topk_device(self, d_queries, k, d_exclude_bits=None, out_key=None, out_dbidx=None, stream=None):
+    def scan_topk_device(self, d_queries, k, d_exclude_bits=None, out_key=None, out_dbidx=None, stream=None,
+                         decoded=False):
         """d_queries: float32 CUDA tensor [nq, dim].  Returns (keys [nq,k] int64 holding the uint64
-        keys, dbidx int32 [nq,k]); asynchronous."""
+        keys, dbidx int32 [nq,k]), or with ``decoded=True`` the dict key/dbidx/score/row/count;
+        asynchronous."""
         import torch
         nq = d_queries.shape[0]
         assert d_queries.is_cuda and d_queries.dtype == torch.float32 and d_queries.is_contiguous()
+        dev = d_queries.device
         if out_key is None:
-            out_key = torch.empty((nq, k), dtype=torch.int64, device=d_queries.device)
+            out_key = torch.empty((nq, k), dtype=torch.int64, device=dev)
         if out_dbidx is None:
-            out_dbidx = torch.empty((nq, k), dtype=torch.int32, device=d_queries.device)
+            out_dbidx = torch.empty((nq, k), dtype=torch.int32, device=dev)
         bits = None if d_exclude_bits is None else C.c_void_p(d_exclude_bits.data_ptr())
+        score = row = count = None
+        if decoded:
+            score = torch.empty((nq, k), dtype=torch.float32, device=dev)
+            row = torch.empty((nq, k), dtype=torch.int64, device=dev)
+            count = torch.empty((nq,), dtype=torch.int32, device=dev)
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
         check(lib.ssw_scan_topk_device(self._h, C.c_void_p(d_queries.data_ptr()), nq, int(k), bits,
-                                       C.c_void_p(out_key.data_ptr()), C.c_void_p(out_dbidx.data_ptr()),
-                                       self._stream(stream)))
+                                       p(out_key), p(out_dbidx), p(score), p(row), p(count), self._stream(stream)))
+        if decoded:
+            return dict(key=out_key, dbidx=out_dbidx, score=score, row=row, count=count)
         return out_key, out_dbidx
 
     def score_all_device(self, d_query, out=None, stream=None):

@@ -159,10 +159,9 @@ class ShardedPatchDatabase:
             d_exclude_bits = self.local.build_exclude_bits(exclude, nq)
         if self._xchg is not None and nq <= self._xchg["nq_cap"] and k <= self._xchg["k_cap"]:
             return self._scan_fused(d_queries, k, d_exclude_bits)
-        keys, dbidx = self.local.scan_topk_device(d_queries, k, d_exclude_bits)
         if self.world_size == 1 and self._merge is None:
-            from .engine import merge_topk_device
-            return merge_topk_device(keys.unsqueeze(0), dbidx.unsqueeze(0), k)
+            return self.local.scan_topk_device(d_queries, k, d_exclude_bits, decoded=True)
+        keys, dbidx = self.local.scan_topk_device(d_queries, k, d_exclude_bits)
         w = self.world_size
         all_k = torch.empty((w * nq, k), dtype=keys.dtype, device=keys.device)
         all_d = torch.empty((w * nq, k), dtype=dbidx.dtype, device=dbidx.device)

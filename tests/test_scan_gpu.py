@@ -266,3 +266,53 @@ def test_merge_kernel_vs_host_statement(eng, n_lists, nq, k):
     assert (out["count"].cpu().numpy() == (hk != 0).sum(axis=1)).all()
     got = out["score"].cpu().numpy()
     assert ((got == s) | (np.isinf(got) & np.isinf(s))).all()
+
+
+# ------------------------------------------------------------------ more edge cases
+def test_max_topk_and_ragged_images(eng):
+    """k at the ABI limit (2048) on the streaming kernel, images from 1 to 300 rows, k > #images."""
+    rng = np.random.default_rng(5)
+    counts = rng.integers(1, 301, size=3000).astype(np.int64)
+    counts[::50] = 1
+    dbidx = synth.dbidx_of_rows(counts, 0, 7)
+    n = int(counts.sum())
+    vecs = synth.synth_rows(0, n, 256, 29, "lattice", np.float32)
+    q = synth.lattice_queries(2, 256, 30)
+    db = eng.PatchDatabase.from_arrays(vecs, dbidx, store="f16")
+    ids = np.unique(dbidx)
+    for k in (2048, 3000 + 5):
+        if k > 2048:
+            with pytest.raises(Exception):
+                db.scan_topk(q, k)
+            continue
+        r = db.scan_topk(q, k, exclude=[ids[::3], None])
+        for qi, e in enumerate([ids[::3], None]):
+            o = orc.query_prelim(vecs, dbidx, q[qi], k, exclude=e)
+            kk = len(o["dbidx"])
+            assert r["count"][qi] == kk
+            assert (r["dbidx"][qi, :kk] == o["dbidx"]).all() and (r["row"][qi, :kk] == o["best_row"]).all()
+            assert (r["score"][qi, :kk] == o["max_score"]).all()
+    db.close()
+
+
+def test_empty_database_and_tiny_batches(eng):
+    db = eng.PatchDatabase.from_arrays(np.zeros((0, 512), np.float32), np.zeros(0, np.int32), store="f16")
+    assert db.n_rows == 0 and db.n_images == 0
+    q = synth.lattice_queries(3, 512, 1)
+    for mode in (1, 2):
+        db.set_scan_mode(mode)
+        r = db.scan_topk(q, 5, exclude=[[1, 2], None, []])
+        assert (r["count"] == 0).all() and (r["dbidx"] == -1).all()
+    assert db.score_all(q[0]).shape == (0,)
+    db.close()
+    # one row in total; batched kernel with k = 64 (its limit) and nq = 1
+    v = synth.synth_rows(0, 1, 512, 2, "lattice", np.float32)
+    db = eng.PatchDatabase.from_arrays(v, np.array([9], np.int32), store="f16")
+    db.set_scan_mode(2)
+    r = db.scan_topk(q[:1], 64)
+    assert r["count"][0] == 1 and r["dbidx"][0, 0] == 9 and r["row"][0, 0] == 0 and r["score"][0, 0] == (v @ q[0])[0]
+    with pytest.raises(Exception):
+        db.scan_topk(q[:1], 65)          # beyond the batched kernel's list length: forced mode must refuse
+    db.set_scan_mode(0)
+    assert db.scan_topk(q[:1], 65)["count"][0] == 1      # auto mode falls back to the streaming kernel
+    db.close()
