@@ -136,6 +136,17 @@ int ssw_set_scan_mode(ssw_db* db, int mode);
 int ssw_score_all(ssw_db* db, const float* query, float* out_scores);
 int ssw_score_all_device(ssw_db* db, const float* d_query, float* d_out_scores, void* stream);
 
+/* ---- top-k images from a caller-supplied score per row ---------------------------------
+ * Replaces _get_top_dbidxs when the scores are not a dot product with the stored vectors: label
+ * propagation over the kNN graph (KnnProp2.next_batch, loops/graph_based.py:97-99, calls
+ * _get_top_dbidxs(vec_idxs, scores, ...) of multiscale_index.py:189-199 on ALL sorted rows).
+ * scores[n_rows] fp32 in ORIGINAL row order; row_mask[n_rows] (0 = row absent, e.g. labeled rows;
+ * NULL = all present); exclude_dbidx[n_exclude] image ids to drop.  Same ranking and outputs as
+ * ssw_scan_topk for one query: per-image max, ties to the lower row, best k images. */
+int ssw_topk_from_scores(ssw_db* db, const float* scores, const uint8_t* row_mask, int k,
+                         const int32_t* exclude_dbidx, int64_t n_exclude, int32_t* out_dbidx,
+                         float* out_score, int64_t* out_row, int32_t* out_count);
+
 /* ---- exact kNN graph -------------------------------------------------------------------
  * Replaces the matmul + row argsort of compute_exact_knn (knn_graph.py:170-182):
  * for rows [row_begin,row_end) of vectors [n, dim]: the k1 = min(n_neighbors+1, n) columns j

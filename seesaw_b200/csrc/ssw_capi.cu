@@ -617,6 +617,59 @@ int ssw_scan_topk(ssw_db* db, const float* queries, int nq, int k, const int32_t
   return SSW_OK;
 }
 
+int ssw_topk_from_scores(ssw_db* db, const float* scores, const uint8_t* row_mask, int k, const int32_t* exclude_dbidx,
+                         int64_t n_exclude, int32_t* out_dbidx, float* out_score, int64_t* out_row, int32_t* out_count) {
+  SSW_REQUIRE(db != nullptr && (scores != nullptr || db->n_rows == 0), "null argument");
+  SSW_REQUIRE(k > 0 && k <= SSW_MAX_TOPK, "k must be in [1, SSW_MAX_TOPK]");
+  SSW_REQUIRE(n_exclude >= 0 && (n_exclude == 0 || exclude_dbidx != nullptr), "bad exclude list");
+  SSW_CUDA(cudaSetDevice(db->device));
+  auto up16 = [](size_t x) { return (x + 15) / 16 * 16; };
+  const int64_t n = db->n_rows;
+  const int64_t n_lists = std::max<int64_t>(1, (db->n_images + k - 1) / k), n_padded = n_lists * k;
+  // device block: scores | mask | offsets | ids | bitmap | image keys | image dbidx | outputs
+  const size_t sc_b = up16((size_t)n * 4), mk_b = row_mask ? up16((size_t)n) : 0, off_b = 16, ids_b = up16((size_t)n_exclude * 4);
+  const size_t bits_b = n_exclude ? up16((size_t)db->excl_words * 4) : 0;
+  const size_t key_b = up16((size_t)n_padded * 8), id_b = up16((size_t)n_padded * 4);
+  const size_t o_db = up16((size_t)k * 4), o_sc = up16((size_t)k * 4), o_row = up16((size_t)k * 8), o_cnt = 16;
+  const size_t in_b = sc_b + mk_b + off_b + ids_b, out_b = o_db + o_sc + o_row + o_cnt;
+  int rc = ensure_stage(db, in_b + bits_b + key_b + id_b + out_b, std::max(off_b + ids_b, out_b));
+  if (rc) return rc;
+  uint8_t* d = static_cast<uint8_t*>(db->d_stage);
+  uint8_t* h = static_cast<uint8_t*>(db->h_stage);
+  cudaStream_t st = db->stream;
+  if (n) SSW_CUDA(cudaMemcpyAsync(d, scores, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  if (row_mask && n) SSW_CUDA(cudaMemcpyAsync(d + sc_b, row_mask, (size_t)n, cudaMemcpyHostToDevice, st));
+  uint32_t* d_bits = nullptr;
+  if (n_exclude) {
+    int64_t* off = reinterpret_cast<int64_t*>(h);
+    off[0] = 0;
+    off[1] = n_exclude;
+    memcpy(h + off_b, exclude_dbidx, (size_t)n_exclude * 4);
+    SSW_CUDA(cudaMemcpyAsync(d + sc_b + mk_b, h, off_b + ids_b, cudaMemcpyHostToDevice, st));
+    d_bits = reinterpret_cast<uint32_t*>(d + in_b);
+    rc = launch_exclude_build(db, reinterpret_cast<const int32_t*>(d + sc_b + mk_b + off_b),
+                              reinterpret_cast<const int64_t*>(d + sc_b + mk_b), 1, d_bits, st);
+    if (rc) return rc;
+  }
+  uint64_t* d_keys = reinterpret_cast<uint64_t*>(d + in_b + bits_b);
+  int32_t* d_ids = reinterpret_cast<int32_t*>(d + in_b + bits_b + key_b);
+  rc = launch_image_max(db, reinterpret_cast<const float*>(d), row_mask ? d + sc_b : nullptr, d_bits, n_padded, d_keys, d_ids, st);
+  if (rc) return rc;
+  uint8_t* d_out = d + in_b + bits_b + key_b + id_b;
+  rc = launch_merge(d_keys, d_ids, (int)n_lists, k, n_padded, 1, k, nullptr, nullptr, reinterpret_cast<int32_t*>(d_out),
+                    reinterpret_cast<float*>(d_out + o_db), reinterpret_cast<int64_t*>(d_out + o_db + o_sc),
+                    reinterpret_cast<int32_t*>(d_out + o_db + o_sc + o_row), st);
+  if (rc) return rc;
+  SSW_CUDA(cudaStreamSynchronize(st));      // the uploads above read pageable host memory: finish before h is reused
+  SSW_CUDA(cudaMemcpyAsync(h, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  SSW_CUDA(cudaStreamSynchronize(st));
+  if (out_dbidx) memcpy(out_dbidx, h, (size_t)k * 4);
+  if (out_score) memcpy(out_score, h + o_db, (size_t)k * 4);
+  if (out_row) memcpy(out_row, h + o_db + o_sc, (size_t)k * 8);
+  if (out_count) memcpy(out_count, h + o_db + o_sc + o_row, 4);
+  return SSW_OK;
+}
+
 int ssw_score_all_device(ssw_db* db, const float* d_query, float* d_out_scores, void* stream) {
   SSW_REQUIRE(db != nullptr && d_query != nullptr && d_out_scores != nullptr, "null argument");
   SSW_CUDA(cudaSetDevice(db->device));

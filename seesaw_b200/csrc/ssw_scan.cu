@@ -842,6 +842,45 @@ int launch_exclude_build(ssw_db* db, const int32_t* d_ids, const int64_t* d_offs
 }
 
 // ------------------------------------------------------------------------------------------
+// K5: per-image best key from a caller-supplied score per row (scores that are not a dot product:
+// label propagation, KnnProp2.next_batch -> _get_top_dbidxs, seesaw/loops/graph_based.py:97-99).
+// One thread per image walks the image's rows; the top-k over the image keys is K4's job.
+// ------------------------------------------------------------------------------------------
+__global__ void image_max_kernel(const float* __restrict__ scores, const uint8_t* __restrict__ row_mask,
+                                 const int64_t* __restrict__ row_ptr, const int64_t* __restrict__ orig_row,
+                                 const int32_t* __restrict__ img_dbidx, const uint32_t* __restrict__ excl,
+                                 int64_t row_base, int64_t n_images, int64_t n_padded, uint64_t* __restrict__ keys_out,
+                                 int32_t* __restrict__ dbidx_out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_padded; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t best = 0;
+    int32_t id = -1;
+    if (i < n_images && !(excl && ((excl[i >> 5] >> (i & 31)) & 1u))) {
+      id = img_dbidx[i];
+      for (int64_t r = row_ptr[i]; r < row_ptr[i + 1]; ++r) {
+        const int64_t o = orig_row ? orig_row[r] : r;
+        if (row_mask && !row_mask[o]) continue;
+        const float sc = scores[o];
+        if (sc != sc) continue;                       // NaN never ranks
+        const uint64_t key = make_key(sc, (uint32_t)(row_base + o));
+        best = key > best ? key : best;
+      }
+    }
+    keys_out[i] = best;
+    dbidx_out[i] = best ? id : -1;
+  }
+}
+
+int launch_image_max(ssw_db* db, const float* d_scores, const uint8_t* d_row_mask, const uint32_t* d_excl,
+                     int64_t n_padded, uint64_t* d_keys, int32_t* d_dbidx, cudaStream_t st) {
+  if (n_padded == 0) return SSW_OK;
+  const int grid = (int)std::min<int64_t>((n_padded + 255) / 256, 148 * 16);
+  image_max_kernel<<<grid, 256, 0, st>>>(d_scores, d_row_mask, db->d_row_ptr, db->d_orig_row, db->d_img_dbidx, d_excl,
+                                         db->row_base, db->n_images, n_padded, d_keys, d_dbidx);
+  SSW_LAUNCHED();
+  return SSW_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // synthetic rows (bit-identical to seesaw_b200/synth.py) and dtype conversion
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t splitmix(uint64_t z) {

@@ -116,6 +116,21 @@ class PatchDatabase:
                                 ptr(out_score), ptr(out_row), ptr(out_count)))
         return dict(dbidx=out_dbidx, score=out_score, row=out_row, count=out_count)
 
+    def topk_from_scores(self, scores, k, exclude=None, row_mask=None):
+        """Per-image max of a caller-supplied score per row (original order) + exclusion + top-k: the
+        ``_get_top_dbidxs`` step of KnnProp2.next_batch (loops/graph_based.py:97-99).  ``row_mask``: rows
+        that take part (default all).  Returns dict(dbidx, score, row) trimmed to the count."""
+        sc = np.ascontiguousarray(np.asarray(scores, dtype=np.float32).reshape(-1))
+        assert sc.shape[0] == self.n_rows
+        mask = None if row_mask is None else np.ascontiguousarray(np.asarray(row_mask).astype(np.uint8).reshape(-1))
+        ids = np.zeros(0, np.int32) if exclude is None else _ids(exclude)
+        out_dbidx, out_score = np.empty(k, np.int32), np.empty(k, np.float32)
+        out_row, cnt = np.empty(k, np.int64), np.zeros(1, np.int32)
+        check(lib.ssw_topk_from_scores(self._h, ptr(sc), ptr(mask), int(k), ptr(ids), len(ids), ptr(out_dbidx),
+                                       ptr(out_score), ptr(out_row), ptr(cnt)))
+        n = int(cnt[0])
+        return dict(dbidx=out_dbidx[:n], score=out_score[:n], row=out_row[:n])
+
     def score_all(self, query):
         q = np.ascontiguousarray(np.asarray(query, dtype=np.float32).reshape(-1))
         assert q.shape[0] == self.dim

@@ -97,6 +97,21 @@ class _GpuIndexMixin:
         """Full score vector in original row order (multiscale_index.py:284-285, coarse_index.py:37-38)."""
         return self.db.score_all(np.asarray(vec, dtype=np.float32).reshape(-1))
 
+    def top_dbidxs(self, *, vec_idxs, scores, exclude=None, topk):
+        """``_get_top_dbidxs(vec_idxs=, scores=, vector_meta=, exclude=, topk=)`` (multiscale_index.py:189-199)
+        for scores that did not come from this index's scan — KnnProp2.next_batch passes the rows sorted by
+        label-propagation score (loops/graph_based.py:97-99).  Only the rows in ``vec_idxs`` take part;
+        their order does not matter (the reference's is score-sorted).  Returns DataFrame(dbidx, max_score)."""
+        vec_idxs = np.asarray(vec_idxs, dtype=np.int64).reshape(-1)
+        dense = np.zeros(len(self._dbidx_of_row), np.float32)
+        dense[vec_idxs] = np.asarray(scores, dtype=np.float32).reshape(-1)
+        mask = None
+        if len(vec_idxs) != len(dense):
+            mask = np.zeros(len(dense), np.uint8)
+            mask[vec_idxs] = 1
+        r = self.db.topk_from_scores(dense, int(topk), exclude=as_id_array(exclude), row_mask=mask)
+        return pd.DataFrame({"dbidx": r["dbidx"].astype(np.int64), "max_score": r["score"], "best_row": r["row"]})
+
     def string2vec(self, string: str) -> np.ndarray:
         init_vec = self.embedding.from_string(string=string)
         return init_vec / np.linalg.norm(init_vec)

@@ -316,3 +316,30 @@ def test_empty_database_and_tiny_batches(eng):
     db.set_scan_mode(0)
     assert db.scan_topk(q[:1], 65)["count"][0] == 1      # auto mode falls back to the streaming kernel
     db.close()
+
+
+# ------------------------------------------------------------------ K5: top-k from caller-supplied scores
+@pytest.mark.parametrize("grouped", [True, False])
+def test_topk_from_scores_matches_get_top_dbidxs(eng, grouped):
+    """KnnProp2.next_batch path: arbitrary row scores (many exact ties), a subset of rows, exclusion."""
+    from seesaw_b200.indices import B200MultiscaleIndex
+    rng = np.random.default_rng(11)
+    counts = synth.patches_per_image(5000, 1, 25, 12)
+    meta = synth.synth_vector_meta(counts, 13, dbidx_start=3, dbidx_stride=2)
+    n = int(counts.sum())
+    vecs = synth.synth_rows(0, n, 256, 14, "lattice", np.float32)
+    if not grouped:
+        perm = rng.permutation(n)
+        vecs, meta = vecs[perm], meta.iloc[perm].reset_index(drop=True)
+    idx = B200MultiscaleIndex(embedding=None, vectors=vecs, vector_meta=meta, store="f16")
+    dbidx = meta.dbidx.to_numpy()
+    scores = (rng.integers(-50, 51, size=n) / 8.0).astype(np.float32)          # heavy ties
+    ids = np.unique(dbidx)
+    for frac, ex, k in ((1.0, None, 50), (0.7, ids[::4], 50), (0.05, ids[:100], 2000), (1.0, ids, 10)):
+        rows = np.sort(rng.choice(n, size=int(n * frac), replace=False)) if frac < 1 else np.arange(n)
+        order = rows[np.argsort(-scores[rows], kind="stable")]                  # what top_k(k=None) hands over
+        got = idx.top_dbidxs(vec_idxs=order, scores=scores[order], exclude=ex, topk=k)
+        d, s, r = orc.get_top_dbidxs(order, scores[order], dbidx, ex, k)
+        assert len(got) == len(d)
+        assert (got.dbidx.values == d).all() and (got.max_score.values == s).all() and (got.best_row.values == r).all()
+    idx.close()
