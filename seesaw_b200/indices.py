@@ -82,6 +82,13 @@ class _GpuIndexMixin:
         self.device = device
         self.store = store
         self.db = PatchDatabase.from_arrays(self.vectors, dbidx.astype(np.int32), store=store, device=device)
+        self._batcher = None
+        # stage-1 scores equal what a host rescoring of self.vectors would give (up to summation order)
+        # exactly when the HBM copy holds the same values: fp32 storage, or fp16-representable data
+        v = self.vectors
+        self._store_exact = store in ("f32", "fp32", "float32") or v.dtype == np.float16 or bool(
+            (v[: min(len(v), 4096)].astype(np.float16).astype(np.float32) == v[: min(len(v), 4096)]).all()
+            and (v.astype(np.float16).astype(np.float32) == v).all())
         # host CSR over ORIGINAL rows: rows of image i are _rows_sorted[_starts[i]:_starts[i+1]], ascending
         order = np.argsort(self._dbidx_of_row, kind="stable")
         sorted_ids = self._dbidx_of_row[order]
@@ -92,6 +99,18 @@ class _GpuIndexMixin:
     def _rows_of(self, dbidx):
         i = np.searchsorted(self._img_ids, dbidx)
         return self._rows_sorted[self._starts[i]:self._starts[i + 1]]
+
+    def attach_batcher(self, batcher):
+        """Route stage-1 scans through a :class:`seesaw_b200.service.ScanBatcher` shared by concurrent
+        sessions (one GPU pass per batch instead of one per session)."""
+        self._batcher = batcher
+
+    def _scan_one(self, qvec, k, ex):
+        if self._batcher is not None:
+            return self._batcher.scan_topk_one(qvec, k, ex)
+        r = self.db.scan_topk(qvec.reshape(1, -1), k, exclude=[ex])
+        n = int(r["count"][0])
+        return dict(dbidx=r["dbidx"][0, :n], score=r["score"][0, :n], row=r["row"][0, :n])
 
     def score(self, vec):
         """Full score vector in original row order (multiscale_index.py:284-285, coarse_index.py:37-38)."""
@@ -166,10 +185,8 @@ class B200MultiscaleIndex(_GpuIndexMixin, AccessMethod):
         if k == 0:
             return pd.DataFrame({"dbidx": np.zeros(0, np.int64), "max_score": np.zeros(0, np.float32),
                                  "best_row": np.zeros(0, np.int64)})
-        r = self.db.scan_topk(np.asarray(vector, dtype=np.float32).reshape(1, -1), k, exclude=[ex])
-        n = int(r["count"][0])
-        return pd.DataFrame({"dbidx": r["dbidx"][0, :n].astype(np.int64), "max_score": r["score"][0, :n],
-                             "best_row": r["row"][0, :n]})
+        r = self._scan_one(np.asarray(vector, dtype=np.float32).reshape(-1), k, ex)
+        return pd.DataFrame({"dbidx": r["dbidx"].astype(np.int64), "max_score": r["score"], "best_row": r["row"]})
 
     # ---- stage 1 + 2 -----------------------------------------------------------------------
     def query(self, *, vector, vector2=None, topk, shortlist_size, exclude=None, force_exact=False, **kwargs):
@@ -181,6 +198,19 @@ class B200MultiscaleIndex(_GpuIndexMixin, AccessMethod):
                                   force_exact=force_exact)
         if len(cand) == 0:
             return {"dbidxs": np.zeros(0, dtype="int"), "activations": []}
+        agg_method = kwargs.get("agg_method", "plain_score")
+        if agg_method == "plain_score" and vector2 is None and kwargs.get("device_rescore", self._store_exact):
+            # 'plain_score' rescoring recomputes exactly what stage 1 already returned — per image the max
+            # patch score and the first row attaining it (:117-118) — so the shortlist only needs the
+            # reference's final ordering: ascending dbidx, then a stable sort by score (:388-399).
+            by_id = cand.sort_values("dbidx", kind="stable")
+            sc = by_id["max_score"].to_numpy()
+            order = np.argsort(-sc.astype(np.float64), kind="stable")[:topk]
+            rows, ids = by_id["best_row"].to_numpy()[order], by_id["dbidx"].to_numpy()[order]
+            acts = [pd.DataFrame({"x1": [self._meta_cols["x1"][r]], "y1": [self._meta_cols["y1"][r]],
+                                  "x2": [self._meta_cols["x2"][r]], "y2": [self._meta_cols["y2"][r]],
+                                  "dbidx": [d], "score": [s]}) for r, d, s in zip(rows, ids, sc[order])]
+            return {"dbidxs": ids.astype("int"), "activations": acts}
         ids = np.sort(cand["dbidx"].to_numpy())
         groups = [self._rows_of(d) for d in ids]                      # CSR ranges, not an O(N) isin
         rows = np.concatenate(groups)
@@ -245,9 +275,8 @@ class B200CoarseIndex(_GpuIndexMixin, AccessMethod):
             best = np.argsort(-scores, kind="stable")[:topk]
             ret, sc = included[best], scores[best]
         else:
-            r = self.db.scan_topk(np.asarray(vector, dtype=np.float32).reshape(1, -1), topk, exclude=[ex])
-            n = int(r["count"][0])
-            ret, sc = r["dbidx"][0, :n].astype(np.int64), r["score"][0, :n]
+            r = self._scan_one(np.asarray(vector, dtype=np.float32).reshape(-1), topk, ex)
+            ret, sc = r["dbidx"].astype(np.int64), r["score"]
         assert ret.shape[0] == topk and len(set(ret.tolist())) == topk                 # :81-85
         assert np.intersect1d(ret, ex).shape[0] == 0
         acts = [pd.DataFrame.from_records([dict(x1=0, y1=0, x2=224, y2=224, dbidx=d, score=s)])
