@@ -98,8 +98,11 @@ static int ensure_lists(ssw_db* db, int nq, int lists, int k) {
   if (nq > db->gthr_capacity) {
     if (db->d_gthr) cudaFree(db->d_gthr);
     db->gthr_capacity = 0;
-    int rc = dev_alloc(&db->d_gthr, (size_t)nq);
-    if (rc) return rc;
+    // one allocation: nq thresholds (8 B) then nq x grid published bests (4 B), zeroed together per call
+    uint8_t* p = nullptr;
+    SSW_CUDA(cudaMalloc((void**)&p, (size_t)nq * 8 + (size_t)nq * db->scan_grid * 4));
+    db->d_gthr = reinterpret_cast<uint64_t*>(p);
+    db->d_pub1 = reinterpret_cast<uint32_t*>(p + (size_t)nq * 8);
     db->gthr_capacity = nq;
   }
   return SSW_OK;
@@ -455,13 +458,13 @@ static int scan_topk_impl(ssw_db* db, const float* d_queries, int nq, int k, con
       if (rc) return rc;
     }
   } else {
-    SSW_CUDA(cudaMemsetAsync(db->d_gthr, 0, (size_t)nq * 8, st));
+    SSW_CUDA(cudaMemsetAsync(db->d_gthr, 0, (size_t)db->gthr_capacity * 8 + (size_t)db->gthr_capacity * db->scan_grid * 4, st));
     for (int q = 0; q < nq; ++q) {
       prof_begin(db, st);
       rc = launch_scan1(db, d_queries + (size_t)q * db->dim, k,
                         d_exclude_bits ? d_exclude_bits + (size_t)q * db->excl_words : nullptr,
                         db->d_list_keys + (size_t)q * lists * k, db->d_list_dbidx + (size_t)q * lists * k,
-                        db->d_gthr + q, st);
+                        db->d_gthr + q, db->d_pub1 + (size_t)q * db->scan_grid, st);
       prof_end(db, st);
       if (rc) return rc;
     }

@@ -159,6 +159,35 @@ __device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
   uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
   return ((uint64_t)hi << 32) | lo;
 }
+// Pooled lower bound of a query's final k-th best score.  Every CTA publishes the best score it holds
+// (order-preserving bits, 0 = none yet); lane l passes v[m] = value of CTA l + 32m.  The CTAs are split
+// into ngp >= k groups (CTA c in group c mod ngp, ngp a power of two <= 128): the smallest group maximum
+// is a score that ngp distinct images reach (distinct CTAs hold distinct images).  Returns 0 while some
+// group has published nothing.
+template <int VMAX>
+__device__ __forceinline__ uint32_t pooled_group_min(const uint32_t* v, int ngp, int lane) {
+  uint32_t t;
+  if (ngp >= 32) {
+    const int gpl = ngp >> 5;                 // groups per lane: 1, 2 or 4
+    t = 0xFFFFFFFFu;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t g = 0;
+#pragma unroll
+      for (int m = 0; m < VMAX; ++m) g = ((m & (gpl - 1)) == j && v[m] > g) ? v[m] : g;
+      t = (j < gpl && g < t) ? g : t;
+    }
+  } else {
+    t = 0;
+#pragma unroll
+    for (int m = 0; m < VMAX; ++m) t = v[m] > t ? v[m] : t;
+    for (int sft = 16; sft >= ngp; sft >>= 1) {
+      const uint32_t o = __shfl_xor_sync(0xffffffffu, t, sft);
+      t = o > t ? o : t;
+    }
+  }
+  return __reduce_min_sync(0xffffffffu, t);
+}
 #endif  // __CUDACC__
 
 }  // namespace ssw

@@ -32,7 +32,8 @@ struct ssw_db {
   cudaStream_t stream = nullptr;
   uint64_t* d_list_keys = nullptr; // [nq][lists][k] per-CTA candidate lists
   int32_t* d_list_dbidx = nullptr;
-  uint64_t* d_gthr = nullptr;      // [nq] shared lower bound on the k-th best key
+  uint64_t* d_gthr = nullptr;      // [nq] shared lower bound on the k-th best key, followed by
+  uint32_t* d_pub1 = nullptr;      // [nq][grid] best score per CTA of the streaming scan (same allocation)
   size_t list_capacity = 0;        // entries
   int gthr_capacity = 0;
   // staging for the host-pointer API
@@ -59,7 +60,7 @@ void prof_end(ssw_db* db, cudaStream_t st);
 // streaming single-query scan (K1); MODE 0 = fused segmented max + exclusion + top-k lists,
 // MODE 1 = plain score vector (index.score)
 int launch_scan1(ssw_db* db, const float* d_query, int k, const uint32_t* d_excl, uint64_t* d_list_keys,
-                 int32_t* d_list_dbidx, uint64_t* d_gthr, cudaStream_t st);
+                 int32_t* d_list_dbidx, uint64_t* d_gthr, uint32_t* d_pub, cudaStream_t st);
 int launch_score_all(ssw_db* db, const float* d_query, float* d_out, cudaStream_t st);
 // tcgen05 batched scan (K2): one pass for up to 64 queries; fp16 storage, dim 256/512/768, k <= 64
 bool scan_tc_supported(const ssw_db* db, int k);

@@ -36,6 +36,7 @@ struct Scan1Args {
   uint64_t* list_keys;       // [grid][k]
   int32_t* list_dbidx;       // [grid][k]
   uint64_t* g_thr;
+  uint32_t* pub;             // [grid] best score every CTA holds (order-preserving bits), pooled into g_thr
   float* scores_out;
   int64_t row_base;
   int k;
@@ -130,6 +131,8 @@ struct TopkList {
   volatile int* cnt;
   volatile int* minpos;
   int* lock;
+  uint32_t* best;            // best score held (order-preserving bits)
+  uint32_t* pub;             // this CTA's slot of the published bests
 };
 
 __device__ __forceinline__ void list_recompute_min(const TopkList& L, int k, int lane, uint64_t* g_thr) {
@@ -173,6 +176,10 @@ __device__ __forceinline__ void list_insert(const TopkList& L, int k, int lane, 
   const int cnt = __shfl_sync(0xffffffffu, (int)*L.cnt, 0);
   const uint64_t lthr = shfl_u64(*L.thr, 0);
   const int mpos = __shfl_sync(0xffffffffu, (int)*L.minpos, 0);
+  if (lane == 0 && (uint32_t)(key >> 32) > *L.best) {      // a new best of this CTA: let the pooled bound see it
+    *L.best = (uint32_t)(key >> 32);
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(L.pub), "r"((uint32_t)(key >> 32)) : "memory");
+  }
   if (cnt < k) {
     if (lane == 0) {
       L.keys[cnt] = key;
@@ -211,7 +218,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scan1_kernel(const Scan1Ar
   uint64_t* s_mbar = reinterpret_cast<uint64_t*>(
       smem + kScanWarps * kStages * Cfg::STAGE_BYTES + ((a.k * 12 + 15) / 16) * 16);
   uint64_t* s_thr = s_mbar + kScanWarps * kStages;
-  int* s_ctrl = reinterpret_cast<int*>(s_thr + 1);   // cnt, minpos, lock
+  int* s_ctrl = reinterpret_cast<int*>(s_thr + 1);   // cnt, minpos, lock, best
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -219,6 +226,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scan1_kernel(const Scan1Ar
     s_ctrl[0] = 0;
     s_ctrl[1] = 0;
     s_ctrl[2] = 0;
+    s_ctrl[3] = 0;
   }
   const uint32_t ring = smem_u32(ring_base + warp * kStages * Cfg::STAGE_BYTES);
   const uint32_t bar0 = smem_u32(s_mbar + warp * kStages);
@@ -230,7 +238,8 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scan1_kernel(const Scan1Ar
   }
   __syncthreads();
 
-  TopkList L{s_keys, s_dbidx, s_thr, s_ctrl, s_ctrl + 1, s_ctrl + 2};
+  TopkList L{s_keys, s_dbidx, s_thr, s_ctrl, s_ctrl + 1, s_ctrl + 2, reinterpret_cast<uint32_t*>(s_ctrl + 3),
+             a.pub + blockIdx.x};
 
   // query slice of this lane: chunk c covers elements (c*32 + lane)*EPC ...
   float qr[NQ];
@@ -284,6 +293,12 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scan1_kernel(const Scan1Ar
     list_insert(L, a.k, lane, key, a.img_dbidx[img], a.g_thr);
   };
 
+  constexpr int kPoolV = 6;                    // up to 192 CTAs
+  int pool_ngp = 1;
+  while (pool_ngp < a.k) pool_ngp <<= 1;
+  const bool pool_here = MODE == 0 && blockIdx.x == 0 && warp == 0 && pool_ngp <= 128 && (int)gridDim.x >= pool_ngp &&
+                         (int)gridDim.x <= 32 * kPoolV;
+  uint32_t pool_v[kPoolV] = {0, 0, 0, 0, 0, 0};
   // boundary bits of the next tile, fetched one tile ahead (2 words cover any alignment of 8 rows)
   uint32_t wb0 = 0, wb1 = 0;
   if (MODE == 0 && ntiles > 0) {
@@ -307,6 +322,19 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scan1_kernel(const Scan1Ar
         wb1 = __ldg(p + 1);
       }
       if ((t & 7) == 0) g_cached = ld_relaxed_u64(a.g_thr);
+      if (pool_here) {          // one warp of the grid turns the published bests into the shared bound (see pooled_group_min)
+        if ((t & 7) == 0) {
+#pragma unroll
+          for (int m = 0; m < kPoolV; ++m) {
+            const int c = lane + 32 * m;
+            pool_v[m] = 0u;
+            if (c < (int)gridDim.x) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(pool_v[m]) : "l"(a.pub + c) : "memory");
+          }
+        } else if ((t & 7) == 1) {
+          const uint32_t tp = pooled_group_min<kPoolV>(pool_v, pool_ngp, lane);
+          if (lane == 0 && tp != 0) atomicMax(reinterpret_cast<unsigned long long*>(a.g_thr), (unsigned long long)tp << 32);
+        }
+      }
       // score an image must reach to matter (possibly stale, i.e. low: the exact test is in emit)
       uint64_t th = *L.thr;
       th = th > g_cached ? th : g_cached;
@@ -407,7 +435,7 @@ template <typename T, int C, int MODE>
 static int launch_scan1_t(ssw_db* db, const Scan1Args& a, cudaStream_t st) {
   using Cfg = Scan1Cfg<T, C>;
   const size_t smem = (size_t)kScanWarps * kStages * Cfg::STAGE_BYTES + ((a.k * 12 + 15) / 16) * 16 +
-                      kScanWarps * kStages * 8 + 8 + 16;
+                      kScanWarps * kStages * 8 + 8 + 16;      // ... | mbar | thr | cnt, minpos, lock, best
   auto kern = scan1_kernel<T, C, MODE>;
   SSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<db->scan_grid, kScanWarps * 32, smem, st>>>(a);
@@ -438,7 +466,7 @@ static int dispatch_scan1(ssw_db* db, const Scan1Args& a, cudaStream_t st) {
 }
 
 int launch_scan1(ssw_db* db, const float* d_query, int k, const uint32_t* d_excl, uint64_t* d_list_keys,
-                 int32_t* d_list_dbidx, uint64_t* d_gthr, cudaStream_t st) {
+                 int32_t* d_list_dbidx, uint64_t* d_gthr, uint32_t* d_pub, cudaStream_t st) {
   Scan1Args a{};
   a.vecs = db->d_vecs;
   a.last_bits = db->d_last_bits;
@@ -451,6 +479,7 @@ int launch_scan1(ssw_db* db, const float* d_query, int k, const uint32_t* d_excl
   a.list_keys = d_list_keys;
   a.list_dbidx = d_list_dbidx;
   a.g_thr = d_gthr;
+  a.pub = d_pub;
   a.scores_out = nullptr;
   a.row_base = db->row_base;
   a.k = k;

@@ -276,16 +276,7 @@ __device__ __forceinline__ void scan_tc_threshold_warp(const QShared& Q, const S
         const int q = q0 + u;
         if (q >= a.nq) break;
         uint32_t t = 0;
-        if (pooled) {
-          if (ngp == 64) {                        // groups lane and lane + 32
-            const uint32_t ga = max(max(v[u][0], v[u][2]), v[u][4]), gb = max(max(v[u][1], v[u][3]), v[u][5]);
-            t = min(ga, gb);
-          } else {                                // group lane % ngp
-            t = max(max(max(v[u][0], v[u][1]), max(v[u][2], v[u][3])), max(v[u][4], v[u][5]));
-            for (int sft = 16; sft >= ngp; sft >>= 1) t = max(t, __shfl_xor_sync(0xffffffffu, t, sft));
-          }
-          t = __reduce_min_sync(0xffffffffu, t);
-        }
+        if (pooled) t = pooled_group_min<VMAX>(v[u], ngp, lane);
         if (lane == 0) {
           const uint64_t tkey = (uint64_t)t << 32;
           if (blockIdx.x == 0 && tkey > g[u]) atomicMax(reinterpret_cast<unsigned long long*>(a.g_thr + q), (unsigned long long)tkey);
