@@ -212,6 +212,8 @@ def main():
     def step_e2e():
         if world == 1:
             return db.scan_topk(q_host, TOPK, exclude=ex_host)          # C ABI ssw_scan_topk: H2D + kernels + D2H
+        if not args.nccl_exchange:
+            return sdb.scan_topk(q_host, TOPK, exclude=ex_host)          # C ABI ssw_scan_topk_sharded, host buffers
         dq = q_pinned.to(dev, non_blocking=True)
         bits = db.build_exclude_bits(ex_host, NQ)
         out = sdb.scan_topk_device(dq, TOPK, d_exclude_bits=bits)
@@ -279,7 +281,8 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                         "d2h_bytes_per_step": int(d2h_bytes), "steps": e2e_steps,
                         "api": "ssw_scan_topk (C ABI, host buffers)" if world == 1 else
-                               "ShardedPatchDatabase.scan_topk_device from pinned host buffers + .cpu()"},
+                               ("ssw_scan_topk_sharded (C ABI, host buffers, every rank)" if not args.nccl_exchange else
+                                "ShardedPatchDatabase.scan_topk_device from pinned host buffers + .cpu()")},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "ssw::scan_tc_kernel<512,128,10> (K2, tcgen05 batched scan)",
                              "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -126,6 +126,13 @@ int ssw_scan_topk_sharded_device(ssw_db* db, const float* d_queries, int nq, int
                                  int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row,
                                  int32_t* d_out_count, void* stream);
 
+/* Host-buffer form of the sharded step (arguments as ssw_scan_topk + the exchange arguments above):
+ * one H2D of queries and id lists, bitmap build, scan, fused exchange + merge, one D2H of the results. */
+int ssw_scan_topk_sharded(ssw_db* db, const float* queries, int nq, int k, const int32_t* exclude_dbidx,
+                          const int64_t* exclude_offsets, void* const* peer_bufs, int world, int rank,
+                          int nq_cap, int k_cap, uint32_t epoch, int32_t* out_dbidx, float* out_score,
+                          int64_t* out_row, int32_t* out_count);
+
 /* Kernel selection for ssw_scan_topk*: 0 = auto (streaming SIMT kernel for nq < 8 queries,
  * tcgen05 batched kernel otherwise), 1 = force streaming kernel, 2 = force tcgen05 kernel. */
 int ssw_set_scan_mode(ssw_db* db, int mode);

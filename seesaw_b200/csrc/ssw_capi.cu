@@ -561,9 +561,9 @@ int ssw_merge_topk_device(int device, const uint64_t* d_keys, const int32_t* d_d
                       d_out_score, d_out_row, d_out_count, (cudaStream_t)stream);
 }
 
-int ssw_scan_topk(ssw_db* db, const float* queries, int nq, int k, const int32_t* exclude_dbidx,
-                  const int64_t* exclude_offsets, int32_t* out_dbidx, float* out_score, int64_t* out_row,
-                  int32_t* out_count) {
+static int scan_topk_host(ssw_db* db, const float* queries, int nq, int k, const int32_t* exclude_dbidx,
+                          const int64_t* exclude_offsets, int32_t* out_dbidx, float* out_score, int64_t* out_row,
+                          int32_t* out_count, const XchgCtx* xc) {
   SSW_REQUIRE(db != nullptr && queries != nullptr, "null argument");
   SSW_REQUIRE(nq > 0, "nq must be positive");
   SSW_REQUIRE(k > 0 && k <= SSW_MAX_TOPK, "k must be in [1, SSW_MAX_TOPK]");
@@ -609,7 +609,7 @@ int ssw_scan_topk(ssw_db* db, const float* queries, int nq, int k, const int32_t
   float* d_score = reinterpret_cast<float*>(d_out + db_b);
   int64_t* d_row = reinterpret_cast<int64_t*>(d_out + db_b + sc_b);
   int32_t* d_cnt = reinterpret_cast<int32_t*>(d_out + db_b + sc_b + row_b);
-  rc = scan_topk_impl(db, d_q, nq, k, d_bits, d_key, d_dbidx, d_score, d_row, d_cnt, st);
+  rc = scan_topk_impl(db, d_q, nq, k, d_bits, d_key, d_dbidx, d_score, d_row, d_cnt, st, xc);
   if (rc) return rc;
   SSW_CUDA(cudaMemcpyAsync(h, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
   SSW_CUDA(cudaStreamSynchronize(st));
@@ -671,6 +671,26 @@ int ssw_topk_from_scores(ssw_db* db, const float* scores, const uint8_t* row_mas
   if (out_row) memcpy(out_row, h + o_db + o_sc, (size_t)k * 8);
   if (out_count) memcpy(out_count, h + o_db + o_sc + o_row, 4);
   return SSW_OK;
+}
+
+int ssw_scan_topk(ssw_db* db, const float* queries, int nq, int k, const int32_t* exclude_dbidx,
+                  const int64_t* exclude_offsets, int32_t* out_dbidx, float* out_score, int64_t* out_row,
+                  int32_t* out_count) {
+  return scan_topk_host(db, queries, nq, k, exclude_dbidx, exclude_offsets, out_dbidx, out_score, out_row, out_count,
+                        nullptr);
+}
+
+int ssw_scan_topk_sharded(ssw_db* db, const float* queries, int nq, int k, const int32_t* exclude_dbidx,
+                          const int64_t* exclude_offsets, void* const* peer_bufs, int world, int rank, int nq_cap,
+                          int k_cap, uint32_t epoch, int32_t* out_dbidx, float* out_score, int64_t* out_row,
+                          int32_t* out_count) {
+  SSW_REQUIRE(db != nullptr && peer_bufs != nullptr, "null argument");
+  SSW_REQUIRE(world >= 1 && world <= SSW_MAX_WORLD && rank >= 0 && rank < world, "bad world/rank");
+  SSW_REQUIRE(nq > 0 && nq <= nq_cap && nq <= db->sm_count, "nq must be in [1, min(nq_cap, SM count)]");
+  SSW_REQUIRE(k > 0 && k <= k_cap, "k must be in [1, k_cap]");
+  SSW_REQUIRE(epoch != 0, "epoch must be non-zero and increase by one per call");
+  XchgCtx xc{peer_bufs, world, rank, nq_cap, k_cap, epoch};
+  return scan_topk_host(db, queries, nq, k, exclude_dbidx, exclude_offsets, out_dbidx, out_score, out_row, out_count, &xc);
 }
 
 int ssw_score_all_device(ssw_db* db, const float* d_query, float* d_out_scores, void* stream) {

@@ -584,17 +584,28 @@ __device__ __forceinline__ int merge_gather(const MergeSmem& M, const uint64_t* 
   if (thr == 0) thr = 1;   // key 0 == empty slot
   auto ldk = [&](int64_t off) { return CG ? __ldcg(kq + off) : kq[off]; };
   auto ldd = [&](int64_t off) { return CG ? __ldcg(dq + off) : dq[off]; };
+  const bool dense = list_stride == (int64_t)k;      // lists back to back: entry e sits at offset e
   auto gather = [&](uint64_t lo) {
     if (tid == 0) *M.cnt = 0;
     __syncthreads();
-    for (uint32_t e = tid; e < total; e += kMergeThreads) {
-      const int64_t off = (int64_t)(e / k) * list_stride + (e % k);
-      const uint64_t key = ldk(off);
-      if (key >= lo) {
-        const int p = atomicAdd(M.cnt, 1);
-        if (p < kMergeCap) {
-          M.sk[p] = key;
-          M.sd[p] = ldd(off);
+    // four independent loads in flight per thread (the lists sit in L2 / peer-written memory)
+    for (uint32_t e0 = tid; e0 < total; e0 += 4 * kMergeThreads) {
+      uint64_t key[4];
+      int64_t off[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t e = e0 + u * kMergeThreads;
+        off[u] = dense ? (int64_t)e : (int64_t)(e / k) * list_stride + (e % k);
+        key[u] = e < total ? ldk(off[u]) : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (key[u] >= lo) {
+          const int p = atomicAdd(M.cnt, 1);
+          if (p < kMergeCap) {
+            M.sk[p] = key[u];
+            M.sd[p] = ldd(off[u]);
+          }
         }
       }
     }
@@ -631,6 +642,27 @@ __device__ __forceinline__ int merge_gather(const MergeSmem& M, const uint64_t* 
 __device__ __forceinline__ int merge_select_sort(const MergeSmem& M, int n, int k) {
   const int tid = threadIdx.x;
   int m;
+  if (n <= kMergeThreads) {
+    // few survivors (the usual case once the pooled thresholds have pruned the lists): every thread ranks
+    // one key by counting the larger ones — keys are unique, so the rank IS the output position
+    for (int i = tid; i < k && i < kMergeOut; i += kMergeThreads) {
+      M.ok[i] = 0;
+      M.od[i] = -1;
+    }
+    __syncthreads();
+    if (tid < n) {
+      const uint64_t mine = M.sk[tid];
+      int rank = 0;
+#pragma unroll 4
+      for (int j = 0; j < n; ++j) rank += M.sk[j] > mine;
+      if (rank < k) {
+        M.ok[rank] = mine;
+        M.od[rank] = M.sd[tid];
+      }
+    }
+    __syncthreads();
+    return min(n, k);
+  }
   if (n <= k) {
     m = n;
     for (int i = tid; i < n; i += kMergeThreads) {

@@ -255,7 +255,7 @@ __device__ __forceinline__ void scan_tc_threshold_warp(const QShared& Q, const S
   constexpr int QB = 8;                         // queries whose loads are in flight together
   while (*done < 4) {
 #pragma unroll 1
-    for (int q0 = 0; q0 < a.nq; q0 += QB) {
+    for (int q0 = 0; q0 < a.nq && *done < 4; q0 += QB) {      // leave promptly once the epilogue is through
       uint32_t v[QB][VMAX];
       uint64_t g[QB];
 #pragma unroll
@@ -285,7 +285,7 @@ __device__ __forceinline__ void scan_tc_threshold_warp(const QShared& Q, const S
         }
       }
     }
-    __nanosleep(2000);
+    if (*done < 4) __nanosleep(1000);
   }
 }
 

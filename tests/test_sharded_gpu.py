@@ -67,6 +67,10 @@ def _worker(rank, world, port, out_dir):
                 res = sdb.scan_topk_device(torch.from_numpy(qs).cuda(), k, exclude=excl)
                 torch.cuda.synchronize()
                 _check(res, counts, dbidx, n, qs, excl, k)
+    # host-buffer form of the fused step
+    for k in (50, 3):
+        res = sdb.scan_topk(qs, k, exclude=excl)
+        _check({n: torch.from_numpy(v) for n, v in res.items()}, counts, dbidx, n, qs, excl, k)
     dist.barrier()
     sdb.close()
     dist.destroy_process_group()
