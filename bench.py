@@ -40,6 +40,22 @@ def workload_config(n_gpus, exchange=None):
             "l2": "inputs (10.24 GB) are larger than L2 (126 MB); no flush needed"}
 
 
+def ncu_traffic_bytes(path=os.path.join(ROOT, "profiles", "r01_k2_scan_tc_ncu_full.txt")):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one K2 launch on this exact workload, from the committed
+    `ncu --set full` summary (scripts/ncu_summary.py); None when the file is missing."""
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    total, seen = 0.0, 0
+    try:
+        for line in open(path):
+            f = line.split()
+            if len(f) == 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[2] in unit:
+                total += float(f[1]) * unit[f[2]]
+                seen += 1
+    except OSError:
+        return None
+    return int(total) if seen == 2 else None
+
+
 def make_queries_and_excludes():
     from seesaw_b200 import synth
     q = synth.unit_queries(NQ, DIM, Q_SEED)
@@ -286,7 +302,9 @@ def main():
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "ssw::scan_tc_kernel<512,128,10> (K2, tcgen05 batched scan)",
                              "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": (achieved / peak) if achieved else None, "traffic": None,
+                             "frac": (achieved / peak) if achieved else None,
+                             "traffic": ncu_traffic_bytes() if world == 1 else None,
+                             "traffic_source": "ncu --set full, one launch on this workload (profiles/r01_k2_scan_tc_ncu_full.txt)",
                              "algorithmic_bytes_per_launch": int(bytes_per_launch),
                              "kernel_ms_avg": kern_avg_ms, "kernel_launches_timed": int(kern_n), "peak_source": peak_src,
                              "kernel_share_of_step": (kern_avg_ms / ms_per_step) if ms_per_step else None},
