@@ -168,6 +168,23 @@ int ssw_knn_build_device(int device, const void* d_vectors_f16, int64_t n, int d
                          int64_t row_begin, int64_t row_end, int32_t* d_out_idx, float* d_out_dist,
                          void* stream);
 
+/* ---- label propagation over the kNN graph ----------------------------------------------
+ * Replaces the iteration of LabelPropagation.fit_transform / _step (label_propagation.py:30-83):
+ * new = (W @ old + reg_lambda * reg_values) / (weight_sum + reg_lambda); new[label_ids] = label_values;
+ * stop when max((new - old)^2) < epsilon.  W (CSR, float64, sorted indices) is what get_weight_matrix
+ * (knn_graph.py:31-104) builds from the kNN edge table; weight_sum[n] = W.sum(0) as the reference
+ * computes it.  All arithmetic is IEEE float64 in scipy's order: iterates are bit-identical.
+ * ssw_lp_fit returns the iterate fit_transform returns (the previous one on convergence), the number
+ * of iterations run and whether it converged.  reg_values / start_value may be NULL as in the reference
+ * (reg_values NULL requires reg_lambda == 0). */
+typedef struct ssw_lp ssw_lp;
+int ssw_lp_create(ssw_lp** out, int device, int64_t n, const int64_t* indptr, const int32_t* indices,
+                  const double* data, const double* weight_sum, double reg_lambda);
+int ssw_lp_destroy(ssw_lp* lp);
+int ssw_lp_fit(ssw_lp* lp, const int64_t* label_ids, const double* label_values, int64_t n_labels,
+               const double* reg_values, const double* start_value, int max_iter, double epsilon,
+               double* out_values, int* out_iterations, int* out_converged);
+
 /* ---- introspection for benchmarks / tests ---------------------------------------------- */
 /* With profiling on, every launch of the dominant scan kernel (K1 streaming or K2 tcgen05) is
  * bracketed by CUDA events on its own stream.  ssw_profile_read synchronises those events and

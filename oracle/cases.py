@@ -49,3 +49,28 @@ def knn_inputs(c):
     return v
 
 
+
+
+# label propagation over an exact kNN graph of `n` synthetic vectors (weights: rbf kernel, symmetric)
+LP = {
+    "lp_reg": dict(n=400, dim=64, seed=51, k=6, edist=0.5, reg_lambda=1.0, max_iter=40, epsilon=1e-7, n_labels=24, lseed=52),
+    "lp_noreg": dict(n=250, dim=64, seed=53, k=5, edist=0.3, reg_lambda=0.0, max_iter=15, epsilon=1e-5, n_labels=10, lseed=54),
+    "lp_start": dict(n=300, dim=64, seed=55, k=4, edist=1.0, reg_lambda=0.25, max_iter=500, epsilon=1e-9, n_labels=30, lseed=56,
+                     start=True),
+}
+
+
+def lp_vectors(c):
+    v = synth.synth_rows(0, c["n"], c["dim"], c["seed"], "tri", np.float32)
+    return (v / np.linalg.norm(v, axis=1, keepdims=True)).astype(np.float32)
+
+
+def lp_inputs(c):
+    """label ids / values (with one duplicate id: the later value wins), prior scores, optional start vector."""
+    rng = np.random.default_rng(c["lseed"])
+    ids = rng.choice(c["n"], size=c["n_labels"], replace=False)
+    ids = np.concatenate([ids, ids[:1]])
+    vals = np.concatenate([(rng.random(c["n_labels"]) < 0.4).astype(np.float64), [1.0]])
+    reg = rng.random(c["n"]) if c["reg_lambda"] > 0 else None
+    start = rng.random(c["n"]) if c.get("start") else None
+    return ids.astype(np.int64), vals, reg, start

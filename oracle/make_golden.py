@@ -22,7 +22,7 @@ sys.path.insert(0, HERE)
 from refstubs import import_reference  # noqa: E402
 from seesaw_b200 import synth  # noqa: E402
 
-from cases import CASES, COARSE, KNN, ms_inputs, exclude_sets, knn_inputs  # noqa: E402
+from cases import CASES, COARSE, KNN, LP, ms_inputs, exclude_sets, knn_inputs, lp_vectors, lp_inputs  # noqa: E402
 
 
 def main():
@@ -72,6 +72,20 @@ def main():
         df = ref.knn_graph.compute_exact_knn(v, n_neighbors=c["k"])
         for col in ("src_vertex", "dst_vertex", "distance", "dst_rank"):
             out[f"{name}/{col}"] = df[col].values
+    # label propagation: the reference's weight matrix (knn_graph.py:31-104) and its fit_transform
+    import importlib
+    lpmod = importlib.import_module("seesaw.label_propagation")
+    for name, c in LP.items():
+        v = lp_vectors(c)
+        df = ref.knn_graph.compute_exact_knn(v, n_neighbors=c["k"])
+        W = ref.knn_graph.get_weight_matrix(df, kfun=ref.knn_graph.rbf_kernel(c["edist"]), self_edges=False,
+                                            normalized=False, symmetric=True)
+        ids, vals, reg, start = lp_inputs(c)
+        lp = lpmod.LabelPropagation(W, reg_lambda=c["reg_lambda"], max_iter=c["max_iter"], epsilon=c["epsilon"])
+        res = lp.fit_transform(label_ids=ids, label_values=vals, reg_values=reg, start_value=start)
+        out[f"{name}/W_indptr"], out[f"{name}/W_indices"], out[f"{name}/W_data"] = W.indptr, W.indices, W.data
+        out[f"{name}/values"] = np.asarray(res, dtype=np.float64)
+
     # the reference's own unit pin (multiscale_index.py:182-187)
     out["pin/distinct_topk_positions"] = ref.multiscale.distinct_topk_positions(
         np.array([10, 11, 11, 12, 12, 12, 13, 13]), 2)
@@ -79,7 +93,7 @@ def main():
     path = os.path.join(ROOT, "tests", "golden", "reference_outputs.npz")
     np.savez_compressed(path, **out)
     with open(os.path.join(ROOT, "tests", "golden", "reference_cases.json"), "w") as f:
-        json.dump(dict(multiscale=CASES, coarse=COARSE, knn=KNN,
+        json.dump(dict(multiscale=CASES, coarse=COARSE, knn=KNN, label_propagation=LP,
                        note="outputs of the unmodified reference; regenerate with oracle/make_golden.py"), f, indent=1)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path)} bytes")
 

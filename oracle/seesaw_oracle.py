@@ -261,6 +261,44 @@ def compute_exact_knn(vectors, n_neighbors):
 
 
 # --------------------------------------------------------------------------------------
+# Label propagation over the kNN graph (label_propagation.py:6-83)
+# --------------------------------------------------------------------------------------
+
+
+def label_propagation_fit(weight_matrix, *, reg_lambda, max_iter, epsilon=1e-5, label_ids, label_values,
+                          reg_values=None, start_value=None):
+    """LabelPropagation(weight_matrix, reg_lambda=, max_iter=, epsilon=).fit_transform(label_ids=,
+    label_values=, reg_values=, start_value=) — label_propagation.py:7-24 (constructor: weight_sum =
+    W.sum(0)), :30-43 (_step) and :45-83 (loop).  Returns (values, iterations, converged); on convergence
+    the PREVIOUS iterate is returned (:66-70, :83), otherwise the last one."""
+    W = weight_matrix
+    n = W.shape[0]
+    weight_sum = np.asarray(W.sum(0)).reshape(-1)                                   # :24
+    if reg_values is not None:
+        assert reg_values.shape[0] == n
+        reg = reg_values
+    else:
+        assert reg_lambda == 0                                                      # :50
+        reg = np.zeros(n)
+    if start_value is not None:
+        old = start_value.copy()                                                    # :54
+    elif reg_values is not None:
+        old = reg_values.copy()                                                     # :56
+    else:
+        old = np.zeros(n)                                                           # :58
+    old[label_ids] = label_values                                                   # :60
+    converged, i = False, 0
+    for i in range(1, max_iter + 1):
+        new = (W @ old + (reg_lambda * reg)) / (weight_sum + reg_lambda)            # :31-32
+        new[label_ids] = label_values                                               # :42
+        if np.max((new - old) ** 2) < epsilon:                                      # :66
+            converged = True
+            break
+        old = new
+    return old, i, converged
+
+
+# --------------------------------------------------------------------------------------
 # helpers for the tolerance rule used by the floating-point parity tests
 # --------------------------------------------------------------------------------------
 

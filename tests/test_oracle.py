@@ -141,3 +141,19 @@ def test_lattice_data_is_exact_in_any_order():
     perm = np.random.default_rng(0).permutation(512)
     assert ((v[:, perm] @ q[perm]) == s32).all()
     assert len(np.unique(s32)) < len(s32) // 4
+
+
+@pytest.mark.parametrize("name", list(cases.LP))
+def test_label_propagation_matches_reference_golden(golden, name):
+    """oracle.label_propagation_fit against the reference's LabelPropagation.fit_transform on the reference's
+    own weight matrix (stored in the fixture): bit-identical float64."""
+    import scipy.sparse as sp
+    c = cases.LP[name]
+    W = sp.csr_array((golden[f"{name}/W_data"], golden[f"{name}/W_indices"], golden[f"{name}/W_indptr"]),
+                     shape=(c["n"], c["n"]))
+    ids, vals, reg, start = cases.lp_inputs(c)
+    got, it, conv = orc.label_propagation_fit(W, reg_lambda=c["reg_lambda"], max_iter=c["max_iter"], epsilon=c["epsilon"],
+                                              label_ids=ids, label_values=vals, reg_values=reg, start_value=start)
+    assert (got == golden[f"{name}/values"]).all()
+    assert (got[ids[-1]] == 1.0) and it >= 1
+    assert conv == (name != "lp_noreg")          # the fixture holds one run that hits max_iter
