@@ -142,7 +142,7 @@ class ClockSampler:
         busy = [c for c in sm if c >= 0.6 * max(sm)] if sm else []
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(busy),
-                "window": "first warm-up step .. last timed step of the HBM-resident leg"}
+                "window": "first warm-up step of the HBM-resident leg .. last timed step of the end-to-end leg"}
 
 
 def main():
@@ -267,9 +267,9 @@ def main():
     sampler = ClockSampler(local_rank)
     dev_ms, wall_ms, launches, (kern_ms, kern_n) = timed(step_resident, args.steps, profile=True,
                                                         before=sampler.start if rank == 0 else None)
-    clocks = sampler.stop() if rank == 0 else None
     e2e_steps = max(3, min(args.steps, 50))
     _, e2e_wall_ms, _, _ = timed(step_e2e, e2e_steps)
+    clocks = sampler.stop() if rank == 0 else None
 
     # parity spot check inside the bench: shard-merged result == single-call result of rank 0's view
     res = step_resident()
@@ -345,6 +345,7 @@ def main():
         v = (v / v.norm(dim=1, keepdim=True)).half().contiguous()
         lo = int(knn_row_ranges(n_knn, world)[rank])
         knn_candidates_device(v, 10, rows=(lo, min(lo + 148 * 128, n_knn)))     # warm-up: one wave of row blocks
+        knn_candidates_sharded(v[:65536], 10, rank=rank, world_size=world)      # ... and the all-gather path
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
