@@ -4,9 +4,9 @@ A numpy/pandas restatement of the reference's algorithm (orm011/seesaw 1.3.0), u
 the checker: by ``tests/``, by ``__graft_entry__.smoke()`` and by ``bench.py``'s
 ``cpu_baseline`` / ``--impl reference`` legs.  The product (``seesaw_b200``) never imports it.
 
-Parity status: PINNED.  ``tests/test_oracle_vs_reference.py`` runs the unmodified reference
-(imported through ``oracle/refstubs.py``) against this restatement on seeded inputs in the build
-container, ``oracle/make_golden.py`` stores reference outputs as fixtures under ``tests/golden/``
+Parity status: PINNED.  ``tests/test_oracle.py`` runs the unmodified reference (imported through
+``oracle/refstubs.py``, when ``/root/reference`` is present) against this restatement on seeded inputs
+in the build container, ``oracle/make_golden.py`` stores reference outputs as fixtures under ``tests/golden/``
 (those travel to the GPU box, the reference does not), and the reference's own unit pin
 ``test_distinct_topk_positions`` (multiscale_index.py:182-187) is reproduced in
 ``tests/test_oracle.py``.
