@@ -143,6 +143,20 @@ int ssw_set_scan_mode(ssw_db* db, int mode);
 int ssw_score_all(ssw_db* db, const float* query, float* out_scores);
 int ssw_score_all_device(ssw_db* db, const float* d_query, float* d_out_scores, void* stream);
 
+/* ---- stage 2: rescoring of the shortlisted images ----------------------------------------
+ * Replaces the gather + matvec of MultiscaleIndex.query (multiscale_index.py:341-349) and
+ * rescore_candidates / score_frame2 (:379-403, :112-150) for the candidate images of stage 1.
+ * ssw_db_set_boxes uploads vector_meta's x1,y1,x2,y2,zoom_level per ORIGINAL row (needed by
+ * 'avg_score', the reference's default aggregation).  ssw_rescore: for every candidate dbidx the
+ * aggregated score of its best patch (float64) and that patch's ORIGINAL row; scores are
+ * vectors.q [- vectors.query2].  agg_method 0 = plain_score, 1 = avg_score; aug_larger 0 = all,
+ * 1 = greater, 2 = adjacent.  The caller orders the images (ascending dbidx, stable by score) and
+ * takes topk, as rescore_candidates does (:388-399).  Ids not in the database give row -1. */
+int ssw_db_set_boxes(ssw_db* db, const int32_t* x1, const int32_t* y1, const int32_t* x2, const int32_t* y2,
+                     const int32_t* zoom_level);
+int ssw_rescore(ssw_db* db, const float* query, const float* query2, const int32_t* cand_dbidx, int n_cand,
+                int agg_method, int aug_larger, double* out_score, int64_t* out_row);
+
 /* ---- top-k images from a caller-supplied score per row ---------------------------------
  * Replaces _get_top_dbidxs when the scores are not a dot product with the stored vectors: label
  * propagation over the kNN graph (KnnProp2.next_batch, loops/graph_based.py:97-99, calls

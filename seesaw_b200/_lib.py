@@ -60,6 +60,8 @@ SIGNATURES = {
     "ssw_scan_topk_sharded": (C.c_int, [_p, _p, C.c_int, C.c_int, _p, _p, C.POINTER(_p), C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_uint32, _p, _p, _p, _p]),
     "ssw_set_scan_mode": (C.c_int, [_p, C.c_int]),
+    "ssw_db_set_boxes": (C.c_int, [_p, _p, _p, _p, _p, _p]),
+    "ssw_rescore": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, _p, _p]),
     "ssw_topk_from_scores": (C.c_int, [_p, _p, _p, C.c_int, _p, C.c_int64, _p, _p, _p, _p]),
     "ssw_score_all": (C.c_int, [_p, _p, _p]),
     "ssw_score_all_device": (C.c_int, [_p, _p, _p, _p]),

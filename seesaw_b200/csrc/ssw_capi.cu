@@ -108,7 +108,7 @@ static int ensure_lists(ssw_db* db, int nq, int lists, int k) {
   return SSW_OK;
 }
 
-static int ensure_stage(ssw_db* db, size_t dev_bytes, size_t host_bytes) {
+int ensure_stage(ssw_db* db, size_t dev_bytes, size_t host_bytes) {
   if (dev_bytes > db->d_stage_bytes) {
     if (db->d_stage) cudaFree(db->d_stage);
     db->d_stage_bytes = 0;
@@ -257,6 +257,7 @@ int ssw_db_destroy(ssw_db* db) {
   cudaFree(db->d_orig_row);
   cudaFree(db->d_part);
   cudaFree(db->d_last_bits);
+  cudaFree(db->d_boxes);
   cudaFree(db->d_tc_ws);
   cudaFree(db->d_list_keys);
   cudaFree(db->d_list_dbidx);

@@ -24,6 +24,8 @@ struct ssw_db {
   int scan_grid = 0;               // CTAs of the streaming scan (one per SM)
   int64_t max_cta_images = 0;      // most images any CTA's range holds
   uint32_t* d_last_bits = nullptr; // [n_rows/32 + pad] bit r set <=> device row r is the last row of its image
+  int32_t* d_boxes = nullptr;      // [n_rows][5] x1,y1,x2,y2,zoom per device row (stage-2 rescoring; optional)
+  std::vector<int32_t> h_img_dbidx; // host copy of d_img_dbidx (candidate id -> image index), filled on first use
   void* d_tc_ws = nullptr;         // prepared A operand of the tcgen05 batched scan (one batch)
 
   int64_t excl_words = 0;          // uint32 words of one exclusion bitmap (n_images bits, padded)
@@ -53,6 +55,7 @@ constexpr int kScanWarps = 8;             // warps per CTA of the streaming scan
 constexpr int kMergeCap = 8192;           // candidates the merge kernel sorts in shared memory
 
 int ensure_device(int device, int* sm_count);
+int ensure_stage(ssw_db* db, size_t dev_bytes, size_t host_bytes);
 // event pair around the scan kernel when profiling is on (no-ops otherwise)
 void prof_begin(ssw_db* db, cudaStream_t st);
 void prof_end(ssw_db* db, cudaStream_t st);

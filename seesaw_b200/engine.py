@@ -116,6 +116,29 @@ class PatchDatabase:
                                 ptr(out_score), ptr(out_row), ptr(out_count)))
         return dict(dbidx=out_dbidx, score=out_score, row=out_row, count=out_count)
 
+    def set_boxes(self, x1, y1, x2, y2, zoom_level):
+        """vector_meta's box columns per ORIGINAL row, for the device stage 2 ('avg_score')."""
+        cols = [np.ascontiguousarray(np.asarray(c).astype(np.int32).reshape(-1)) for c in (x1, y1, x2, y2, zoom_level)]
+        assert all(c.shape[0] == self.n_rows for c in cols)
+        check(lib.ssw_db_set_boxes(self._h, *[ptr(c) for c in cols]))
+        self.has_boxes = True
+
+    _AGG = {"plain_score": 0, "avg_score": 1}
+    _AUG = {"all": 0, "greater": 1, "adjacent": 2}
+
+    def rescore(self, query, cand_dbidx, *, query2=None, agg_method="avg_score", aug_larger="all"):
+        """Stage 2 for the candidate images (rescore_candidates / score_frame2, multiscale_index.py:379-403,
+        112-150): per candidate the aggregated score of its best patch (float64) and that patch's original
+        row.  Scores are vectors.q [- vectors.query2]."""
+        q = np.ascontiguousarray(np.asarray(query, dtype=np.float32).reshape(-1))
+        q2 = None if query2 is None else np.ascontiguousarray(np.asarray(query2, dtype=np.float32).reshape(-1))
+        ids = np.ascontiguousarray(np.asarray(cand_dbidx).astype(np.int32).reshape(-1))
+        score = np.empty(len(ids), np.float64)
+        row = np.empty(len(ids), np.int64)
+        check(lib.ssw_rescore(self._h, ptr(q), ptr(q2), ptr(ids), len(ids), self._AGG[agg_method], self._AUG[aug_larger],
+                              ptr(score), ptr(row)))
+        return score, row
+
     def topk_from_scores(self, scores, k, exclude=None, row_mask=None):
         """Per-image max of a caller-supplied score per row (original order) + exclusion + top-k: the
         ``_get_top_dbidxs`` step of KnnProp2.next_batch (loops/graph_based.py:97-99).  ``row_mask``: rows

@@ -159,6 +159,10 @@ class B200MultiscaleIndex(_GpuIndexMixin, AccessMethod):
         self._init_device(device, store)
         self._meta_cols = {c: self.vector_meta[c].to_numpy() for c in ("x1", "y1", "x2", "y2", "zoom_level")
                            if c in self.vector_meta.columns}
+        self._boxes_on_device = len(self._meta_cols) == 5 and all(
+            np.issubdtype(v.dtype, np.integer) for v in self._meta_cols.values())
+        if self._boxes_on_device:
+            self.db.set_boxes(*[self._meta_cols[c] for c in ("x1", "y1", "x2", "y2", "zoom_level")])
 
     @staticmethod
     def from_path(index_path: str, *, use_vec_index=False, device=0, store="f16", exclude=None, **options):
@@ -212,6 +216,16 @@ class B200MultiscaleIndex(_GpuIndexMixin, AccessMethod):
                                   "dbidx": [d], "score": [s]}) for r, d, s in zip(rows, ids, sc[order])]
             return {"dbidxs": ids.astype("int"), "activations": acts}
         ids = np.sort(cand["dbidx"].to_numpy())
+        aug_larger = kwargs.get("aug_larger", "all")
+        if (agg_method in ("plain_score", "avg_score") and aug_larger in ("all", "greater", "adjacent")
+                and kwargs.get("device_rescore", self._store_exact and (agg_method == "plain_score" or self._boxes_on_device))):
+            # stage 2 on the device (K7): patch scores, IoU join and per-level averaging for the <= shortlist images
+            sc, rows = self.db.rescore(qvec, ids, query2=vector2, agg_method=agg_method, aug_larger=aug_larger)
+            order = np.argsort(-sc, kind="stable")[:topk]              # images ascending in dbidx, stable by score (:388-399)
+            acts = [pd.DataFrame({"x1": [self._meta_cols["x1"][r]], "y1": [self._meta_cols["y1"][r]],
+                                  "x2": [self._meta_cols["x2"][r]], "y2": [self._meta_cols["y2"][r]],
+                                  "dbidx": [d], "score": [s]}) for r, d, s in zip(rows[order], ids[order], sc[order])]
+            return {"dbidxs": ids[order].astype("int"), "activations": acts}
         groups = [self._rows_of(d) for d in ids]                      # CSR ranges, not an O(N) isin
         rows = np.concatenate(groups)
         sub = self.vectors[rows]

@@ -146,3 +146,28 @@ def test_batcher_on_gpu(ix):
         assert (a["dbidxs"] == g["dbidxs"]).all()
     idx.attach_batcher(None)
     idx.close()
+
+
+@pytest.mark.parametrize("aug", ["all", "greater", "adjacent"])
+def test_device_stage2_avg_score_vs_oracle(ix, aug):
+    """K7 (IoU join + per-zoom-level averaging on the device) against the oracle's score_frame2 restatement,
+    all three aug_larger filters, images of 1..80 patches, exact lattice scores (ties between patches)."""
+    counts = synth.patches_per_image(600, 1, 80, 21)
+    meta = synth.synth_vector_meta(counts, 22, dbidx_start=7, dbidx_stride=2)
+    vecs = synth.synth_rows(0, int(counts.sum()), 512, 23, "lattice", np.float32)
+    idx = ix.B200MultiscaleIndex(embedding=None, vectors=vecs, vector_meta=meta, store="f16")
+    qs = synth.lattice_queries(3, 512, 24)
+    ex = np.unique(meta.dbidx.values)[::5]
+    for q, v2 in ((qs[0], None), (qs[1], qs[2] * 0.5)):
+        got = idx.query(vector=q, vector2=v2, topk=7, shortlist_size=40, exclude=ix.BitMap(ex), agg_method="avg_score",
+                        aug_larger=aug)
+        want = orc.multiscale_query(vecs, meta, q, 7, 40, exclude=ex, vector2=v2, agg_method="avg_score", aug_larger=aug)
+        host = idx.query(vector=q, vector2=v2, topk=7, shortlist_size=40, exclude=ix.BitMap(ex), agg_method="avg_score",
+                         aug_larger=aug, device_rescore=False)
+        assert (np.asarray(got["dbidxs"]) == want["dbidxs"]).all() and (np.asarray(host["dbidxs"]) == want["dbidxs"]).all()
+        gs = np.array([a.score.values[0] for a in got["activations"]])
+        ws = np.array([a.score.values[0] for a in want["activations"]])
+        np.testing.assert_allclose(gs, ws, rtol=1e-6, atol=1e-7)
+        for a, b in zip(got["activations"], want["activations"]):
+            assert (a[["x1", "y1", "x2", "y2"]].values == b[["x1", "y1", "x2", "y2"]].values).all()
+    idx.close()
