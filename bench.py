@@ -367,6 +367,19 @@ def main():
                                               "frac_of_sustained": tf / (float(peaks.get("bf16_tflops_sustained", tpeak / world)) * world)},
                                  "sharding": f"output rows over {world} GPU(s), V replicated, final all-gather of [N,11] ids+distances included",
                                  "self_is_nearest_spot_check": self_ok}
+        if rank == 0 and world == 1:
+            # the reference-facing call with HOST vectors in and the edge-table DataFrame out
+            from seesaw_b200.knn_graph import compute_exact_knn
+            v_host = v.cpu().numpy()
+            del idx
+            torch.cuda.empty_cache()
+            t0 = time.perf_counter()
+            df = compute_exact_knn(v_host, 10, device=local_rank)
+            line["knn_build"]["e2e"] = {"seconds": time.perf_counter() - t0, "edges": int(len(df)),
+                                        "api": "seesaw_b200.knn_graph.compute_exact_knn (C ABI ssw_knn_graph): H2D of the vectors, "
+                                               "candidates + post_process_graph_df on the device, D2H of the edge table"}
+            del df, v_host
+            idx = None
         del v, idx
         torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -182,6 +182,20 @@ int ssw_knn_build_device(int device, const void* d_vectors_f16, int64_t n, int d
                          int64_t row_begin, int64_t row_end, int32_t* d_out_idx, float* d_out_dist,
                          void* stream);
 
+/* The whole compute_exact_knn (knn_graph.py:170-191) in one call: candidates (above) + post_process_graph_df
+ * (:142-168) on the device.  Outputs are the four columns of the reference's edge table in its order
+ * (src_vertex, dst_rank): int32 src / dst, float32 distance (clipped at 0), int32 dst_rank; one rank-0
+ * self edge per vertex; *out_edges rows are valid.  capacity >= n * (min(n_neighbors+1, n) + 1). */
+int ssw_knn_graph(int device, const void* vectors, int dtype_in, int64_t n, int dim, int n_neighbors,
+                  int32_t* out_src, int32_t* out_dst, float* out_distance, int32_t* out_rank, int64_t capacity,
+                  int64_t* out_edges);
+/* Device-resident post-processing of a candidate table [rows, k1] (rows are vertices src_offset ..);
+ * d_workspace: ssw_knn_edges_workspace_bytes(rows); outputs sized rows * (k1 + 1); *d_total = edges. */
+int ssw_knn_edges_workspace_bytes(int64_t rows, int64_t* bytes);
+int ssw_knn_edges_device(int device, const int32_t* d_idx, const float* d_dist, int64_t rows, int k1,
+                         int64_t src_offset, int32_t* d_src, int32_t* d_dst, float* d_distance, int32_t* d_rank,
+                         int64_t* d_total, void* d_workspace, void* stream);
+
 /* ---- label propagation over the kNN graph ----------------------------------------------
  * Replaces the iteration of LabelPropagation.fit_transform / _step (label_propagation.py:30-83):
  * new = (W @ old + reg_lambda * reg_values) / (weight_sum + reg_lambda); new[label_ids] = label_values;

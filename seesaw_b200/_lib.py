@@ -67,6 +67,9 @@ SIGNATURES = {
     "ssw_score_all_device": (C.c_int, [_p, _p, _p, _p]),
     "ssw_knn_build": (C.c_int, [C.c_int, _p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64, _p, _p]),
     "ssw_knn_build_device": (C.c_int, [C.c_int, _p, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64, _p, _p, _p]),
+    "ssw_knn_graph": (C.c_int, [C.c_int, _p, C.c_int, C.c_int64, C.c_int, C.c_int, _p, _p, _p, _p, C.c_int64, _i64p]),
+    "ssw_knn_edges_workspace_bytes": (C.c_int, [C.c_int64, _i64p]),
+    "ssw_knn_edges_device": (C.c_int, [C.c_int, _p, _p, C.c_int64, C.c_int, C.c_int64, _p, _p, _p, _p, _p, _p, _p]),
     "ssw_lp_create": (C.c_int, [C.POINTER(_p), C.c_int, C.c_int64, _p, _p, _p, _p, C.c_double]),
     "ssw_lp_destroy": (C.c_int, [_p]),
     "ssw_lp_fit": (C.c_int, [_p, _p, _p, C.c_int64, _p, _p, C.c_int, C.c_double, _p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -760,6 +760,93 @@ static int launch_knn(int sm_count, const KnnArgs& a, int dim, cudaStream_t st) 
   return SSW_ERR_INVALID;
 }
 
+// ------------------------------------------------------------------------------------------
+// Edge table on the device: post_process_graph_df (seesaw/knn_graph.py:142-168) applied to the candidate
+// table [rows, k1] (already ordered by (distance, column)): distances clipped at 0, self edges dropped,
+// dst_rank = 1.. in table order (== rank('first') of the clipped, non-decreasing distances), one rank-0
+// zero-distance self edge per vertex, rows ordered by (src_vertex, dst_rank).  Three small kernels: per-row
+// counts + block-local scan, scan of the block totals, scatter.
+// ------------------------------------------------------------------------------------------
+constexpr int kEdgeBlock = 1024;
+
+__global__ void __launch_bounds__(kEdgeBlock) knn_edge_count_kernel(const int32_t* __restrict__ idx, int64_t rows, int k1,
+                                                                    int64_t src_offset, int32_t* __restrict__ local_off,
+                                                                    int64_t* __restrict__ block_total) {
+  __shared__ int s_warp[32];
+  const int64_t r = blockIdx.x * (int64_t)kEdgeBlock + threadIdx.x;
+  int c = 0;
+  if (r < rows) {
+    const int32_t self = (int32_t)(r + src_offset);
+    c = 1;
+    for (int j = 0; j < k1; ++j) {
+      const int32_t v = idx[r * k1 + j];
+      c += (v >= 0 && v != self);
+    }
+  }
+  int incl = c;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int m = 1; m < 32; m <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, incl, m);
+    if (lane >= m) incl += o;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = s_warp[lane];
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, w, m);
+      if (lane >= m) w += o;
+    }
+    s_warp[lane] = w;
+  }
+  __syncthreads();
+  const int before = (warp ? s_warp[warp - 1] : 0) + incl - c;
+  if (r < rows) local_off[r] = before;
+  if (threadIdx.x == kEdgeBlock - 1) block_total[blockIdx.x] = before + c;
+}
+
+__global__ void knn_edge_scan_kernel(int64_t* block_total, int64_t n_blocks, int64_t* total_out) {
+  // single thread: n_blocks = rows / 1024 (~1000 for a million vertices)
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int64_t run = 0;
+    for (int64_t b = 0; b < n_blocks; ++b) {
+      const int64_t t = block_total[b];
+      block_total[b] = run;
+      run += t;
+    }
+    *total_out = run;
+  }
+}
+
+__global__ void __launch_bounds__(kEdgeBlock) knn_edge_write_kernel(const int32_t* __restrict__ idx, const float* __restrict__ dist,
+                                                                    int64_t rows, int k1, int64_t src_offset,
+                                                                    const int32_t* __restrict__ local_off,
+                                                                    const int64_t* __restrict__ block_base, int32_t* __restrict__ src,
+                                                                    int32_t* __restrict__ dst, float* __restrict__ distance,
+                                                                    int32_t* __restrict__ rank) {
+  const int64_t r = blockIdx.x * (int64_t)kEdgeBlock + threadIdx.x;
+  if (r >= rows) return;
+  const int32_t self = (int32_t)(r + src_offset);
+  int64_t o = block_base[blockIdx.x] + local_off[r];
+  src[o] = self;
+  dst[o] = self;
+  distance[o] = 0.f;
+  rank[o] = 0;
+  int rk = 0;
+  for (int j = 0; j < k1; ++j) {
+    const int32_t v = idx[r * k1 + j];
+    if (v < 0 || v == self) continue;
+    ++o;
+    ++rk;
+    src[o] = self;
+    dst[o] = v;
+    distance[o] = fmaxf(dist[r * k1 + j], 0.f);
+    rank[o] = rk;
+  }
+}
+
 }  // namespace ssw
 
 using namespace ssw;
@@ -828,6 +915,113 @@ int ssw_knn_build(int device, const void* vectors, int dtype_in, int64_t n, int 
   if ((rc = chk(cudaDeviceSynchronize(), "knn kernel"))) return rc;
   if ((rc = chk(cudaMemcpy(out_idx, d_idx, nout * 4, cudaMemcpyDeviceToHost), "cudaMemcpy(out_idx)"))) return rc;
   if ((rc = chk(cudaMemcpy(out_dist, d_dist, nout * 4, cudaMemcpyDeviceToHost), "cudaMemcpy(out_dist)"))) return rc;
+  cleanup();
+  return SSW_OK;
+}
+
+int ssw_knn_edges_device(int device, const int32_t* d_idx, const float* d_dist, int64_t rows, int k1, int64_t src_offset,
+                         int32_t* d_src, int32_t* d_dst, float* d_distance, int32_t* d_rank, int64_t* d_total,
+                         void* d_workspace, void* stream) {
+  SSW_REQUIRE(d_idx && d_dist && d_src && d_dst && d_distance && d_rank && d_total && d_workspace, "null argument");
+  SSW_REQUIRE(rows >= 0 && k1 >= 1, "bad shape");
+  int rc = ensure_device(device, nullptr);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n_blocks = (rows + kEdgeBlock - 1) / kEdgeBlock;
+  int64_t* block_total = static_cast<int64_t*>(d_workspace);                         // [n_blocks]
+  int32_t* local_off = reinterpret_cast<int32_t*>(block_total + std::max<int64_t>(n_blocks, 1));   // [rows]
+  if (rows == 0) {
+    SSW_CUDA(cudaMemsetAsync(d_total, 0, 8, st));
+    return SSW_OK;
+  }
+  knn_edge_count_kernel<<<(int)n_blocks, kEdgeBlock, 0, st>>>(d_idx, rows, k1, src_offset, local_off, block_total);
+  SSW_LAUNCHED();
+  knn_edge_scan_kernel<<<1, 32, 0, st>>>(block_total, n_blocks, d_total);
+  SSW_LAUNCHED();
+  knn_edge_write_kernel<<<(int)n_blocks, kEdgeBlock, 0, st>>>(d_idx, d_dist, rows, k1, src_offset, local_off, block_total, d_src,
+                                                               d_dst, d_distance, d_rank);
+  SSW_LAUNCHED();
+  return SSW_OK;
+}
+
+int ssw_knn_edges_workspace_bytes(int64_t rows, int64_t* bytes) {
+  SSW_REQUIRE(bytes != nullptr && rows >= 0, "bad argument");
+  *bytes = (std::max<int64_t>((rows + kEdgeBlock - 1) / kEdgeBlock, 1)) * 8 + std::max<int64_t>(rows, 1) * 4;
+  return SSW_OK;
+}
+
+int ssw_knn_graph(int device, const void* vectors, int dtype_in, int64_t n, int dim, int n_neighbors, int32_t* out_src,
+                  int32_t* out_dst, float* out_distance, int32_t* out_rank, int64_t capacity, int64_t* out_edges) {
+  SSW_REQUIRE(vectors && out_src && out_dst && out_distance && out_rank && out_edges, "null argument");
+  SSW_REQUIRE(dtype_in == SSW_F16 || dtype_in == SSW_F32, "dtype_in must be SSW_F32 or SSW_F16");
+  SSW_REQUIRE(n > 0 && n < (int64_t)0x7FFFFFFF && n_neighbors >= 0, "bad shape");
+  const int k1 = (int)std::min<int64_t>((int64_t)n_neighbors + 1, n);
+  SSW_REQUIRE(k1 <= SSW_MAX_KNN_K1, "n_neighbors + 1 exceeds SSW_MAX_KNN_K1");
+  SSW_REQUIRE(capacity >= n * (k1 + 1), "output capacity must be n * (min(n_neighbors + 1, n) + 1) edges");
+  int rc = ensure_device(device, nullptr);
+  if (rc) return rc;
+  const size_t es = dtype_in == SSW_F16 ? 2 : 4;
+  const size_t cand = (size_t)n * k1, cap = (size_t)n * (k1 + 1);
+  int64_t ws_bytes = 0;
+  ssw_knn_edges_workspace_bytes(n, &ws_bytes);
+  void *d_in = nullptr, *d_v = nullptr, *d_ws = nullptr;
+  int32_t *d_idx = nullptr, *d_src = nullptr, *d_dst = nullptr, *d_rank = nullptr;
+  float *d_dist = nullptr, *d_edist = nullptr;
+  int64_t* d_total = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_in);
+    if (d_v != d_in) cudaFree(d_v);
+    cudaFree(d_ws);
+    cudaFree(d_idx);
+    cudaFree(d_dist);
+    cudaFree(d_src);
+    cudaFree(d_dst);
+    cudaFree(d_edist);
+    cudaFree(d_rank);
+    cudaFree(d_total);
+  };
+  auto chk = [&](cudaError_t e, const char* what) -> int {
+    if (e == cudaSuccess) return SSW_OK;
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    cleanup();
+    return e == cudaErrorMemoryAllocation ? SSW_ERR_OOM : SSW_ERR_CUDA;
+  };
+#define KG_TRY(expr)                   \
+  if ((rc = chk((expr), #expr))) return rc
+  KG_TRY(cudaMalloc(&d_in, (size_t)n * dim * es));
+  KG_TRY(cudaMemcpy(d_in, vectors, (size_t)n * dim * es, cudaMemcpyHostToDevice));
+  if (dtype_in == SSW_F32) {
+    KG_TRY(cudaMalloc(&d_v, (size_t)n * dim * 2));
+    if ((rc = launch_convert_rows(d_in, SSW_F32, d_v, SSW_F16, n * dim, nullptr))) {
+      cleanup();
+      return rc;
+    }
+  } else {
+    d_v = d_in;
+  }
+  KG_TRY(cudaMalloc((void**)&d_idx, cand * 4));
+  KG_TRY(cudaMalloc((void**)&d_dist, cand * 4));
+  KG_TRY(cudaMalloc((void**)&d_src, cap * 4));
+  KG_TRY(cudaMalloc((void**)&d_dst, cap * 4));
+  KG_TRY(cudaMalloc((void**)&d_edist, cap * 4));
+  KG_TRY(cudaMalloc((void**)&d_rank, cap * 4));
+  KG_TRY(cudaMalloc((void**)&d_total, 8));
+  KG_TRY(cudaMalloc(&d_ws, (size_t)ws_bytes));
+  rc = ssw_knn_build_device(device, d_v, n, dim, k1, 0, n, d_idx, d_dist, nullptr);
+  if (!rc) rc = ssw_knn_edges_device(device, d_idx, d_dist, n, k1, 0, d_src, d_dst, d_edist, d_rank, d_total, d_ws, nullptr);
+  if (rc) {
+    cleanup();
+    return rc;
+  }
+  KG_TRY(cudaDeviceSynchronize());
+  int64_t total = 0;
+  KG_TRY(cudaMemcpy(&total, d_total, 8, cudaMemcpyDeviceToHost));
+  KG_TRY(cudaMemcpy(out_src, d_src, (size_t)total * 4, cudaMemcpyDeviceToHost));
+  KG_TRY(cudaMemcpy(out_dst, d_dst, (size_t)total * 4, cudaMemcpyDeviceToHost));
+  KG_TRY(cudaMemcpy(out_distance, d_edist, (size_t)total * 4, cudaMemcpyDeviceToHost));
+  KG_TRY(cudaMemcpy(out_rank, d_rank, (size_t)total * 4, cudaMemcpyDeviceToHost));
+#undef KG_TRY
+  *out_edges = total;
   cleanup();
   return SSW_OK;
 }

@@ -95,8 +95,23 @@ def post_process_graph_df(df, nvec):
 
 
 def compute_exact_knn(vectors, n_neighbors, *, device=0):
-    idx, dist = knn_candidates(vectors, n_neighbors, device=device)
-    return edges_from_candidates(idx, dist, vectors.shape[0])
+    """compute_exact_knn (knn_graph.py:170-191): tcgen05 candidates + the edge table of post_process_graph_df,
+    both on the device (C ABI ``ssw_knn_graph``); the host only wraps the four columns in a DataFrame."""
+    v = np.ascontiguousarray(vectors)
+    if v.dtype not in (np.float16, np.float32):
+        v = v.astype(np.float32)
+    n, dim = v.shape
+    k1 = min(int(n_neighbors) + 1, n)
+    if k1 > SSW_MAX_KNN_K1:
+        raise ValueError(f"n_neighbors+1 = {k1} exceeds the fused epilogue's limit {SSW_MAX_KNN_K1}")
+    cap = n * (k1 + 1)
+    src, dst = np.empty(cap, np.int32), np.empty(cap, np.int32)
+    dis, rank = np.empty(cap, np.float32), np.empty(cap, np.int32)
+    total = C.c_int64()
+    check(lib.ssw_knn_graph(device, ptr(v), SSW_F16 if v.dtype == np.float16 else SSW_F32, n, dim, int(n_neighbors),
+                            ptr(src), ptr(dst), ptr(dis), ptr(rank), cap, C.byref(total)))
+    t = total.value
+    return pd.DataFrame({"src_vertex": src[:t], "dst_vertex": dst[:t], "distance": dis[:t], "dst_rank": rank[:t]})
 
 
 def get_lookup_ranges(sorted_col, nvecs):

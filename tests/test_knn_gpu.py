@@ -82,3 +82,17 @@ def test_knn_gaussian_and_row_ranges(kg):
     assert (i2 == idx[1000:1777]).all() and (d2 == dist[1000:1777]).all()
     g, _ = kg.KNNGraph.from_vectors(v[:700], n_neighbors=5)
     assert g.nvecs == 700 and g.k >= 5
+
+
+@pytest.mark.parametrize("n,dup", [(3000, False), (1025, True), (5, False)])
+def test_edge_table_on_device_equals_post_process_graph_df(kg, n, dup):
+    """ssw_knn_graph (candidates + post_process_graph_df on the device) == oracle edge table, frame-equal:
+    self edges, dropped self columns, ranks, clipping, order; duplicates make rows with k1 instead of k1-1 edges."""
+    v = synth.synth_rows(0, n, 512, 27, "lattice", np.float32) * np.float32(0.25)
+    if dup:
+        v[1::7] = v[0::7][: len(v[1::7])]
+    df = kg.compute_exact_knn(v, 10)
+    want = orc.compute_exact_knn(v, 10)
+    pd.testing.assert_frame_equal(df, want)
+    g = kg.KNNGraph(df)
+    assert g.nvecs == n and (np.diff(g.ind_ptr) >= 1).all()
