@@ -289,6 +289,21 @@ __device__ __forceinline__ void scan_tc_threshold_warp(const QShared& Q, const S
   }
 }
 
+// (max, LOWEST index attaining it) of 8 values as a depth-3 tree: the epilogue warps run alone on their
+// schedulers, so dependent-issue latency — not instruction count — is what a tile costs (ncu: stall_wait
+// is the top stall reason); a sequential running max would be a chain of 8 compare/select pairs.
+__device__ __forceinline__ void argmax8(const float* x, float& m, int& idx) {
+  const bool p0 = x[1] > x[0], p1 = x[3] > x[2], p2 = x[5] > x[4], p3 = x[7] > x[6];
+  const float m0 = p0 ? x[1] : x[0], m1 = p1 ? x[3] : x[2], m2 = p2 ? x[5] : x[4], m3 = p3 ? x[7] : x[6];
+  const int i0 = p0 ? 1 : 0, i1 = p1 ? 3 : 2, i2 = p2 ? 5 : 4, i3 = p3 ? 7 : 6;
+  const bool q0 = m1 > m0, q1 = m3 > m2;
+  const float n0 = q0 ? m1 : m0, n1 = q1 ? m3 : m2;
+  const int j0 = q0 ? i1 : i0, j1 = q1 ? i3 : i2;
+  const bool r = n1 > n0;
+  m = r ? n1 : n0;
+  idx = r ? j1 : j0;
+}
+
 // 32 accumulator columns starting at column `colbase`: v0 / v1 are the 16x256b loads of half 0 / 1,
 // em has bit c set when column colbase + c is the last row of its image.
 __device__ __forceinline__ void scan_tc_group(EpiState& st, const EpiCtx& cx, const QShared& Q, const ScanTcArgs& a,
@@ -303,13 +318,12 @@ __device__ __forceinline__ void scan_tc_group(EpiState& st, const EpiCtx& cx, co
   }
   const int cb = colbase + 2 * cx.j;
   if (em == 0) {            // warp-uniform fast path: no image ends inside these 32 columns
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        if (sa[2 * i + e] > st.m0) { st.m0 = sa[2 * i + e]; st.c0 = cb + 8 * i + e; }
-        if (sb[2 * i + e] > st.m1) { st.m1 = sb[2 * i + e]; st.c1 = cb + 8 * i + e; }
-      }
+    float ma, mb;
+    int ia, ib;
+    argmax8(sa, ma, ia);
+    argmax8(sb, mb, ib);
+    if (ma > st.m0) { st.m0 = ma; st.c0 = cb + ((ia >> 1) << 3) + (ia & 1); }
+    if (mb > st.m1) { st.m1 = mb; st.c1 = cb + ((ib >> 1) << 3) + (ib & 1); }
     return;
   }
   // walk the image boundaries in order (warp-uniform loop); fold in this thread's columns of each segment
@@ -318,16 +332,21 @@ __device__ __forceinline__ void scan_tc_group(EpiState& st, const EpiCtx& cx, co
     const int p = em ? __ffs(em) - 1 : 31;
     const uint32_t seg = (0xFFFFFFFFu >> (31 - p)) & (0xFFFFFFFFu << lo);   // columns lo..p
     const uint32_t mine = seg >> (2 * cx.j);                                // bit 8i+e <-> my column 8i+2j+e
+    float xa[8], xb[8];       // branch-free: a column outside the segment competes with -inf
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int e = 0; e < 2; ++e)
-      {                       // branch-free: a column outside the segment competes with -inf
+      for (int e = 0; e < 2; ++e) {
         const bool on = (mine >> (8 * i + e)) & 1u;
-        const float xa = on ? sa[2 * i + e] : -INFINITY, xb = on ? sb[2 * i + e] : -INFINITY;
-        if (xa > st.m0) { st.m0 = xa; st.c0 = cb + 8 * i + e; }
-        if (xb > st.m1) { st.m1 = xb; st.c1 = cb + 8 * i + e; }
+        xa[2 * i + e] = on ? sa[2 * i + e] : -INFINITY;
+        xb[2 * i + e] = on ? sb[2 * i + e] : -INFINITY;
       }
+    float ma, mb;
+    int ia, ib;
+    argmax8(xa, ma, ia);
+    argmax8(xb, mb, ib);
+    if (ma > st.m0) { st.m0 = ma; st.c0 = cb + ((ia >> 1) << 3) + (ia & 1); }
+    if (mb > st.m1) { st.m1 = mb; st.c1 = cb + ((ib >> 1) << 3) + (ib & 1); }
     if (em == 0) break;
     em &= em - 1;
     scan_tc_boundary(st, cx, Q, a);
