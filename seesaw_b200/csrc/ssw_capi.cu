@@ -571,8 +571,12 @@ static int scan_topk_host(ssw_db* db, const float* queries, int nq, int k, const
   SSW_REQUIRE((exclude_dbidx == nullptr) == (exclude_offsets == nullptr) || exclude_offsets != nullptr,
               "exclude_offsets is required with exclude_dbidx");
   SSW_CUDA(cudaSetDevice(db->device));
+  if (exclude_offsets) {
+    SSW_REQUIRE(exclude_offsets[0] == 0, "exclude_offsets[0] must be 0");
+    for (int i = 0; i < nq; ++i) SSW_REQUIRE(exclude_offsets[i + 1] >= exclude_offsets[i], "exclude_offsets must be non-decreasing");
+  }
   const int64_t n_ids = exclude_offsets ? exclude_offsets[nq] : 0;
-  SSW_REQUIRE(n_ids >= 0, "exclude_offsets must be non-decreasing");
+  SSW_REQUIRE(n_ids == 0 || exclude_dbidx != nullptr, "exclude_dbidx is null");
   const bool has_excl = exclude_offsets != nullptr && n_ids > 0;
   // one staging block each side:  queries | offsets | ids   ->   + bitmaps | keys | dbidx | score | row | count
   auto up16 = [](size_t x) { return (x + 15) / 16 * 16; };

@@ -65,3 +65,20 @@ def test_product_does_not_import_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "seesaw_oracle" not in src and "refstubs" not in src and "import oracle" not in src, fn
+
+
+def test_every_entry_rejects_null_handles_without_a_device():
+    """Argument checks come before any CUDA call: a NULL handle is SSW_ERR_INVALID (1) everywhere."""
+    from seesaw_b200 import _lib
+    L = _lib.lib
+    z = None
+    assert L.ssw_scan_topk(z, z, 1, 1, z, z, z, z, z, z) == 1
+    assert L.ssw_scan_topk_device(z, z, 1, 1, z, z, z, z, z, z, z) == 1
+    assert L.ssw_score_all(z, z, z) == 1
+    assert L.ssw_topk_from_scores(z, z, z, 1, z, 0, z, z, z, z) == 1
+    assert L.ssw_rescore(z, z, z, z, 0, 0, 0, z, z) == 1
+    assert L.ssw_db_set_boxes(z, z, z, z, z, z) == 1
+    assert L.ssw_lp_fit(z, z, z, 0, z, z, 1, 1e-5, z, None, None) == 1
+    assert L.ssw_lp_destroy(z) == 0 and L.ssw_xchg_destroy(0, z) == 0
+    assert L.ssw_knn_build(0, z, 0, 10, 512, 3, 0, 10, z, z) == 1
+    assert b"null" in L.ssw_last_error()
