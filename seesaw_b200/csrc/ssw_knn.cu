@@ -27,6 +27,7 @@ struct KnnArgs {
   int32_t* out_idx;     // [(row_end-row_begin), k1]
   float* out_dist;
   int debug;            // dev only (SSW_KNN_DEBUG): 1 = epilogue skips the accumulator reads
+  unsigned int* wave_sync;  // one counter: TMA producers of all CTAs meet here between row blocks
 };
 
 // Per-row list state in shared memory (one 16-byte record per epilogue thread), so the out-of-line
@@ -67,11 +68,16 @@ __device__ __noinline__ float knn_offer(KnnRowState* st, uint64_t* mylist, int k
   return key_score(mk);
 }
 
-// Dot-product value every column that can still enter the list must reach: d = fl(1 - x) <= thr holds
-// for every x >= 1 - thr, and rounding can pull in x at most one ulp of the distance (< 2^-22) below
-// that; the margin makes the cheap test conservative, the exact test on d follows in the rare path.
+// Dot-product value a column must EXCEED to be able to enter a full list.  Columns arrive in ascending
+// order, so a newcomer that only ties the list's worst distance loses on the column: it needs
+// d = fl(1 - x) < thr.  For thr in [0.5, 2] the subtraction 1 - thr is exact (Sterbenz) and x <= 1 - thr
+// implies d >= thr: the bound is tight, which matters for degenerate rows (an all-zero vector ties every
+// column at d = 1).  Below 0.5 one ulp of margin keeps the cheap test conservative; the exact test on d
+// follows in the rare path.
 __device__ __forceinline__ float knn_thr_dot(float thr) {
-  return thr == INFINITY ? -INFINITY : (1.0f - thr) - 4.8e-7f;
+  if (thr == INFINITY) return -INFINITY;
+  const float u = 1.0f - thr;
+  return thr >= 0.5f ? u : u - 1.2e-7f;
 }
 
 // 32 accumulator columns (dots of this thread's row with columns col0 .. col0+31).  Common case: one
@@ -86,16 +92,16 @@ __device__ __forceinline__ void knn_group(const uint32_t* v, float& thr, float& 
     m8[s] = fmaxf(fmaxf(a, b), fmaxf(__uint_as_float(v[8 * s + 6]), __uint_as_float(v[8 * s + 7])));
   }
   const float mx = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
-  if (mx >= thr_dot) {
+  if (mx > thr_dot) {
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-      if (m8[s] >= thr_dot) {
+      if (m8[s] > thr_dot) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float x = __uint_as_float(v[8 * s + e]);
-          if (x >= thr_dot) {
+          if (x > thr_dot) {
             const float d = __fsub_rn(1.0f, x);
-            if (d <= thr) {
+            if (d < thr) {
               thr = knn_offer(st, mylist, k1, d, col0 + 8 * s + e, n);
               thr_dot = knn_thr_dot(thr);
             }
@@ -212,7 +218,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_kernel(const __grid_constan
       st->cnt = 0;
       st->maxpos = 0;
       st->maxkey = ~0ull;
-      float thr = INFINITY, thr_dot = -INFINITY;
+      float thr = INFINITY, thr_dot = row_ok ? -INFINITY : INFINITY;   // padding rows (zero vectors) skip everything
       for (int t = 0; t < ntiles; ++t, ++it) {
         const uint32_t as = NACC == 2 ? (it & 1) : 0;
         mbar_wait(S.tmem_full + 8 * as, (NACC == 2 ? (it >> 1) : it) & 1);
@@ -396,7 +402,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       st->cnt = 0;
       st->maxpos = 0;
       st->maxkey = ~0ull;
-      float thr = INFINITY, thr_dot = -INFINITY;
+      float thr = INFINITY, thr_dot = row_ok ? -INFINITY : INFINITY;   // padding rows (zero vectors) skip everything
       for (int t = 0; t < ntiles; ++t, ++it) {
         const uint32_t as = it & 1;
         mbar_wait(S.tmem_full + 8 * as, (it >> 1) & 1);
@@ -510,6 +516,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       int stage = 0;
       uint32_t phase = 0, blk = 0;
       for (int64_t b = pair; b < nblocks2; b += npairs, ++blk) {
+        // Every CTA streams ALL of V once per row block.  V (1 GB at 1M x 512) does not fit in L2, so the
+        // CTAs only share each B tile through L2 while they walk V in step; left alone they drift apart
+        // over tens of blocks and the build turns HBM-bound (measured on the full 1M build: 1085 ms without,
+        // 920 ms with this meeting point).  The producers therefore meet between row blocks.
+        if (blk > 0 && a.wave_sync) {
+          const unsigned int want = blk * gridDim.x;
+          unsigned int seen;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.wave_sync) : "memory");
+            if (seen < want) __nanosleep(500);
+          } while (seen < want);
+        }
         // this CTA's 128 rows of A, once the previous block's MMAs have all completed
         if (blk > 0) mbar_wait_parked(a_empty, (blk - 1) & 1);
         if (leader) mbar_expect_tx(a_ready, 2 * A_BYTES);
@@ -528,6 +546,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
             }
           }
         }
+        if (a.wave_sync) atomicAdd(a.wave_sync, 1u);       // all loads of this row block are issued
       }
     }
   } else if (warp == 1) {
@@ -582,7 +601,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       st->cnt = 0;
       st->maxpos = 0;
       st->maxkey = ~0ull;
-      float thr = INFINITY, thr_dot = -INFINITY;
+      float thr = INFINITY, thr_dot = row_ok ? -INFINITY : INFINITY;   // padding rows (zero vectors) skip everything
       for (int t = 0; t < ntiles; ++t, ++it) {
         const uint32_t as = it & 1;
         mbar_wait(tmem_full + 8 * as, (it >> 1) & 1);
@@ -717,7 +736,15 @@ static int launch_knn3_t(int sm_count, const KnnArgs& a, cudaStream_t st, bool* 
   const size_t smem = fixed + (size_t)NS * 16384;
   auto kern = knn3_kernel<DIM>;
   SSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, kTcThreads, smem, st>>>(tmap, a, NS);
+  // inter-block meeting point of the producers (one word per device, zeroed on the launch stream)
+  static unsigned int* sync_word[64] = {};
+  int dev = 0;
+  SSW_CUDA(cudaGetDevice(&dev));
+  if (!sync_word[dev]) SSW_CUDA(cudaMalloc((void**)&sync_word[dev], 128));
+  SSW_CUDA(cudaMemsetAsync(sync_word[dev], 0, 4, st));
+  KnnArgs a2 = a;
+  a2.wave_sync = getenv("SSW_KNN_NOSYNC") ? nullptr : sync_word[dev];
+  kern<<<grid, kTcThreads, smem, st>>>(tmap, a2, NS);
   SSW_LAUNCHED();
   *launched = true;
   return SSW_OK;
@@ -863,7 +890,7 @@ int ssw_knn_build_device(int device, const void* d_vectors_f16, int64_t n, int d
   int rc = ensure_device(device, &sms);
   if (rc) return rc;
   if (row_begin == row_end) return SSW_OK;
-  KnnArgs a{static_cast<const __half*>(d_vectors_f16), n, k1, row_begin, row_end, d_out_idx, d_out_dist, 0};
+  KnnArgs a{static_cast<const __half*>(d_vectors_f16), n, k1, row_begin, row_end, d_out_idx, d_out_dist, 0, nullptr};
   if (const char* e = getenv("SSW_KNN_DEBUG")) a.debug = atoi(e);
   return launch_knn(sms, a, dim, (cudaStream_t)stream);
 }
