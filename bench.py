@@ -99,12 +99,14 @@ def cpu_reference_arm(steps, warmup, n_queries_per_step=2):
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi in the background (it needs about a second to start, so it is launched at program start);
+    samples are kept when their timestamp falls inside the timed window."""
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu_index, self.proc = gpu_index, None
+        self.gpu_index, self.proc, self.t0, self.t1 = gpu_index, None, None, None
 
     def start(self):
         try:
@@ -114,7 +116,14 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def window_begin(self):
+        self.t0 = time.time()
+
+    def window_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -123,25 +132,26 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), [n for n, v in zip(names, f[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, v in zip(names, f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        # samples taken while the GPU was busy: the sampler runs from the first warm-up step to the end of
-        # the timed steps (idle samples before the first launch sit at a lower clock and are dropped)
-        busy = [c for c in sm if c >= 0.6 * max(sm)] if sm else []
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(busy),
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.02 <= r[0] <= (self.t1 or r[0]) + 0.02]
+        how = "timestamps inside the timed legs"
+        if not inside and rows:       # clock skew / too short a window: fall back to the samples taken under load
+            top = max(r[1] for r in rows)
+            inside, how = [r for r in rows if r[1] >= 0.6 * top], "no sample inside the window: samples with the SM clock above idle"
+        sm = [r[1] for r in inside]
+        reasons = sorted({n for r in inside for n in r[3]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max((r[2] for r in rows), default=None),
+                "reasons": reasons, "samples": len(sm), "selection": how,
                 "window": "first warm-up step of the HBM-resident leg .. last timed step of the end-to-end leg"}
 
 
@@ -184,6 +194,9 @@ def main():
         emit(line)
         return
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     import torch
     import torch.distributed as dist
     from seesaw_b200 import _lib, synth
@@ -264,11 +277,12 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), float(t[1]), launches, kern
 
-    sampler = ClockSampler(local_rank)
     dev_ms, wall_ms, launches, (kern_ms, kern_n) = timed(step_resident, args.steps, profile=True,
-                                                        before=sampler.start if rank == 0 else None)
+                                                        before=sampler.window_begin if rank == 0 else None)
     e2e_steps = max(3, min(args.steps, 50))
     _, e2e_wall_ms, _, _ = timed(step_e2e, e2e_steps)
+    if rank == 0:
+        sampler.window_end()
     clocks = sampler.stop() if rank == 0 else None
 
     # parity spot check inside the bench: shard-merged result == single-call result of rank 0's view
