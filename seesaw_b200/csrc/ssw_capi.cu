@@ -258,6 +258,7 @@ int ssw_db_destroy(ssw_db* db) {
   cudaFree(db->d_part);
   cudaFree(db->d_last_bits);
   cudaFree(db->d_boxes);
+  cudaFree(db->d_xchg_timed_out);
   cudaFree(db->d_tc_ws);
   cudaFree(db->d_list_keys);
   cudaFree(db->d_list_dbidx);
@@ -470,10 +471,15 @@ static int scan_topk_impl(ssw_db* db, const float* d_queries, int nq, int k, con
       if (rc) return rc;
     }
   }
-  if (xc)
+  if (xc) {
+    if (!db->d_xchg_timed_out) {
+      SSW_CUDA(cudaMalloc((void**)&db->d_xchg_timed_out, 4));
+      SSW_CUDA(cudaMemset(db->d_xchg_timed_out, 0, 4));
+    }
     return launch_exchange_merge(db->d_list_keys, db->d_list_dbidx, lists, k, (int64_t)lists * k, nq, k, db->d_gthr,
-                                 xc->peers, xc->world, xc->rank, xc->nq_cap, xc->k_cap, xc->epoch, d_out_key,
-                                 d_out_dbidx, d_out_score, d_out_row, d_out_count, st);
+                                 xc->peers, xc->world, xc->rank, xc->nq_cap, xc->k_cap, xc->epoch, db->d_xchg_timed_out,
+                                 d_out_key, d_out_dbidx, d_out_score, d_out_row, d_out_count, st);
+  }
   return launch_merge(db->d_list_keys, db->d_list_dbidx, lists, k, (int64_t)lists * k, nq, k, db->d_gthr,
                       d_out_key, d_out_dbidx, d_out_score, d_out_row, d_out_count, st);
 }
@@ -618,6 +624,15 @@ static int scan_topk_host(ssw_db* db, const float* queries, int nq, int k, const
   if (rc) return rc;
   SSW_CUDA(cudaMemcpyAsync(h, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
   SSW_CUDA(cudaStreamSynchronize(st));
+  if (xc && db->d_xchg_timed_out) {
+    int flag = 0;
+    SSW_CUDA(cudaMemcpy(&flag, db->d_xchg_timed_out, 4, cudaMemcpyDeviceToHost));
+    if (flag) {
+      cudaMemset(db->d_xchg_timed_out, 0, 4);
+      set_error("fused exchange: a peer rank did not deliver its lists within 10 s");
+      return SSW_ERR_CUDA;
+    }
+  }
   if (out_dbidx) memcpy(out_dbidx, h, nk * 4);
   if (out_score) memcpy(out_score, h + db_b, nk * 4);
   if (out_row) memcpy(out_row, h + db_b + sc_b, nk * 8);

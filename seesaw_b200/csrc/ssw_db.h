@@ -26,6 +26,7 @@ struct ssw_db {
   uint32_t* d_last_bits = nullptr; // [n_rows/32 + pad] bit r set <=> device row r is the last row of its image
   int32_t* d_boxes = nullptr;      // [n_rows][5] x1,y1,x2,y2,zoom per device row (stage-2 rescoring; optional)
   std::vector<int32_t> h_img_dbidx; // host copy of d_img_dbidx (candidate id -> image index), filled on first use
+  int* d_xchg_timed_out = nullptr; // set by the fused exchange kernel when a peer never answered
   void* d_tc_ws = nullptr;         // prepared A operand of the tcgen05 batched scan (one batch)
 
   int64_t excl_words = 0;          // uint32 words of one exclusion bitmap (n_images bits, padded)
@@ -79,8 +80,9 @@ int launch_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_lists, in
 size_t xchg_bytes(int world, int nq_cap, int k_cap);
 int launch_exchange_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_lists, int64_t list_stride,
                           int64_t query_stride, int nq, int k, const uint64_t* d_thr, void* const* peers, int world,
-                          int rank, int nq_cap, int k_cap, uint32_t epoch, uint64_t* d_out_key, int32_t* d_out_dbidx,
-                          float* d_out_score, int64_t* d_out_row, int32_t* d_out_count, cudaStream_t st);
+                          int rank, int nq_cap, int k_cap, uint32_t epoch, int* d_timed_out, uint64_t* d_out_key,
+                          int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row, int32_t* d_out_count,
+                          cudaStream_t st);
 int launch_image_max(ssw_db* db, const float* d_scores, const uint8_t* d_row_mask, const uint32_t* d_excl,
                      int64_t n_padded, uint64_t* d_keys, int32_t* d_dbidx, cudaStream_t st);
 int launch_exclude_build(ssw_db* db, const int32_t* d_ids, const int64_t* d_offsets, int nq, uint32_t* d_bits,

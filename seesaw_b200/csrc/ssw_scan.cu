@@ -797,7 +797,10 @@ struct XchgArgs {
   void* peers[8];              // exchange buffer of every rank, as mapped on this device
   int world, rank, nq_cap, k_cap;
   uint32_t epoch;              // strictly increasing per call, same on all ranks
+  int* timed_out;              // set to 1 when a peer's flag did not arrive within kXchgTimeoutNs
 };
+
+constexpr unsigned long long kXchgTimeoutNs = 10ull * 1000 * 1000 * 1000;   // a dead peer must not hang the GPU
 
 __host__ __device__ inline size_t xchg_keys_bytes(int world, int nq_cap, int k_cap) { return (size_t)2 * world * nq_cap * k_cap * 8; }
 __host__ __device__ inline size_t xchg_dbidx_bytes(int world, int nq_cap, int k_cap) { return (size_t)2 * world * nq_cap * k_cap * 4; }
@@ -840,8 +843,17 @@ __global__ void __launch_bounds__(kMergeThreads, 1) exchange_merge_kernel(const 
                                                              xchg_dbidx_bytes(x.world, x.nq_cap, x.k_cap)) +
                            (((size_t)par * x.world + tid) * x.nq_cap + q);
     uint32_t v;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     do {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+      if (v != x.epoch) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > kXchgTimeoutNs) {
+          if (x.timed_out) *x.timed_out = 1;
+          break;
+        }
+      }
     } while (v != x.epoch);
   }
   __syncthreads();
@@ -856,9 +868,11 @@ __global__ void __launch_bounds__(kMergeThreads, 1) exchange_merge_kernel(const 
 
 int launch_exchange_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_lists, int64_t list_stride,
                           int64_t query_stride, int nq, int k, const uint64_t* d_thr, void* const* peers, int world,
-                          int rank, int nq_cap, int k_cap, uint32_t epoch, uint64_t* d_out_key, int32_t* d_out_dbidx,
-                          float* d_out_score, int64_t* d_out_row, int32_t* d_out_count, cudaStream_t st) {
+                          int rank, int nq_cap, int k_cap, uint32_t epoch, int* d_timed_out, uint64_t* d_out_key,
+                          int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row, int32_t* d_out_count,
+                          cudaStream_t st) {
   XchgArgs x{};
+  x.timed_out = d_timed_out;
   x.m = MergeArgs{d_keys, d_dbidx, n_lists, list_stride, query_stride, k, d_thr,
                   d_out_key, d_out_dbidx, d_out_score, d_out_row, d_out_count};
   for (int i = 0; i < world; ++i) x.peers[i] = peers[i];
