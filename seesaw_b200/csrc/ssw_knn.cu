@@ -523,9 +523,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
         if (blk > 0 && a.wave_sync) {
           const unsigned int want = blk * gridDim.x;
           unsigned int seen;
+          unsigned long long t0, t1;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
           do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.wave_sync) : "memory");
-            if (seen < want) __nanosleep(500);
+            if (seen < want) {
+              __nanosleep(500);
+              // the meeting point only improves L2 sharing: if some CTA is not even resident yet (GPU shared
+              // with another kernel) stop waiting instead of risking a dead lock
+              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+              if (t1 - t0 > 200000000ull) break;
+            }
           } while (seen < want);
         }
         // this CTA's 128 rows of A, once the previous block's MMAs have all completed
@@ -736,16 +744,22 @@ static int launch_knn3_t(int sm_count, const KnnArgs& a, cudaStream_t st, bool* 
   const size_t smem = fixed + (size_t)NS * 16384;
   auto kern = knn3_kernel<DIM>;
   SSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // inter-block meeting point of the producers (one word per device, zeroed on the launch stream)
-  static unsigned int* sync_word[64] = {};
-  int dev = 0;
-  SSW_CUDA(cudaGetDevice(&dev));
-  if (!sync_word[dev]) SSW_CUDA(cudaMalloc((void**)&sync_word[dev], 128));
-  SSW_CUDA(cudaMemsetAsync(sync_word[dev], 0, 4, st));
+  // inter-block meeting point of the producers: one word per launch, allocated and freed in stream order
+  unsigned int* sync_word = nullptr;
+  if (!getenv("SSW_KNN_NOSYNC")) {
+    SSW_CUDA(cudaMallocAsync((void**)&sync_word, 128, st));
+    SSW_CUDA(cudaMemsetAsync(sync_word, 0, 4, st));
+  }
   KnnArgs a2 = a;
-  a2.wave_sync = getenv("SSW_KNN_NOSYNC") ? nullptr : sync_word[dev];
+  a2.wave_sync = sync_word;
   kern<<<grid, kTcThreads, smem, st>>>(tmap, a2, NS);
-  SSW_LAUNCHED();
+  ++ssw::g_launch_count;
+  const cudaError_t le = cudaGetLastError();
+  if (sync_word) cudaFreeAsync(sync_word, st);
+  if (le != cudaSuccess) {
+    set_error(std::string("knn3_kernel launch: ") + cudaGetErrorString(le));
+    return SSW_ERR_CUDA;
+  }
   *launched = true;
   return SSW_OK;
 }
