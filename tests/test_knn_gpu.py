@@ -96,3 +96,17 @@ def test_edge_table_on_device_equals_post_process_graph_df(kg, n, dup):
     pd.testing.assert_frame_equal(df, want)
     g = kg.KNNGraph(df)
     assert g.nvecs == n and (np.diff(g.ind_ptr) >= 1).all()
+
+
+@pytest.mark.parametrize("n,dim,k", [(2, 512, 10), (257, 256, 1), (700, 512, 40), (900, 256, 63), (1300, 768, 33),
+                                     (513, 512, 32), (2049, 512, 5)])
+def test_knn_variants_and_limits(kg, n, dim, k):
+    """Every launch path: CTA pairs with N=256 (k1 <= 33 at dim 512), the TS pair kernel (larger k1), the single-CTA
+    kernel (dim 768); k1 up to the limit of 64; n not a multiple of any tile — bit-exact on lattice data."""
+    v = synth.synth_rows(0, n, dim, 35, "lattice", np.float32) * np.float32(0.25)
+    idx, dist = kg.knn_candidates(v, k)
+    oi, od = orc.exact_knn_candidates_blockwise(v, k, block=256)
+    assert idx.shape == oi.shape
+    assert (dist == od).all() and (idx == oi).all()
+    with pytest.raises(Exception):
+        kg.knn_candidates(synth.synth_rows(0, 100, dim, 1, "lattice", np.float32), 64)     # k1 = 65 > SSW_MAX_KNN_K1

@@ -343,3 +343,42 @@ def test_topk_from_scores_matches_get_top_dbidxs(eng, grouped):
         assert len(got) == len(d)
         assert (got.dbidx.values == d).all() and (got.max_score.values == s).all() and (got.best_row.values == r).all()
     idx.close()
+
+
+# ------------------------------------------------------------------ randomized configurations
+def test_random_configurations_both_kernels(eng):
+    """Seeded sweep over shapes the fixed cases do not hit together: ragged images, tiny and odd sizes, all dims,
+    k from 1 to 64, partial / multi-pass batches, permuted rows, both kernels — ids, rows and scores bit-exact
+    against the oracle on exact-arithmetic data."""
+    rng = np.random.default_rng(2024)
+    for trial in range(24):
+        dim = int(rng.choice([256, 512, 768]))
+        n_images = int(rng.choice([1, 2, 37, 149, 600, 2500]))
+        hi = int(rng.choice([1, 3, 17, 70]))
+        counts = rng.integers(1, hi + 1, size=n_images).astype(np.int64)
+        dbidx = synth.dbidx_of_rows(counts, int(rng.integers(0, 50)), int(rng.integers(1, 4)))
+        n = int(counts.sum())
+        vecs = synth.synth_rows(0, n, dim, 100 + trial, "lattice", np.float32)
+        if rng.random() < 0.5:
+            perm = rng.permutation(n)
+            vecs, dbidx = vecs[perm], dbidx[perm]
+        nq = int(rng.choice([1, 2, 9, 33, 64, 70]))
+        k = int(rng.choice([1, 5, 50, 64]))
+        mode = int(rng.choice([1, 2]))
+        qs = synth.lattice_queries(nq, dim, 500 + trial)
+        ids = np.unique(dbidx)
+        ex = [None if rng.random() < 0.3 else rng.choice(ids, size=int(rng.integers(0, len(ids) + 1)), replace=False)
+              for _ in range(nq)]
+        db = eng.PatchDatabase.from_arrays(vecs, dbidx, store="f16")
+        db.set_scan_mode(mode)
+        r = db.scan_topk(qs, k, exclude=ex)
+        for qi in range(nq):
+            o = orc.query_prelim(vecs, dbidx, qs[qi], k, exclude=ex[qi])
+            kk = len(o["dbidx"])
+            tag = (trial, dim, n_images, hi, nq, k, mode, qi)
+            assert r["count"][qi] == kk, tag
+            assert (r["dbidx"][qi, :kk] == o["dbidx"]).all(), tag
+            assert (r["row"][qi, :kk] == o["best_row"]).all(), tag
+            assert (r["score"][qi, :kk] == o["max_score"]).all(), tag
+            assert (r["dbidx"][qi, kk:] == -1).all(), tag
+        db.close()
