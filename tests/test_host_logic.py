@@ -1,0 +1,95 @@
+"""CPU tests of the host-side mirrors of the reference interface (no GPU): stage-2 rescoring, edge-table
+post-processing, the KNNGraph container, the id-set class."""
+import numpy as np
+import pandas as pd
+import pytest
+
+import cases
+import seesaw_oracle as orc
+from seesaw_b200 import synth
+
+
+@pytest.mark.parametrize("agg,aug", [("plain_score", "all"), ("avg_score", "all"), ("avg_score", "greater"), ("avg_score", "adjacent")])
+def test_host_rescore_matches_oracle(agg, aug):
+    """seesaw_b200.rescore (vectorised) == the oracle's pandas-style restatement of rescore_candidates / score_frame2."""
+    from seesaw_b200.rescore import rescore_candidates
+    counts = synth.patches_per_image(60, 1, 45, 3)
+    meta = synth.synth_vector_meta(counts, 4, dbidx_start=9, dbidx_stride=4)
+    n = int(counts.sum())
+    rng = np.random.default_rng(5)
+    scores = (rng.integers(-20, 21, size=n) / 16.0).astype(np.float32)          # many exact ties
+    want = orc.rescore_candidates(meta, scores, 7, agg_method=agg, aug_larger=aug)
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    groups = [np.arange(starts[i], starts[i + 1]) for i in range(len(counts))]
+    cols = {c: meta[c].to_numpy() for c in ("x1", "y1", "x2", "y2", "zoom_level")}
+    got = rescore_candidates(groups, np.unique(meta.dbidx.values), [scores[g] for g in groups], cols, 7,
+                             agg_method=agg, aug_larger=aug)
+    assert (got["dbidxs"] == want["dbidxs"]).all()
+    for a, b in zip(got["activations"], want["activations"]):
+        assert (a[["x1", "y1", "x2", "y2", "dbidx"]].values == b[["x1", "y1", "x2", "y2", "dbidx"]].values).all()
+        np.testing.assert_allclose(a.score.values, b.score.values, rtol=1e-6)
+
+
+def test_edge_table_host_functions_and_container(tmp_path):
+    from seesaw_b200 import knn_graph as kg
+    v = cases.knn_inputs(cases.KNN["knn_dups"])
+    oi, od = orc.exact_knn_candidates(v, 5)
+    want = orc.post_process_graph(oi, od, len(v))
+    got = kg.edges_from_candidates(oi, od, len(v))
+    pd.testing.assert_frame_equal(got, want)
+    # the generic form on a shuffled raw edge table
+    raw = pd.DataFrame({"src_vertex": np.repeat(np.arange(len(v)), oi.shape[1]), "dst_vertex": oi.reshape(-1),
+                        "distance": od.reshape(-1)})
+    pd.testing.assert_frame_equal(kg.post_process_graph_df(raw, len(v)), want)
+    # partial tables (the multi-GPU unit): rows [100, 200) with their own self edges
+    part = kg.edges_from_candidates(oi[100:200], od[100:200], len(v), src_offset=100)
+    pd.testing.assert_frame_equal(part.reset_index(drop=True),
+                                  want[(want.src_vertex >= 100) & (want.src_vertex < 200)].reset_index(drop=True))
+    g = kg.KNNGraph(want)
+    assert g.nvecs == len(v) and g.k in (4, 5) and g.ind_ptr[-1] == len(want)
+    assert (g.rev_lookup(7).src_vertex == 7).all()
+    small = g.restrict_k(k=3)
+    assert small.knn_df.dst_rank.max() == 2
+    with pytest.raises(AssertionError):
+        g.restrict_k(k=99)
+    g.save(str(tmp_path / "g"))
+    pd.testing.assert_frame_equal(kg.KNNGraph.from_file(str(tmp_path / "g")).knn_df, want)
+    with pytest.raises(FileExistsError):
+        g.save(str(tmp_path / "g"))                     # like the CLI: the output path must not exist
+    g.save(str(tmp_path / "g"), overwrite=True)
+
+
+def test_bitmap_matches_python_sets():
+    from seesaw_b200.bitmap import BitMap, FrozenBitMap, as_id_array
+    rng = np.random.default_rng(6)
+    for _ in range(20):
+        a = set(rng.integers(0, 200, size=rng.integers(0, 60)).tolist())
+        b = set(rng.integers(0, 200, size=rng.integers(0, 60)).tolist())
+        A, B = BitMap(a), BitMap(np.array(sorted(b), dtype=np.int64))
+        assert list(A) == sorted(a) and len(A) == len(a)
+        assert list(A - B) == sorted(a - b) and list(A | B) == sorted(a | b) and list(A & B) == sorted(a & b)
+        assert list(A.difference(B)) == sorted(a - b) and A.intersection_cardinality(B) == len(a & b)
+        assert np.array_equal(np.array(A), np.array(sorted(a), dtype=np.uint32))
+        assert all((x in A) == (x in a) for x in range(0, 200, 7))
+        C = BitMap(a)
+        C.update(b)
+        assert list(C) == sorted(a | b)
+        assert list(FrozenBitMap(a) - A) == []
+        assert np.array_equal(as_id_array(A), np.array(sorted(a), dtype=np.int64))
+    assert as_id_array(None).shape == (0,)
+
+
+def test_query_interface_loop_without_gpu():
+    """InteractiveQuery bookkeeping (query_interface.py:34-49) with a stub index."""
+    from seesaw_b200.indices import InteractiveQuery
+
+    class Stub:
+        def query(self, *, topk, exclude, **kw):
+            pool = [i for i in range(100) if i not in exclude]
+            return {"dbidxs": np.array(pool[:topk]), "activations": None}
+
+    iq = InteractiveQuery(Stub())
+    got = []
+    for _ in range(4):
+        got += iq.query_stateful(vector=None, batch_size=3)["dbidxs"].tolist()
+    assert got == list(range(12)) and sorted(iq.returned) == got
