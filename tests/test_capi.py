@@ -82,3 +82,46 @@ def test_every_entry_rejects_null_handles_without_a_device():
     assert L.ssw_lp_destroy(z) == 0 and L.ssw_xchg_destroy(0, z) == 0
     assert L.ssw_knn_build(0, z, 0, 10, 512, 3, 0, 10, z, z) == 1
     assert b"null" in L.ssw_last_error()
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: the header must compile as C99 and as C++ on its own."""
+    import subprocess
+    h = os.path.join(ROOT, "include", "seesaw_b200.h")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", h],
+                ["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", h]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
+def test_c_program_links_against_the_library(tmp_path):
+    """A C caller (what a cgo / JNI / ctypes-free maintainer would write) builds and runs against the .so;
+    without a GPU it must get SSW_ERR_NO_DEVICE and a message, not a crash."""
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stdlib.h>
+#include "seesaw_b200.h"
+int main(void) {
+  int n = -1;
+  if (ssw_device_count(&n) != SSW_OK) return 10;
+  float* v = (float*)calloc(4 * 512, sizeof(float));
+  int32_t ids[4] = {0, 0, 1, 1};
+  ssw_db* db = NULL;
+  int rc = ssw_db_create(&db, 0, v, SSW_F32, SSW_F16, 4, 512, ids, 0);
+  printf("devices=%d rc=%d msg=%s version=%d\n", n, rc, ssw_last_error(), ssw_version());
+  if (n == 0 && rc != SSW_ERR_NO_DEVICE) return 11;
+  if (rc == SSW_OK) ssw_db_destroy(db);
+  free(v);
+  return 0;
+}
+''')
+    exe = tmp_path / "t"
+    lib_dir = os.path.join(ROOT, "seesaw_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L", lib_dir, "-lseesaw_b200", f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "version=" in r.stdout
