@@ -2,14 +2,16 @@
 //
 // Replaces   all_pairs = 1. - V @ V.T ; np.argsort(all_pairs, axis=-1)[:, :k+1]
 // (seesaw/knn_graph.py:170-182, compute_exact_knn).  The N x N matrix is never materialised:
-// a CTA keeps a 128-row block of V in tensor memory as the A operand, streams every row of V
-// through shared memory as B (TMA, SWIZZLE_128B), accumulates 128 x NT dot products in TMEM and
-// the four epilogue warps (one thread per output row) turn each accumulator tile into
-// d = fp32(1 - dot) and keep the k1 smallest (d, column) pairs of their row.
+// a CTA keeps a 128-row block of V resident as the A operand (tensor memory in the TS variants, shared
+// memory in the CTA-pair N=256 variant that is the default), streams every row of V through shared
+// memory as B (TMA, SWIZZLE_128B), accumulates the dot products in TMEM and the four epilogue warps
+// (one thread per output row) turn each accumulator tile into d = fp32(1 - dot) and keep the k1
+// smallest (d, column) pairs of their row — one max tree and one compare per 32 columns in the
+// common case.  The edge table of post_process_graph_df is produced on the device too (bottom).
 // Ranking is on d, not on the dot: the rounding of 1 - dot merges near-equal dots into exact ties,
 // which break by ascending column (SURVEY.md §7 "Graph ties are created by the 1 - dot rounding").
-// Work: 2*N^2*DIM flops; HBM traffic is negligible (V is L2-resident for N <= ~60k, and streamed
-// once per 128-row block otherwise).
+// Work: 2*N^2*DIM flops; V is read from HBM about once per wave of row blocks (the CTAs walk it in
+// step and share it through L2).
 #include <algorithm>
 #include <cstdlib>
 #include <vector>

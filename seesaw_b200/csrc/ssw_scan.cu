@@ -11,11 +11,13 @@
 // shared memory: 8 warps x 3 stages x 8 KB = 192 KB in flight per SM, far above the ~45 KB
 // Little's law needs at 6.5 TB/s.  No thread ever issues a global load for vector data.
 // Compute: conflict-free 128-bit LDS, fp32 FMA against the query held in registers, a
-// transposing butterfly so 8 row sums cost 9 shuffles, then a warp-uniform segmented max over
-// the image ids, the exclusion bitmap test and a threshold-filtered insert into the CTA's top-k
-// list.  A global lower bound on the k-th best key (max over CTAs of their k-th best) is shared
-// through one L2 word so late candidates are rejected with one compare.
-// HBM bytes per row: dim*sizeof(T) + 4 (image id)  -> the roofline in DESIGN.md.
+// transposing butterfly so 8 row sums cost 9 shuffles, then a segmented max driven by the
+// image-boundary bitmap (per-lane running maxima, combined only when an image ends AND can still
+// matter), the exclusion bitmap test and a threshold-filtered insert into the CTA's top-k list.
+// A global lower bound on the k-th best key is shared through one L2 word so late candidates are
+// rejected with one compare: max over CTAs of their k-th best, and the pooled group-min bound over
+// the CTAs' published bests (pooled_group_min, ssw_common.cuh).
+// HBM bytes per row: dim*sizeof(T) + 1 bit (image boundary)  -> the roofline in DESIGN.md.
 #include <cuda.h>
 
 #include <algorithm>

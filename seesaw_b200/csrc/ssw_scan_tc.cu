@@ -18,10 +18,12 @@
 // so a 16x256b tcgen05.ld of half h hands thread (r = lane/4, j = lane%4) BOTH parts of one query for
 // columns 8i+2j, 8i+2j+1 (i = 0..3): hi + lo needs no shuffle and no lane is redundant.
 //
-// Epilogue cost model: per 128-row tile a thread does 64 x (FADD, FSETP, 2 SEL); an image
-// boundary costs one vote, and only when some lane's partial max reaches its query's threshold a quad
-// reduction (8 SHFL) plus the owner's threshold / exclusion / list work.  Everything lives in registers
-// and shared memory: no local memory, no out-of-line calls.
+// Epilogue cost model: per 128-row tile a thread folds 64 scores (FADD hi + lo, then a
+// depth-3 argmax tree per 8 columns: the epilogue warps run alone on their schedulers, so dependent-issue
+// latency is what a tile costs); an image boundary costs one vote, and only when some lane's partial max
+// reaches its query's threshold a quad reduction (8 SHFL) plus the owner's threshold / exclusion / list
+// work.  Everything lives in registers and shared memory: no local memory, no out-of-line calls.  A seventh
+// warp pools the CTAs' published bests into tighter thresholds for the whole life of the kernel.
 #include <algorithm>
 #include <cstdlib>
 
