@@ -349,6 +349,45 @@ def main():
                                 "queries_per_s": 1e3 / step_ms, "kernel_ms_avg": k1_ms / max(k1_n, 1),
                                 "achieved_gbs": bytes1 / (k1_ms / max(k1_n, 1) * 1e-3) / 1e9,
                                 "frac_of_peak": bytes1 / (k1_ms / max(k1_n, 1) * 1e-3) / 1e9 / line["roofline"]["peak"]}
+    # ---- BASELINE configs[1]: 120k images x ~40 patches x 512 fp16 on one GPU, through the reference-facing class
+    if rank == 0 and world == 1:
+        from seesaw_b200.engine import PatchDatabase
+        from seesaw_b200.indices import B200MultiscaleIndex, BitMap
+        counts2 = synth.patches_per_image(120_000, 20, 60, 3)
+        meta2 = synth.synth_vector_meta(counts2, 4)
+        db2 = PatchDatabase.synthetic(meta2["dbidx"].to_numpy().astype(np.int32), DIM, seed=4, kind="tri", store="f16",
+                                      device=local_rank)
+        idx2 = B200MultiscaleIndex.from_database(db2, meta2)
+        seen = BitMap(np.random.default_rng(5).choice(120_000, size=30, replace=False))
+        for _ in range(3):
+            idx2.query(vector=q_host[0], topk=3, shortlist_size=50, exclude=seen, agg_method="avg_score")
+        t0 = time.perf_counter()
+        reps = 20
+        for i in range(reps):
+            out2 = idx2.query(vector=q_host[i % NQ], topk=3, shortlist_size=50, exclude=seen, agg_method="avg_score")
+        ms_query = (time.perf_counter() - t0) / reps * 1e3
+        d_q2 = d_q[:1].contiguous()
+        bits2 = db2.build_exclude_bits([np.asarray(list(seen))], 1)
+        db2.set_scan_mode(1)
+        for _ in range(3):
+            db2.scan_topk_device(d_q2, TOPK, bits2)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            db2.scan_topk_device(d_q2, TOPK, bits2)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_k1 = e0.elapsed_time(e1) / 20
+        line["config2_multiscale_120k_images"] = {
+            "n_rows": int(db2.n_rows), "dim": DIM, "storage": "fp16",
+            "single_query_scan_ms": ms_k1, "single_query_scan_gbs": db2.n_rows * DIM * 2 / (ms_k1 * 1e-3) / 1e9,
+            "query_call_ms": ms_query, "query_call_qps": 1e3 / ms_query,
+            "query_call": "B200MultiscaleIndex.query(vector, topk=3, shortlist_size=50, exclude=30 seen ids, agg_method='avg_score'): "
+                          "stage 1 (K1) + stage 2 (K7) on the GPU, host buffers in, result dict with activation DataFrames out",
+            "returned": [int(x) for x in out2["dbidxs"]]}
+        idx2.close()
+        del db2, idx2
+        torch.cuda.empty_cache()
     # ---- kNN-graph build (BASELINE config 4): k=10 exact graph over 1M x 512, output rows split over the ranks
     if not args.no_knn:
         from seesaw_b200.knn_graph import knn_candidates_device

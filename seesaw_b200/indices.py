@@ -76,19 +76,25 @@ def _column_to_matrix(col) -> np.ndarray:
 class _GpuIndexMixin:
     """Device copy + host CSR shared by the multiscale and coarse classes."""
 
-    def _init_device(self, device, store):
+    def _init_device(self, device, store, db=None):
         dbidx = self.vector_meta["dbidx"].to_numpy()
         self._dbidx_of_row = dbidx.astype(np.int64)
         self.device = device
         self.store = store
-        self.db = PatchDatabase.from_arrays(self.vectors, dbidx.astype(np.int32), store=store, device=device)
         self._batcher = None
-        # stage-1 scores equal what a host rescoring of self.vectors would give (up to summation order)
-        # exactly when the HBM copy holds the same values: fp32 storage, or fp16-representable data
-        v = self.vectors
-        self._store_exact = store in ("f32", "fp32", "float32") or v.dtype == np.float16 or bool(
-            (v[: min(len(v), 4096)].astype(np.float16).astype(np.float32) == v[: min(len(v), 4096)]).all()
-            and (v.astype(np.float16).astype(np.float32) == v).all())
+        self._all_ids = np.sort(as_id_array(self.all_indices))     # eligible image ids, for the top-k clamp
+        if db is not None:
+            # serving-only: the vectors already live in HBM (from_database); no host copy is kept
+            assert db.n_rows == len(dbidx)
+            self.db, self._store_exact = db, True
+        else:
+            self.db = PatchDatabase.from_arrays(self.vectors, dbidx.astype(np.int32), store=store, device=device)
+            # stage-1 scores equal what a host rescoring of self.vectors would give (up to summation order)
+            # exactly when the HBM copy holds the same values: fp32 storage, or fp16-representable data
+            v = self.vectors
+            self._store_exact = store in ("f32", "fp32", "float32") or v.dtype == np.float16 or bool(
+                (v[: min(len(v), 4096)].astype(np.float16).astype(np.float32) == v[: min(len(v), 4096)]).all()
+                and (v.astype(np.float16).astype(np.float32) == v).all())
         # host CSR over ORIGINAL rows: rows of image i are _rows_sorted[_starts[i]:_starts[i+1]], ascending
         order = np.argsort(self._dbidx_of_row, kind="stable")
         sorted_ids = self._dbidx_of_row[order]
@@ -144,25 +150,33 @@ class B200MultiscaleIndex(_GpuIndexMixin, AccessMethod):
     the GPU.  Constructor and attributes follow MultiscaleIndex (multiscale_index.py:203-231)."""
 
     def __init__(self, *, embedding, vectors: np.ndarray, vector_meta: pd.DataFrame, vec_index=None,
-                 min_zoom_level=1, path: str = None, excluded=None, device: int = 0, store: str = "f16"):
+                 min_zoom_level=1, path: str = None, excluded=None, device: int = 0, store: str = "f16", _db=None):
         self.embedding = embedding
         self.path = path
         self.excluded = BitMap([]) if excluded is None else BitMap(as_id_array(excluded))
-        if min_zoom_level != 1:   # multiscale_index.py:224-231
+        if min_zoom_level != 1 and _db is None:   # multiscale_index.py:224-231
             keep = (vector_meta["zoom_level"] >= min_zoom_level).to_numpy()
             vector_meta = vector_meta[keep].reset_index(drop=True)
             vectors = vectors[keep]
-        self.vectors = np.ascontiguousarray(vectors)
+        self.vectors = None if vectors is None else np.ascontiguousarray(vectors)
         self.vector_meta = vector_meta
         self.vec_index = vec_index          # accepted for interface parity; the exact GPU scan supersedes it
         self.all_indices = FrozenBitMap(self.vector_meta["dbidx"].to_numpy()) - self.excluded
-        self._init_device(device, store)
+        self._init_device(device, store, db=_db)
         self._meta_cols = {c: self.vector_meta[c].to_numpy() for c in ("x1", "y1", "x2", "y2", "zoom_level")
                            if c in self.vector_meta.columns}
         self._boxes_on_device = len(self._meta_cols) == 5 and all(
             np.issubdtype(v.dtype, np.integer) for v in self._meta_cols.values())
         if self._boxes_on_device:
             self.db.set_boxes(*[self._meta_cols[c] for c in ("x1", "y1", "x2", "y2", "zoom_level")])
+
+    @staticmethod
+    def from_database(db: PatchDatabase, vector_meta: pd.DataFrame, *, embedding=None, path=None):
+        """Serving-only index over vectors that already live in HBM (a :class:`PatchDatabase`, e.g. one shard
+        generated or loaded on the device): both query stages run on the GPU, so no host copy of the
+        vectors is kept (``vectors`` is None; ``get_data`` / host rescoring are unavailable)."""
+        return B200MultiscaleIndex(embedding=embedding, vectors=None, vector_meta=vector_meta, path=path,
+                                   device=db.device, store="f16" if db.dtype == np.float16 else "f32", _db=db)
 
     @staticmethod
     def from_path(index_path: str, *, use_vec_index=False, device=0, store="f16", exclude=None, **options):
@@ -179,17 +193,26 @@ class B200MultiscaleIndex(_GpuIndexMixin, AccessMethod):
         return len(self.all_indices)
 
     # ---- stage 1 ---------------------------------------------------------------------------
+    def _prelim_arrays(self, qvec, topk_dbidx, exclude_dbidx):
+        """Stage 1 as plain arrays: dict(dbidx, score, row) best first, or None when nothing is eligible.
+        The clamp of multiscale_index.py:295-298 needs only the NUMBER of eligible images."""
+        ex = as_id_array(exclude_dbidx)
+        pos = np.searchsorted(self._all_ids, ex)
+        pos[pos == len(self._all_ids)] = 0
+        n_excluded = int(np.unique(ex[self._all_ids[pos] == ex]).shape[0]) if len(ex) and len(self._all_ids) else 0
+        k = min(int(topk_dbidx), len(self._all_ids) - n_excluded)
+        if k <= 0:
+            return None
+        return self._scan_one(qvec, k, ex)
+
     def _query_prelim(self, *, vector, topk_dbidx, exclude_dbidx=None, force_exact=False):
         """multiscale_index.py:291-312.  Returns DataFrame(dbidx, max_score) like the reference
         (plus best_row); an EMPTY frame when nothing is eligible (the reference returns the tuple
         ``[], [], []`` there, which its own caller cannot use)."""
-        ex = as_id_array(exclude_dbidx)
-        included = np.setdiff1d(as_id_array(self.all_indices), ex)
-        k = min(int(topk_dbidx), included.shape[0])
-        if k == 0:
+        r = self._prelim_arrays(np.asarray(vector, dtype=np.float32).reshape(-1), topk_dbidx, exclude_dbidx)
+        if r is None:
             return pd.DataFrame({"dbidx": np.zeros(0, np.int64), "max_score": np.zeros(0, np.float32),
                                  "best_row": np.zeros(0, np.int64)})
-        r = self._scan_one(np.asarray(vector, dtype=np.float32).reshape(-1), k, ex)
         return pd.DataFrame({"dbidx": r["dbidx"].astype(np.int64), "max_score": r["score"], "best_row": r["row"]})
 
     # ---- stage 1 + 2 -----------------------------------------------------------------------
@@ -198,34 +221,32 @@ class B200MultiscaleIndex(_GpuIndexMixin, AccessMethod):
         if shortlist_size is None:
             shortlist_size = topk * 5
         qvec = np.asarray(vector, dtype=np.float32).reshape(-1)
-        cand = self._query_prelim(vector=qvec, topk_dbidx=shortlist_size, exclude_dbidx=exclude,
-                                  force_exact=force_exact)
-        if len(cand) == 0:
+        cand = self._prelim_arrays(qvec, shortlist_size, exclude)
+        if cand is None:
             return {"dbidxs": np.zeros(0, dtype="int"), "activations": []}
         agg_method = kwargs.get("agg_method", "plain_score")
+        by_id = np.argsort(cand["dbidx"], kind="stable")               # the reference walks images in ascending dbidx (:388)
+        ids = cand["dbidx"][by_id].astype(np.int64)
+
+        def result(order, rows, scores):
+            acts = [pd.DataFrame({"x1": [self._meta_cols["x1"][r]], "y1": [self._meta_cols["y1"][r]],
+                                  "x2": [self._meta_cols["x2"][r]], "y2": [self._meta_cols["y2"][r]],
+                                  "dbidx": [d], "score": [s]}) for r, d, s in zip(rows[order], ids[order], scores[order])]
+            return {"dbidxs": ids[order].astype("int"), "activations": acts}
+
         if agg_method == "plain_score" and vector2 is None and kwargs.get("device_rescore", self._store_exact):
             # 'plain_score' rescoring recomputes exactly what stage 1 already returned — per image the max
             # patch score and the first row attaining it (:117-118) — so the shortlist only needs the
             # reference's final ordering: ascending dbidx, then a stable sort by score (:388-399).
-            by_id = cand.sort_values("dbidx", kind="stable")
-            sc = by_id["max_score"].to_numpy()
-            order = np.argsort(-sc.astype(np.float64), kind="stable")[:topk]
-            rows, ids = by_id["best_row"].to_numpy()[order], by_id["dbidx"].to_numpy()[order]
-            acts = [pd.DataFrame({"x1": [self._meta_cols["x1"][r]], "y1": [self._meta_cols["y1"][r]],
-                                  "x2": [self._meta_cols["x2"][r]], "y2": [self._meta_cols["y2"][r]],
-                                  "dbidx": [d], "score": [s]}) for r, d, s in zip(rows, ids, sc[order])]
-            return {"dbidxs": ids.astype("int"), "activations": acts}
-        ids = np.sort(cand["dbidx"].to_numpy())
+            sc = cand["score"][by_id]
+            return result(np.argsort(-sc.astype(np.float64), kind="stable")[:topk], cand["row"][by_id], sc)
         aug_larger = kwargs.get("aug_larger", "all")
         if (agg_method in ("plain_score", "avg_score") and aug_larger in ("all", "greater", "adjacent")
                 and kwargs.get("device_rescore", self._store_exact and (agg_method == "plain_score" or self._boxes_on_device))):
             # stage 2 on the device (K7): patch scores, IoU join and per-level averaging for the <= shortlist images
             sc, rows = self.db.rescore(qvec, ids, query2=vector2, agg_method=agg_method, aug_larger=aug_larger)
-            order = np.argsort(-sc, kind="stable")[:topk]              # images ascending in dbidx, stable by score (:388-399)
-            acts = [pd.DataFrame({"x1": [self._meta_cols["x1"][r]], "y1": [self._meta_cols["y1"][r]],
-                                  "x2": [self._meta_cols["x2"][r]], "y2": [self._meta_cols["y2"][r]],
-                                  "dbidx": [d], "score": [s]}) for r, d, s in zip(rows[order], ids[order], sc[order])]
-            return {"dbidxs": ids[order].astype("int"), "activations": acts}
+            return result(np.argsort(-sc, kind="stable")[:topk], rows, sc)   # stable by score over ascending dbidx (:388-399)
+        assert self.vectors is not None, "host rescoring needs the host copy of the vectors (index built with from_database)"
         groups = [self._rows_of(d) for d in ids]                      # CSR ranges, not an O(N) isin
         rows = np.concatenate(groups)
         sub = self.vectors[rows]

@@ -171,3 +171,23 @@ def test_device_stage2_avg_score_vs_oracle(ix, aug):
         for a, b in zip(got["activations"], want["activations"]):
             assert (a[["x1", "y1", "x2", "y2"]].values == b[["x1", "y1", "x2", "y2"]].values).all()
     idx.close()
+
+
+def test_serving_only_index_from_database(ix):
+    """from_database (vectors generated in HBM, no host copy) answers like the host-constructed index."""
+    from seesaw_b200.engine import PatchDatabase
+    counts = synth.patches_per_image(800, 3, 30, 31)
+    meta = synth.synth_vector_meta(counts, 32)
+    n = int(counts.sum())
+    db = PatchDatabase.synthetic(meta.dbidx.to_numpy().astype(np.int32), 512, seed=33, kind="lattice", store="f16")
+    served = ix.B200MultiscaleIndex.from_database(db, meta)
+    vecs = synth.synth_rows(0, n, 512, 33, "lattice", np.float32)
+    q = synth.lattice_queries(1, 512, 34)[0]
+    ex = np.unique(meta.dbidx.values)[::6]
+    for agg in ("plain_score", "avg_score"):
+        got = served.query(vector=q, topk=5, shortlist_size=30, exclude=ix.BitMap(ex), agg_method=agg)
+        want = orc.multiscale_query(vecs, meta, q, 5, 30, exclude=ex, agg_method=agg)
+        assert (np.asarray(got["dbidxs"]) == want["dbidxs"]).all()
+    assert served.vectors is None and len(served) == 800
+    assert (served.score(q) == vecs @ q).all()
+    served.close()
