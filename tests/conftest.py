@@ -11,6 +11,10 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the shared library is a build artefact (git-ignored): build it in-tree when a fresh checkout has none
+    if not os.path.exists(os.path.join(ROOT, "seesaw_b200", "libseesaw_b200.so")):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 @pytest.fixture(scope="session")
