@@ -314,7 +314,7 @@ def main():
                                ("ssw_scan_topk_sharded (C ABI, host buffers, every rank)" if not args.nccl_exchange else
                                 "ShardedPatchDatabase.scan_topk_device from pinned host buffers + .cpu()")},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "kernel": "ssw::scan_tc_kernel<512,128,10> (K2, tcgen05 batched scan)",
+                "roofline": {"bound": "hbm", "kernel": "ssw::scan_tc8_kernel<512,128,10,2> (K2, tcgen05 batched scan, 8 epilogue warps)",
                              "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": (achieved / peak) if achieved else None,
                              "traffic": ncu_traffic_bytes() if world == 1 else None,

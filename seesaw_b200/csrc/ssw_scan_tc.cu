@@ -247,7 +247,7 @@ __device__ __forceinline__ void scan_tc_boundary(EpiState& st, const EpiCtx& cx,
 // (expected list updates per query and CTA drop from k*ln(n/k) to a handful).  One warp per CTA sweeps
 // the queries for the whole life of the kernel and raises the thresholds the epilogue warps read each
 // tile; it never touches the epilogue's critical path.
-__device__ __forceinline__ void scan_tc_threshold_warp(const QShared& Q, const ScanTcArgs& a, int lane) {
+__device__ __forceinline__ void scan_tc_threshold_warp(const QShared& Q, const ScanTcArgs& a, int lane, int n_epi = 4) {
   constexpr int VMAX = 6;                       // up to 192 CTAs
   const int G = gridDim.x;
   int ngp = 1;
@@ -255,9 +255,9 @@ __device__ __forceinline__ void scan_tc_threshold_warp(const QShared& Q, const S
   const bool pooled = G >= ngp && G <= 32 * VMAX;
   volatile int* done = Q.done;
   constexpr int QB = 8;                         // queries whose loads are in flight together
-  while (*done < 4) {
+  while (*done < n_epi) {
 #pragma unroll 1
-    for (int q0 = 0; q0 < a.nq && *done < 4; q0 += QB) {      // leave promptly once the epilogue is through
+    for (int q0 = 0; q0 < a.nq && *done < n_epi; q0 += QB) {      // leave promptly once the epilogue is through
       uint32_t v[QB][VMAX];
       uint64_t g[QB];
 #pragma unroll
@@ -287,7 +287,7 @@ __device__ __forceinline__ void scan_tc_threshold_warp(const QShared& Q, const S
         }
       }
     }
-    if (*done < 4) __nanosleep(1000);
+    if (*done < n_epi) __nanosleep(1000);
   }
 }
 
@@ -569,6 +569,278 @@ __global__ void __launch_bounds__(kScanTcThreads, 1) scan_tc_kernel(const __grid
   if (warp == 1) tmem_dealloc(tmem, Cfg::TMEM_ALLOC);
 }
 
+// ------------------------------------------------------------------------------------------
+// Eight-warp epilogue variant.  The four-warp epilogue is bound by dependent-issue latency (one warp per
+// scheduler, nothing to switch to).  Here two warps share each 32-lane quarter of tensor memory: warp
+// q4 handles the quarter's half 0 (queries 16*q4 + r), warp q4 + 4 its half 1 (queries 16*q4 + 8 + r), so
+// a thread carries ONE query instead of two and every scheduler has two epilogue warps to alternate.
+// Everything else (operand layout, thresholds, lists, boundary walk) is the kernel above.
+// ------------------------------------------------------------------------------------------
+struct Epi1State {
+  float m;            // running max of this thread's columns for its quad's query
+  int c;
+  float thr;
+  int cur_img;
+};
+struct Epi1Ctx {
+  int j;
+  bool owner;         // j == 0 owns the quad's query
+  int own_q;
+  float inv, scale;
+  int64_t r_begin;
+  int slice_base;
+};
+
+__device__ __forceinline__ void scan_tc8_boundary(Epi1State& st, const Epi1Ctx& cx, const QShared& Q, const ScanTcArgs& a) {
+  if (__any_sync(0xffffffffu, st.m >= st.thr)) {
+    uint64_t k0 = ((uint64_t)f32_ordered(st.m) << 32) | (uint32_t)(0x7FFFFFFF - st.c);
+    uint64_t o0 = shfl_xor_u64(k0, 1);
+    k0 = o0 > k0 ? o0 : k0;
+    o0 = shfl_xor_u64(k0, 2);
+    k0 = o0 > k0 ? o0 : k0;
+    if (cx.owner) {
+      const float best = f32_from_ordered((uint32_t)(k0 >> 32));
+      if (best >= st.thr) {
+        const int col = 0x7FFFFFFF - (int)(uint32_t)(k0 & 0xFFFFFFFFu);
+        const uint64_t nthr = scan_tc_offer(Q, a, cx.own_q, best, cx.inv, cx.r_begin + col, st.cur_img, cx.slice_base);
+        st.thr = thr_to_acc(nthr, cx.scale);
+      }
+    }
+    __syncwarp();
+  }
+  st.m = -INFINITY;
+  st.c = 0;
+  ++st.cur_img;
+}
+
+__device__ __forceinline__ void scan_tc8_group(Epi1State& st, const Epi1Ctx& cx, const QShared& Q, const ScanTcArgs& a,
+                                               const uint32_t* v, uint32_t em, int colbase) {
+  float sa[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    sa[2 * i] = __uint_as_float(v[4 * i]) + __uint_as_float(v[4 * i + 2]);
+    sa[2 * i + 1] = __uint_as_float(v[4 * i + 1]) + __uint_as_float(v[4 * i + 3]);
+  }
+  const int cb = colbase + 2 * cx.j;
+  float ma;
+  int ia;
+  if (em == 0) {
+    argmax8(sa, ma, ia);
+    if (ma > st.m) { st.m = ma; st.c = cb + ((ia >> 1) << 3) + (ia & 1); }
+    return;
+  }
+  int lo = 0;
+  for (;;) {
+    const int p = em ? __ffs(em) - 1 : 31;
+    const uint32_t seg = (0xFFFFFFFFu >> (31 - p)) & (0xFFFFFFFFu << lo);
+    const uint32_t mine = seg >> (2 * cx.j);
+    float xa[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) xa[2 * i + e] = ((mine >> (8 * i + e)) & 1u) ? sa[2 * i + e] : -INFINITY;
+    argmax8(xa, ma, ia);
+    if (ma > st.m) { st.m = ma; st.c = cb + ((ia >> 1) << 3) + (ia & 1); }
+    if (em == 0) break;
+    em &= em - 1;
+    scan_tc8_boundary(st, cx, Q, a);
+    lo = p + 1;
+    if (lo == 32) break;
+  }
+}
+
+__device__ __forceinline__ void tmem_ld_wait_regs16(uint32_t* x) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]),
+                 "+r"(x[8]), "+r"(x[9]), "+r"(x[10]), "+r"(x[11]), "+r"(x[12]), "+r"(x[13]), "+r"(x[14]), "+r"(x[15])
+               :
+               : "memory");
+}
+
+constexpr int kScanTc8Threads = 64 + 8 * 32 + 32;   // producer, MMA, 8 epilogue warps, threshold warp
+
+template <int DIM, int NT, int NS, int NACC>
+__global__ void __launch_bounds__(kScanTc8Threads, 1) scan_tc8_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                   const ScanTcArgs a) {
+  using Cfg = TcCfg<DIM, NT, NACC>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem;
+  const TcSmem S = tc_carve(smem_raw, NS, Cfg::STAGE_BYTES, &smem);
+  uint8_t* after = smem + NS * Cfg::STAGE_BYTES + ((tc_bar_bytes(NS) + 15) / 16) * 16;
+  const QShared Q = qshared_carve(after, a.k);
+  if (threadIdx.x < 64) {
+    Q.thr[threadIdx.x] = 0;
+    Q.cnt[threadIdx.x] = 0;
+    Q.minpos[threadIdx.x] = 0;
+    Q.best[threadIdx.x] = 0;
+    if (threadIdx.x == 0) *Q.done = 0;
+  }
+  const uint32_t tmem = tc_setup(S, NS, Cfg::TMEM_ALLOC, &tmap, 256);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int img0 = a.part[blockIdx.x * kScanWarps], img1 = a.part[(blockIdx.x + 1) * kScanWarps];
+  const int64_t r_begin = a.row_ptr[img0], r_end = a.row_ptr[img1];
+  const int64_t nrows = r_end - r_begin;
+  const int ntiles = (int)((nrows + NT - 1) / NT);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      TcPipe p(NS);
+      for (int t = 0; t < ntiles; ++t) {
+        for (int kc = 0; kc < Cfg::KC; ++kc) {
+          mbar_wait_parked(S.empty + 8 * p.stage, p.phase ^ 1);
+          mbar_expect_tx(S.full + 8 * p.stage, Cfg::STAGE_BYTES);
+          tma_load_2d(S.stages + p.stage * Cfg::STAGE_BYTES, &tmap, kc * kTcKChunk, (int)(r_begin + (int64_t)t * NT),
+                      S.full + 8 * p.stage);
+          p.advance();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    TcPipe p(NS);
+    mbar_wait_parked(S.a_ready, 0);
+    tc_fence_after();
+    for (int t = 0; t < ntiles; ++t) {
+      const uint32_t as = NACC == 2 ? (t & 1) : 0;
+      mbar_wait_parked(S.tmem_empty + 8 * as, ((NACC == 2 ? (t >> 1) : t) & 1) ^ 1);
+      tc_fence_after();
+      for (int kc = 0; kc < Cfg::KC; ++kc) {
+        mbar_wait_parked(S.full + 8 * p.stage, p.phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t bdesc = make_bdesc_sw128(S.stages + p.stage * Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            mma_f16_ts(tmem + Cfg::ACC_BASE + as * NT, tmem + Cfg::A_BASE + kc * 32 + k * 8, bdesc + 2 * k, Cfg::IDESC,
+                       (kc | k) != 0);
+          tc_commit(S.empty + 8 * p.stage);
+        }
+        __syncwarp();
+        p.advance();
+      }
+      if (lane == 0) tc_commit(S.tmem_full + 8 * as);
+      __syncwarp();
+    }
+  } else if (warp == 10) {
+    scan_tc_threshold_warp(Q, a, lane, 8);
+  } else {
+    // ===== epilogue warps 2..9: quarter = warp % 4, half = (warp - 2) / 4
+    const int q4 = warp & 3, h = (warp - 2) >> 2;
+    const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
+    const int k = a.k;
+    if (h == 0) {          // A operand: the first warp of every quarter copies its 32 TMEM lanes
+      const uint4* src = reinterpret_cast<const uint4*>(a.a_img + (size_t)(q4 * 32 + lane) * (DIM / 2));
+#pragma unroll 1
+      for (int c = 0; c < Cfg::A_COLS / 32; ++c) {
+        uint32_t rr[32];
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+          const uint4 w = __ldg(src + c * 8 + x);
+          rr[4 * x] = w.x;
+          rr[4 * x + 1] = w.y;
+          rr[4 * x + 2] = w.z;
+          rr[4 * x + 3] = w.w;
+        }
+        tmem_st32(lane_addr + Cfg::A_BASE + c * 32, rr);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(S.a_ready);
+    }
+    const int slice_base = img0 >> 5;
+    if (a.excl && a.excl_slice_words > 0 && img1 > img0) {
+      const int nw = ((img1 - 1) >> 5) - slice_base + 1;
+      for (int i = 0; i < 8; ++i) {
+        const int qs = q4 * 16 + h * 8 + i;
+        if (qs >= a.nq) break;
+        for (int w = lane; w < nw; w += 32)
+          Q.excl[qs * a.excl_slice_words + w] = __ldg(a.excl + (size_t)qs * a.excl_words + slice_base + w);
+      }
+      __syncwarp();
+    }
+    Epi1Ctx cx;
+    cx.slice_base = slice_base;
+    cx.j = lane & 3;
+    const int r = lane >> 2;
+    const int qA = q4 * 16 + h * 8 + r;
+    cx.own_q = qA;
+    cx.owner = cx.j == 0 && qA < a.nq;
+    cx.inv = __ldg(a.inv_scale + qA);
+    cx.scale = 1.0f / cx.inv;
+    cx.r_begin = r_begin;
+    Epi1State st;
+    st.m = -INFINITY;
+    st.c = 0;
+    st.thr = -INFINITY;
+    st.cur_img = img0;
+
+    constexpr int NG = NT / 32;
+    static_assert(NG == 2 || NG == 4, "tile must be 64 or 128 rows");
+    uint32_t wb[NG + 1];
+    auto fetch_bits = [&](int t) {
+      const uint32_t* p = a.last_bits + ((r_begin + (int64_t)t * NT) >> 5);
+#pragma unroll
+      for (int i = 0; i <= NG; ++i) wb[i] = __ldg(p + i);
+    };
+    if (ntiles > 0) fetch_bits(0);
+    const uint32_t half_addr = (uint32_t)(h * 16) << 16;
+    for (int t = 0; t < ntiles; ++t) {
+      const uint32_t as = NACC == 2 ? (t & 1) : 0;
+      const int64_t row0 = r_begin + (int64_t)t * NT;
+      const int sh = (int)(row0 & 31);
+      const int valid = (int)min((int64_t)NT, r_end - row0);
+      uint32_t ends[NG];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const int rem = valid - 32 * g;
+        const uint32_t keep = rem >= 32 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+        ends[g] = __funnelshift_r(wb[g], wb[g + 1], sh) & keep;
+      }
+      if (t + 1 < ntiles) fetch_bits(t + 1);
+      st.thr = thr_to_acc(Q.thr[qA], cx.scale);
+      mbar_wait(S.tmem_full + 8 * as, (NACC == 2 ? (t >> 1) : t) & 1);
+      tc_fence_after();
+      const uint32_t acc = lane_addr + half_addr + Cfg::ACC_BASE + as * NT;
+      const int colbase = (int)(row0 - r_begin);
+      uint32_t va[16], vb[16];
+      tmem_ld_16x256b_x4(acc, va);
+      tmem_ld_wait_regs16(va);
+#pragma unroll 1
+      for (int gp = 0; gp < NG; gp += 2) {
+        uint32_t eA = ends[0], eB = ends[1];
+        if constexpr (NG == 4) {
+          eA = gp ? ends[2] : eA;
+          eB = gp ? ends[3] : eB;
+        }
+        tmem_ld_16x256b_x4(acc + 32 * (gp + 1), vb);
+        scan_tc8_group(st, cx, Q, a, va, eA, colbase + 32 * gp);
+        tmem_ld_wait_regs16(vb);
+        if (gp + 2 < NG) tmem_ld_16x256b_x4(acc + 32 * (gp + 2), va);
+        scan_tc8_group(st, cx, Q, a, vb, eB, colbase + 32 * (gp + 1));
+        if (gp + 2 < NG) tmem_ld_wait_regs16(va);
+      }
+      tc_fence_before();
+      mbar_arrive(S.tmem_empty + 8 * as);
+    }
+    __syncwarp();
+    if (lane == 0) atomicAdd(Q.done, 1);
+    {
+      const int nqw = min(8, a.nq - (q4 * 16 + h * 8));
+#pragma unroll 4
+      for (int e = lane; e < nqw * k; e += 32) {
+        const int qi = q4 * 16 + h * 8 + e / k, sl = e % k;
+        const bool ok = sl < Q.cnt[qi];
+        const int64_t o = ((int64_t)qi * gridDim.x + blockIdx.x) * k + sl;
+        a.list_keys[o] = ok ? Q.keys[sl * 64 + qi] : 0ull;
+        a.list_dbidx[o] = ok ? __ldg(a.img_dbidx + Q.img[sl * 64 + qi]) : -1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, Cfg::TMEM_ALLOC);
+}
+
 template <int DIM, int NT, int NS, int NACC>
 static int launch_scan_tc_t(ssw_db* db, const ScanTcArgs& a, cudaStream_t st) {
   using Cfg = TcCfg<DIM, NT, NACC>;
@@ -585,11 +857,20 @@ static int launch_scan_tc_t(ssw_db* db, const ScanTcArgs& a, cudaStream_t st) {
       smem += (size_t)64 * words * 4;
     }
   }
-  auto kern = scan_tc_kernel<DIM, NT, NS, NACC>;
-  SSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  prof_begin(db, st);      // times the scan kernel alone (not the query preparation)
-  kern<<<db->scan_grid, kScanTcThreads, smem, st>>>(tmap, a2);
-  prof_end(db, st);
+  static const bool epi4 = [] { const char* e = getenv("SSW_TC_EPI4"); return e && e[0] == '1'; }();
+  if (epi4) {
+    auto kern = scan_tc_kernel<DIM, NT, NS, NACC>;
+    SSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prof_begin(db, st);      // times the scan kernel alone (not the query preparation)
+    kern<<<db->scan_grid, kScanTcThreads, smem, st>>>(tmap, a2);
+    prof_end(db, st);
+  } else {
+    auto kern = scan_tc8_kernel<DIM, NT, NS, NACC>;
+    SSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prof_begin(db, st);
+    kern<<<db->scan_grid, kScanTc8Threads, smem, st>>>(tmap, a2);
+    prof_end(db, st);
+  }
   SSW_LAUNCHED();
   return SSW_OK;
 }

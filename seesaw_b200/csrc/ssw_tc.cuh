@@ -226,7 +226,8 @@ __device__ __forceinline__ TcSmem tc_carve(uint8_t* smem, int ns, int stage_byte
 __host__ __device__ constexpr int tc_bar_bytes(int ns) { return 16 * ns + 16 + 16 + 8 + 8; }
 
 // Called by every thread at kernel start.  Returns the TMEM base address.
-__device__ __forceinline__ uint32_t tc_setup(const TcSmem& s, int ns, uint32_t tmem_cols, const CUtensorMap* tmap) {
+__device__ __forceinline__ uint32_t tc_setup(const TcSmem& s, int ns, uint32_t tmem_cols, const CUtensorMap* tmap,
+                                             uint32_t epilogue_threads = 128) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(tmap);
@@ -236,7 +237,7 @@ __device__ __forceinline__ uint32_t tc_setup(const TcSmem& s, int ns, uint32_t t
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(s.tmem_full + 8 * i, 1);
-      mbar_init(s.tmem_empty + 8 * i, 128);
+      mbar_init(s.tmem_empty + 8 * i, epilogue_threads);
     }
     mbar_init(s.a_ready, 128);
     fence_mbar_init();
