@@ -133,7 +133,7 @@ int ssw_scan_topk_sharded(ssw_db* db, const float* queries, int nq, int k, const
                           int nq_cap, int k_cap, uint32_t epoch, int32_t* out_dbidx, float* out_score,
                           int64_t* out_row, int32_t* out_count);
 
-/* Kernel selection for ssw_scan_topk*: 0 = auto (streaming SIMT kernel for nq < 8 queries,
+/* Kernel selection for ssw_scan_topk*: 0 = auto (streaming SIMT kernel for a single query or k > 64,
  * tcgen05 batched kernel otherwise), 1 = force streaming kernel, 2 = force tcgen05 kernel. */
 int ssw_set_scan_mode(ssw_db* db, int mode);
 

@@ -448,7 +448,7 @@ static int scan_topk_impl(ssw_db* db, const float* d_queries, int nq, int k, con
     set_error("tcgen05 batched scan needs fp16 storage, dim 256/512/768 and k <= 64");
     return SSW_ERR_INVALID;
   }
-  const bool use_tc = db->scan_mode == 2 || (db->scan_mode == 0 && tc_ok && nq >= 8);
+  const bool use_tc = db->scan_mode == 2 || (db->scan_mode == 0 && tc_ok && nq >= 2);   // one batched pass costs about one streaming pass
   if (use_tc) {
     if (!db->d_tc_ws) SSW_CUDA(cudaMalloc(&db->d_tc_ws, scan_tc_workspace_bytes(db->dim, db->scan_grid)));
     for (int q0 = 0; q0 < nq; q0 += SSW_MAX_BATCH) {
