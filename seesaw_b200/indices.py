@@ -111,12 +111,24 @@ class _GpuIndexMixin:
         sessions (one GPU pass per batch instead of one per session)."""
         self._batcher = batcher
 
+    def _map_rows(self, rows):
+        """device-reported ORIGINAL rows -> positions in this index's vectors / vector_meta (identity, except
+        for a subset view that shares its parent's database)."""
+        return rows
+
+    def _always_excluded(self):
+        return None
+
     def _scan_one(self, qvec, k, ex):
+        extra = self._always_excluded()
+        if extra is not None:
+            ex = np.concatenate([np.asarray(ex, dtype=np.int64).reshape(-1), extra])
         if self._batcher is not None:
-            return self._batcher.scan_topk_one(qvec, k, ex)
+            r = self._batcher.scan_topk_one(qvec, k, ex)
+            return dict(dbidx=r["dbidx"], score=r["score"], row=self._map_rows(r["row"]))
         r = self.db.scan_topk(qvec.reshape(1, -1), k, exclude=[ex])
         n = int(r["count"][0])
-        return dict(dbidx=r["dbidx"][0, :n], score=r["score"][0, :n], row=r["row"][0, :n])
+        return dict(dbidx=r["dbidx"][0, :n], score=r["score"][0, :n], row=self._map_rows(r["row"][0, :n]))
 
     def score(self, vec):
         """Full score vector in original row order (multiscale_index.py:284-285, coarse_index.py:37-38)."""
@@ -245,6 +257,7 @@ class B200MultiscaleIndex(_GpuIndexMixin, AccessMethod):
                 and kwargs.get("device_rescore", self._store_exact and (agg_method == "plain_score" or self._boxes_on_device))):
             # stage 2 on the device (K7): patch scores, IoU join and per-level averaging for the <= shortlist images
             sc, rows = self.db.rescore(qvec, ids, query2=vector2, agg_method=agg_method, aug_larger=aug_larger)
+            rows = self._map_rows(rows)
             return result(np.argsort(-sc, kind="stable")[:topk], rows, sc)   # stable by score over ascending dbidx (:388-399)
         assert self.vectors is not None, "host rescoring needs the host copy of the vectors (index built with from_database)"
         groups = [self._rows_of(d) for d in ids]                      # CSR ranges, not an O(N) isin
@@ -265,14 +278,67 @@ class B200MultiscaleIndex(_GpuIndexMixin, AccessMethod):
         rows = self._rows_of(dbidx)
         return self.vector_meta.iloc[rows].assign(vectors=list(self.vectors[rows]))
 
-    def subset(self, indices):
-        """multiscale_index.py:364-376 — a new index over the rows of the given images."""
+    def subset(self, indices, share_device=False):
+        """multiscale_index.py:364-376 — a new index over the rows of the given images.  With
+        ``share_device=True`` the subset keeps using THIS index's database in HBM and only masks the other
+        images out of every scan (a device-side image mask instead of a second copy of the vectors); the
+        host-side ``vectors`` / ``vector_meta`` of the subset are renumbered like the reference's."""
         mask = np.isin(self._dbidx_of_row, as_id_array(indices))
         if mask.all():
             return self
+        if share_device:
+            return _SharedSubset(self, mask)
+        assert self.vectors is not None, "a copying subset needs the host vectors; use share_device=True"
         return B200MultiscaleIndex(embedding=self.embedding, vectors=self.vectors[mask],
                                    vector_meta=self.vector_meta[mask].reset_index(drop=True),
                                    device=self.device, store=self.store)
+
+
+class _SharedSubset(B200MultiscaleIndex):
+    """Subset view over the parent's device database (see B200MultiscaleIndex.subset)."""
+
+    def __init__(self, parent, row_mask):
+        self._parent = parent
+        self.embedding, self.path, self.vec_index = parent.embedding, parent.path, None
+        self.excluded = parent.excluded
+        self._parent_rows = np.flatnonzero(row_mask)                       # subset position -> parent row
+        self.vectors = None if parent.vectors is None else parent.vectors[row_mask]
+        self.vector_meta = parent.vector_meta[row_mask].reset_index(drop=True)
+        self._dbidx_of_row = parent._dbidx_of_row[row_mask]
+        keep = np.unique(self._dbidx_of_row)
+        self.all_indices = FrozenBitMap(keep) - self.excluded
+        self._all_ids = np.sort(as_id_array(self.all_indices))
+        self._complement = np.setdiff1d(parent._img_ids, keep).astype(np.int64)   # masked out of every scan
+        self.db, self.device, self.store = parent.db, parent.device, parent.store
+        self._batcher, self._store_exact = None, parent._store_exact
+        order = np.argsort(self._dbidx_of_row, kind="stable")
+        self._img_ids, self._starts = np.unique(self._dbidx_of_row[order], return_index=True)
+        self._starts = np.append(self._starts, len(order))
+        self._rows_sorted = order
+        self._meta_cols = {c: v[row_mask] for c, v in parent._meta_cols.items()}
+        self._boxes_on_device = parent._boxes_on_device
+
+    def _map_rows(self, rows):
+        return np.searchsorted(self._parent_rows, np.asarray(rows, dtype=np.int64))
+
+    def _always_excluded(self):
+        return self._complement
+
+    def score(self, vec):
+        return self._parent.score(vec)[self._parent_rows]
+
+    def top_dbidxs(self, *, vec_idxs, scores, exclude=None, topk):
+        ex = np.concatenate([as_id_array(exclude), self._complement])
+        r = self._parent.top_dbidxs(vec_idxs=self._parent_rows[np.asarray(vec_idxs, dtype=np.int64)], scores=scores,
+                                    exclude=ex, topk=topk)
+        return r.assign(best_row=self._map_rows(r["best_row"].to_numpy()))
+
+    def subset(self, indices, share_device=True):
+        keep_rows = np.isin(self._parent._dbidx_of_row, np.intersect1d(as_id_array(indices), self._img_ids))
+        return _SharedSubset(self._parent, keep_rows)
+
+    def close(self):          # the database belongs to the parent
+        pass
 
 
 class B200CoarseIndex(_GpuIndexMixin, AccessMethod):

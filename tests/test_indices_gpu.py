@@ -191,3 +191,44 @@ def test_serving_only_index_from_database(ix):
     assert served.vectors is None and len(served) == 800
     assert (served.score(q) == vecs @ q).all()
     served.close()
+
+
+def test_subset_as_device_mask(ix):
+    """subset(share_device=True): no second copy in HBM, other images masked out of every scan; results equal the
+    copying subset and the oracle on the masked data, rows renumbered like the reference's subset."""
+    counts = synth.patches_per_image(1200, 2, 25, 41)
+    meta = synth.synth_vector_meta(counts, 42, dbidx_start=3, dbidx_stride=3)
+    n = int(counts.sum())
+    vecs = synth.synth_rows(0, n, 512, 43, "lattice", np.float32)
+    idx = ix.B200MultiscaleIndex(embedding=None, vectors=vecs, vector_meta=meta, store="f16")
+    keep = np.unique(meta.dbidx.values)[1::4]
+    view = idx.subset(ix.BitMap(keep), share_device=True)
+    copy = idx.subset(ix.BitMap(keep))
+    assert view.db is idx.db and copy.db is not idx.db
+    mask = np.isin(meta.dbidx.values, keep)
+    sub_v, sub_m = vecs[mask], meta[mask].reset_index(drop=True)
+    assert len(view) == len(keep) and (view.vectors == sub_v).all() and view.vector_meta.equals(sub_m)
+    qs = synth.lattice_queries(3, 512, 44)
+    seen = keep[::9]
+    for q in qs:
+        assert (view.score(q) == sub_v @ q).all()
+        for agg in ("plain_score", "avg_score"):
+            a = view.query(vector=q, topk=4, shortlist_size=25, exclude=ix.BitMap(seen), agg_method=agg)
+            b = copy.query(vector=q, topk=4, shortlist_size=25, exclude=ix.BitMap(seen), agg_method=agg)
+            w = orc.multiscale_query(sub_v, sub_m, q, 4, 25, exclude=seen, agg_method=agg)
+            assert (np.asarray(a["dbidxs"]) == w["dbidxs"]).all() and (np.asarray(b["dbidxs"]) == w["dbidxs"]).all()
+            for x, y in zip(a["activations"], w["activations"]):
+                assert (x[["x1", "y1", "x2", "y2"]].values == y[["x1", "y1", "x2", "y2"]].values).all()
+        p = view._query_prelim(vector=q, topk_dbidx=30, exclude_dbidx=ix.BitMap(seen))
+        o = orc.query_prelim(sub_v, sub_m.dbidx.values, q, 30, exclude=seen)
+        assert (p.dbidx.values == o["dbidx"]).all() and (p.best_row.values == o["best_row"]).all()
+    # everything of the subset excluded -> empty; a subset of the subset
+    assert len(view.query(vector=qs[0], topk=3, shortlist_size=10, exclude=ix.BitMap(keep))["dbidxs"]) == 0
+    inner = view.subset(ix.BitMap(keep[::2]))
+    w = orc.multiscale_query(vecs[np.isin(meta.dbidx.values, keep[::2])],
+                             meta[np.isin(meta.dbidx.values, keep[::2])].reset_index(drop=True), qs[1], 3, 20)
+    assert (np.asarray(inner.query(vector=qs[1], topk=3, shortlist_size=20)["dbidxs"]) == w["dbidxs"]).all()
+    view.close()
+    copy.close()
+    assert idx.query(vector=qs[0], topk=2, shortlist_size=10)["dbidxs"].shape == (2,)      # parent still alive
+    idx.close()
