@@ -388,6 +388,32 @@ def main():
         idx2.close()
         del db2, idx2
         torch.cuda.empty_cache()
+    # ---- BASELINE configs[0]: coarse index, 10k images x 512, one vector per image, top-10 with 300 excluded
+    if rank == 0 and world == 1:
+        import pandas as pd
+        from seesaw_b200.indices import B200CoarseIndex, BitMap as _BitMap
+        vc = synth.synth_rows(0, 10_000, DIM, 0, "tri", np.float32)
+        cidx = B200CoarseIndex(embedding=None, vectors=vc, vector_meta=pd.DataFrame({"dbidx": np.arange(10_000, dtype=np.int64)}),
+                               device=local_rank)
+        exc = np.sort(np.random.default_rng(2).choice(10_000, size=300, replace=False))
+        exb = _BitMap(exc)
+        for _ in range(3):
+            rc_ = cidx.query(topk=10, vector=q_host[0], exclude=exb)
+        t0 = time.perf_counter()
+        for i in range(50):
+            rc_ = cidx.query(topk=10, vector=q_host[i % NQ], exclude=exb)
+        ms_ours = (time.perf_counter() - t0) / 50 * 1e3
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import seesaw_oracle as _orc
+        t0 = time.perf_counter()
+        for i in range(20):
+            ro_ = _orc.coarse_query(vc, np.arange(10_000), q_host[i % NQ], 10, exclude=exc)
+        ms_cpu = (time.perf_counter() - t0) / 20 * 1e3
+        same = bool((np.asarray(rc_["dbidxs"]) == _orc.coarse_query(vc, np.arange(10_000), q_host[49 % NQ], 10, exclude=exc)["dbidxs"]).all())
+        line["config1_coarse_10k"] = {"query_call_ms": ms_ours, "cpu_oracle_ms": ms_cpu, "ids_equal_to_oracle": same,
+                                      "query_call": "B200CoarseIndex.query(topk=10, vector, exclude=300 ids): host buffers in, result dict out",
+                                      "cpu": f"oracle.coarse_query (numpy port of coarse_index.py:57-96) on {os.cpu_count()} host cores"}
+        cidx.close()
     # ---- kNN-graph build (BASELINE config 4): k=10 exact graph over 1M x 512, output rows split over the ranks
     if not args.no_knn:
         from seesaw_b200.knn_graph import knn_candidates_device
