@@ -10,9 +10,15 @@ import json
 import os
 import sys
 
-import numpy as np
-import torch
-import torch.distributed as dist
+# one JSON line on the real stdout; whatever libraries print (NCCL's version banner) goes to stderr
+os.environ.setdefault("NCCL_DEBUG", "WARN")
+sys.stdout.flush()
+_real_stdout = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from seesaw_b200 import synth  # noqa: E402
@@ -59,10 +65,11 @@ res = sdb.scan_topk_device(q, K, d_exclude_bits=bits)
 torch.cuda.synchronize()
 if rank == 0:
     gb = rows_total * DIM * 2 / 1e9
-    print(json.dumps({"config": f"{rows_total} x {DIM} fp16 ({gb:.1f} GB) over {world} GPU(s), {rows_total // world} rows per GPU",
+    _real_stdout.write(json.dumps({"config": f"{rows_total} x {DIM} fp16 ({gb:.1f} GB) over {world} GPU(s), {rows_total // world} rows per GPU",
                       "batched_64": {"ms_per_batch": ms_batch, "queries_per_s": NQ / ms_batch * 1e3, "aggregate_hbm_gbs": gb / ms_batch * 1e3},
                       "single_query": {"ms": ms_single, "aggregate_hbm_gbs": gb / ms_single * 1e3},
-                      "top1_dbidx_q0": int(res["dbidx"][0, 0]), "count_q0": int(res["count"][0])}))
+                      "top1_dbidx_q0": int(res["dbidx"][0, 0]), "count_q0": int(res["count"][0])}) + "\n")
+    _real_stdout.flush()
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()

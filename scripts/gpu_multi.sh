@@ -11,5 +11,5 @@ for n in 2 4 8; do
   fi
 done
 if [ "$N" = "8" ]; then
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 scripts/bench_config5.py 2> gpurun_out/config5_n8.err | grep "^{" > gpurun_out/config5_n8.json; echo "config5 rc=$?"; true 2> gpurun_out/config5_n8.err; echo "config5 rc=$?"; tail -2 gpurun_out/config5_n8.err; cat gpurun_out/config5_n8.json
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 scripts/bench_config5.py > gpurun_out/config5_n8.json 2> gpurun_out/config5_n8.err; echo "config5 rc=$?"; tail -2 gpurun_out/config5_n8.err; cat gpurun_out/config5_n8.json
 fi
