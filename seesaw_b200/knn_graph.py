@@ -130,6 +130,12 @@ class KNNGraph:
         self.nvecs = ks.shape[0]
         self.ind_ptr = get_lookup_ranges(knn_df.src_vertex, self.nvecs)
 
+    def _check_rep(self):
+        """knn_graph.py:258-262: with one self edge per vertex the sources and destinations coincide."""
+        srcs, dsts = np.unique(self.knn_df.src_vertex.values), np.unique(self.knn_df.dst_vertex.values)
+        assert np.array_equal(srcs, dsts), "self edges should guarantee this"
+        assert self._ks.index.max() + 1 == len(srcs), "self edges guarantee this"
+
     @staticmethod
     def from_vectors(vectors, *, n_neighbors, device=0, **_ignored):
         """Entry point of scripts/make_knn_graph.py:49 — returns (graph, auxiliary index or None)."""

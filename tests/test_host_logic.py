@@ -46,6 +46,7 @@ def test_edge_table_host_functions_and_container(tmp_path):
     pd.testing.assert_frame_equal(part.reset_index(drop=True),
                                   want[(want.src_vertex >= 100) & (want.src_vertex < 200)].reset_index(drop=True))
     g = kg.KNNGraph(want)
+    g._check_rep()
     assert g.nvecs == len(v) and g.k in (4, 5) and g.ind_ptr[-1] == len(want)
     assert (g.rev_lookup(7).src_vertex == 7).all()
     small = g.restrict_k(k=3)
