@@ -81,3 +81,44 @@ def test_segment_walk_matches_per_image_argmax():
             s = scores[starts[im]:starts[im + 1]]
             want.append((s.max(), int(starts[im] + np.flatnonzero(s == s.max())[0])))
         assert got == want, trial
+
+
+def pooled_group_min(v, ngp, vmax=6):
+    """numpy model of pooled_group_min (csrc/ssw_common.cuh): lane l holds CTAs l + 32m; CTA c is in group c mod ngp."""
+    g_total = len(v)
+    lanes = [[v[l + 32 * m] if l + 32 * m < g_total else 0 for m in range(vmax)] for l in range(32)]
+    if ngp >= 32:
+        gpl = ngp >> 5
+        t = []
+        for l in range(32):
+            tl = 0xFFFFFFFF
+            for j in range(gpl):
+                tl = min(tl, max(lanes[l][m] for m in range(vmax) if (m & (gpl - 1)) == j))
+            t.append(tl)
+    else:
+        t = [max(x) for x in lanes]
+        sft = 16
+        while sft >= ngp:
+            t = [max(t[l], t[l ^ sft]) for l in range(32)]
+            sft >>= 1
+    return min(t)
+
+
+def test_pooled_bound_is_reached_by_at_least_k_ctas():
+    """The invariant the scan kernels rely on: the pooled value never exceeds the k-th largest published best."""
+    rng = np.random.default_rng(1)
+    for trial in range(300):
+        g_total = int(rng.choice([148, 132, 160, 64, 33]))
+        k = int(rng.integers(1, 65))
+        ngp = 1
+        while ngp < k:
+            ngp <<= 1
+        if g_total < ngp:
+            continue
+        v = rng.integers(1, 2 ** 31, size=g_total).astype(np.int64)
+        v[rng.random(g_total) < rng.choice([0.0, 0.1, 0.9])] = 0            # CTAs that have published nothing yet
+        t = pooled_group_min(v.tolist(), ngp)
+        if t > 0:
+            assert int((v >= t).sum()) >= k, (trial, g_total, k, ngp)
+        kth = np.sort(v)[::-1][k - 1]
+        assert t <= kth
