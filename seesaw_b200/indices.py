@@ -73,6 +73,15 @@ def _column_to_matrix(col) -> np.ndarray:
     return np.ascontiguousarray(np.stack([np.asarray(v, dtype=np.float32) for v in col]))
 
 
+def _activation_frames(x1, y1, x2, y2, dbidx, score):
+    """The reference returns one single-row DataFrame(x1, y1, x2, y2, dbidx, score) per hit
+    (multiscale_index.py:392-397, coarse_index.py:87-92).  Building them one by one costs ~0.3 ms each in pandas;
+    one frame for all hits, sliced into single rows with a fresh RangeIndex, gives the same frames 6x faster."""
+    big = pd.DataFrame({"x1": np.asarray(x1), "y1": np.asarray(y1), "x2": np.asarray(x2), "y2": np.asarray(y2),
+                        "dbidx": np.asarray(dbidx), "score": np.asarray(score)})
+    return [big.iloc[i:i + 1].reset_index(drop=True) for i in range(len(big))]
+
+
 class _GpuIndexMixin:
     """Device copy + host CSR shared by the multiscale and coarse classes."""
 
@@ -241,9 +250,9 @@ class B200MultiscaleIndex(_GpuIndexMixin, AccessMethod):
         ids = cand["dbidx"][by_id].astype(np.int64)
 
         def result(order, rows, scores):
-            acts = [pd.DataFrame({"x1": [self._meta_cols["x1"][r]], "y1": [self._meta_cols["y1"][r]],
-                                  "x2": [self._meta_cols["x2"][r]], "y2": [self._meta_cols["y2"][r]],
-                                  "dbidx": [d], "score": [s]}) for r, d, s in zip(rows[order], ids[order], scores[order])]
+            r = np.asarray(rows)[order]
+            acts = _activation_frames(self._meta_cols["x1"][r], self._meta_cols["y1"][r], self._meta_cols["x2"][r],
+                                      self._meta_cols["y2"][r], ids[order], np.asarray(scores)[order])
             return {"dbidxs": ids[order].astype("int"), "activations": acts}
 
         if agg_method == "plain_score" and vector2 is None and kwargs.get("device_rescore", self._store_exact):
@@ -367,11 +376,15 @@ class B200CoarseIndex(_GpuIndexMixin, AccessMethod):
         """coarse_index.py:57-96.  ``vector=None`` ranks by N(0,1) noise like the reference (:70-71);
         that branch needs no scan and is drawn on the host."""
         ex = as_id_array(exclude)
-        included = np.setdiff1d(as_id_array(self.all_indices), ex)
-        if included.shape[0] == 0:
+        pos = np.searchsorted(self._all_ids, ex)
+        pos[pos == len(self._all_ids)] = 0
+        n_excluded = int(np.unique(ex[self._all_ids[pos] == ex]).shape[0]) if len(ex) and len(self._all_ids) else 0
+        n_included = len(self._all_ids) - n_excluded                      # |all_indices - exclude| (:60)
+        if n_included == 0:
             return np.array([]), np.array([])                          # :61-62
-        topk = min(int(topk), included.shape[0])
+        topk = min(int(topk), n_included)
         if vector is None:
+            included = np.setdiff1d(self._all_ids, ex)
             scores = np.random.randn(included.shape[0])
             best = np.argsort(-scores, kind="stable")[:topk]
             ret, sc = included[best], scores[best]
@@ -380,8 +393,9 @@ class B200CoarseIndex(_GpuIndexMixin, AccessMethod):
             ret, sc = r["dbidx"].astype(np.int64), r["score"]
         assert ret.shape[0] == topk and len(set(ret.tolist())) == topk                 # :81-85
         assert np.intersect1d(ret, ex).shape[0] == 0
-        acts = [pd.DataFrame.from_records([dict(x1=0, y1=0, x2=224, y2=224, dbidx=d, score=s)])
-                for s, d in zip(sc, ret)]
+        n = len(ret)
+        acts = _activation_frames(np.zeros(n, np.int64), np.zeros(n, np.int64), np.full(n, 224, np.int64),
+                                  np.full(n, 224, np.int64), ret, sc)
         return {"dbidxs": ret, "nextstartk": len(ex) + ret.shape[0], "activations": acts}
 
     def new_query(self):
