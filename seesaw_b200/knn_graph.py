@@ -114,6 +114,77 @@ def compute_exact_knn(vectors, n_neighbors, *, device=0):
     return pd.DataFrame({"src_vertex": src[:t], "dst_vertex": dst[:t], "distance": dis[:t], "dst_rank": rank[:t]})
 
 
+def rbf_kernel(edist):
+    """knn_graph.py:8-22: cosine distance -> weight exp(-distance / edist), float64."""
+    assert edist > 0
+    spread = 1.0 / edist
+
+    def kernel(arr):
+        assert arr.min() >= -0.0001 and arr.max() <= 2.0001
+        return np.exp(-(arr.astype("float64") * spread))
+
+    return kernel
+
+
+def knn_kernel(edist=2.1):
+    """knn_graph.py:24-30: 0/1 weights, neighbours beyond ``edist`` discarded."""
+    assert edist > 0.0
+
+    def kernel(arr):
+        return (arr <= edist).astype("float32")
+
+    return kernel
+
+
+def get_weight_matrix(df, *, kfun, self_edges=False, normalized, laplacian=False, symmetric=True):
+    """Weight matrix / graph Laplacian of a kNN edge table — get_weight_matrix (knn_graph.py:31-104), the input of
+    label propagation.  One-off host step (scipy); stated here so the graph chain compute_exact_knn ->
+    get_weight_matrix -> B200LabelPropagation lives in one package.  Same semantics: weights kfun(distance), an
+    edge listed from both ends gets the mean of its two weights, one listed from one end keeps its weight, the
+    diagonal is stored as explicit zeros (the reference's setdiag(0.) keeps them), CSR with sorted indices;
+    ``laplacian`` gives D - W (optionally D^-1/2 (D - W) D^-1/2)."""
+    import scipy.sparse as sp
+    assert not self_edges
+    src, dst = df.src_vertex.values.astype(np.int64), df.dst_vertex.values.astype(np.int64)
+    n = np.unique(src).shape[0]
+    assert int((src == dst).sum()) == n, "one self edge per vertex expected"
+    w = kfun(df.distance.values)
+    assert (w >= 0).all(), "edge weights must be non-negative"
+    w = np.asarray(w, dtype=np.float64)
+    if symmetric:
+        # every listed edge votes once for (i, j) and once for (j, i); weight = sum of listed weights / votes
+        i2, j2 = np.concatenate([src, dst]), np.concatenate([dst, src])
+        votes = sp.coo_array((np.ones(i2.shape[0]), (i2, j2)), shape=(n, n)).tocsr()
+        pos_w = w > 0
+        ww = np.where(pos_w, w, 0.0)
+        wsum = sp.coo_array((np.concatenate([ww, ww]), (i2, j2)), shape=(n, n)).tocsr()
+        votes.sum_duplicates(), wsum.sum_duplicates()
+        votes.sort_indices(), wsum.sort_indices()
+        assert np.array_equal(votes.indptr, wsum.indptr) and np.array_equal(votes.indices, wsum.indices)
+        out = sp.csr_array((wsum.data / votes.data, wsum.indices.copy(), wsum.indptr.copy()), shape=(n, n))
+        assert np.isclose(out.diagonal(), 1.0, atol=1e-5).all()       # kfun(0) == 1 on the self edges
+    else:
+        keep = w > 0
+        out = sp.coo_array((w[keep], (src[keep], dst[keep])), shape=(n, n)).tocsr()
+        out.sum_duplicates()
+        out.sort_indices()
+    rows = np.repeat(np.arange(n), np.diff(out.indptr))
+    out.data[rows == out.indices] = 0.0                               # setdiag(0.): stored zeros stay
+    degree = np.asarray(out.sum(axis=1)).reshape(-1)
+    assert (degree > 0).all(), "no zero degree nodes allowed"
+    if laplacian:
+        assert symmetric
+        out = -out
+        out.setdiag(degree)
+        if normalized:
+            inv_sqrt = sp.dia_array((1.0 / np.sqrt(degree), 0), shape=(n, n))
+            out = inv_sqrt @ (out @ inv_sqrt)
+    out = sp.csr_array(out)
+    out.sum_duplicates()
+    out.sort_indices()
+    return out
+
+
 def get_lookup_ranges(sorted_col, nvecs):
     """CSR row pointer over a sorted vertex column (knn_graph.py:136-140)."""
     counts = np.bincount(np.asarray(sorted_col, dtype=np.int64), minlength=nvecs)
