@@ -74,3 +74,7 @@ def lp_inputs(c):
     reg = rng.random(c["n"]) if c["reg_lambda"] > 0 else None
     start = rng.random(c["n"]) if c.get("start") else None
     return ids.astype(np.int64), vals, reg, start
+
+
+# feedback session of the label-propagation ranker: (row ids, 0/1 labels) per round
+RANKER_STEPS = [([3, 17], [1, 1]), ([40], [0]), ([5, 77, 120], [1, 0, 0])]

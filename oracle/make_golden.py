@@ -22,7 +22,7 @@ sys.path.insert(0, HERE)
 from refstubs import import_reference  # noqa: E402
 from seesaw_b200 import synth  # noqa: E402
 
-from cases import CASES, COARSE, KNN, LP, ms_inputs, exclude_sets, knn_inputs, lp_vectors, lp_inputs  # noqa: E402
+from cases import CASES, COARSE, KNN, LP, RANKER_STEPS, ms_inputs, exclude_sets, knn_inputs, lp_vectors, lp_inputs  # noqa: E402
 
 
 def main():
@@ -85,6 +85,20 @@ def main():
         res = lp.fit_transform(label_ids=ids, label_values=vals, reg_values=reg, start_value=start)
         out[f"{name}/W_indptr"], out[f"{name}/W_indices"], out[f"{name}/W_data"] = W.indptr, W.indices, W.data
         out[f"{name}/values"] = np.asarray(res, dtype=np.float64)
+
+    # the knn_model of KnnProp2: LabelPropagationRanker2 over a short feedback session (research/knn_methods.py:97-199)
+    km = importlib.import_module("seesaw.research.knn_methods")
+    c = LP["lp_reg"]
+    W = ref.knn_graph.get_weight_matrix(ref.knn_graph.compute_exact_knn(lp_vectors(c), n_neighbors=c["k"]),
+                                        kfun=ref.knn_graph.rbf_kernel(c["edist"]), self_edges=False, normalized=False,
+                                        symmetric=True)
+    rk = km.LabelPropagationRanker2(weight_matrix=W, normalize_scores=False, sigmoid_before_propagate=True, calib_a=2.0,
+                                    calib_b=-0.1, prior_weight=1.0)
+    base = np.random.default_rng(9).standard_normal(c["n"])
+    rk.set_base_scores(base.copy())
+    for step, (idxs, labels) in enumerate(RANKER_STEPS):
+        rk.update(idxs, labels)
+        out[f"ranker/scores/{step}"] = np.asarray(rk.current_scores(), dtype=np.float64)
 
     # the reference's own unit pin (multiscale_index.py:182-187)
     out["pin/distinct_topk_positions"] = ref.multiscale.distinct_topk_positions(

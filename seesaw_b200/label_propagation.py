@@ -69,3 +69,72 @@ class B200LabelPropagation:
         if not self.converged:
             print(f"warning: did not converge after {it.value} iterations")   # :80-81
         return out
+
+
+def normalize_scores(scores, epsilon):
+    """research/knn_methods.py:87-95: affine map of the scores onto [epsilon, 1 - epsilon] (all equal -> 0.5)."""
+    assert epsilon < 0.5
+    lo, hi = scores.min(), scores.max()
+    if hi - lo == 0:
+        return scores - scores + 0.5
+    return (scores - lo) / (hi - lo) * (1 - 2 * epsilon) + epsilon
+
+
+class B200LabelPropagationRanker:
+    """The ``knn_model`` of KnnProp2 (seesaw/loops/graph_based.py:70-113) — LabelPropagationRanker2 with its base
+    class (research/knn_methods.py:97-199): prior scores from the text query, user labels clamped, propagation over
+    the kNN graph on the GPU (:class:`B200LabelPropagation`), ``top_k`` over the unlabeled rows.  Same constructor
+    keywords and methods; ``top_k`` breaks exact score ties by ascending row (the reference's argsort is unstable)."""
+
+    def __init__(self, *, weight_matrix, normalize_scores, sigmoid_before_propagate, calib_a, calib_b, prior_weight,
+                 normalize_epsilon=None, verbose=0, device=0, lp_factory=None, **other):
+        self.nvecs = weight_matrix.shape[0]
+        self.normalize_scores = normalize_scores
+        if normalize_scores:
+            assert normalize_epsilon is not None
+            self.epsilon = normalize_epsilon
+        self.calib_a, self.calib_b, self.prior_weight = calib_a, calib_b, prior_weight
+        self.sigmoid_before_propagate = sigmoid_before_propagate
+        self.is_labeled = np.zeros(self.nvecs)
+        self.labels = np.zeros(self.nvecs)
+        self.prior_scores = None
+        self._current_scores = None
+        self.weight_matrix = weight_matrix
+        make = lp_factory or (lambda **kw: B200LabelPropagation(device=device, **kw))
+        self.lp = make(reg_lambda=prior_weight, weight_matrix=weight_matrix, max_iter=300, verbose=verbose)   # :186-187
+
+    def set_base_scores(self, init_scores):
+        assert self.nvecs == init_scores.shape[0]
+        if self.normalize_scores:
+            init_scores = normalize_scores(init_scores, epsilon=self.epsilon)
+        if self.sigmoid_before_propagate:
+            from scipy.special import expit          # the reference's sigmoid (research/knn_methods.py:6)
+            init_scores = expit(self.calib_a * (init_scores + self.calib_b))
+        self.prior_scores = init_scores
+        if self.is_labeled.sum() == 0:                      # no labels yet: nothing to propagate (:136-139)
+            self._current_scores = self.prior_scores
+        else:
+            self._current_scores = self._propagate(self.prior_scores)
+
+    def _propagate(self, scores):
+        ids = np.flatnonzero(self.is_labeled.reshape(-1))
+        return self.lp.fit_transform(label_ids=ids, label_values=self.labels.reshape(-1)[ids],
+                                     reg_values=self.prior_scores, start_value=scores)
+
+    def update(self, idxs, labels):
+        for idx, label in zip(idxs, labels):
+            label = float(label)
+            assert np.isclose(label, 0) or np.isclose(label, 1)
+            self.labels[int(idx)] = label
+            self.is_labeled[int(idx)] = 1
+        if (self.labels[self.is_labeled > 0] == 0).sum() > 0:    # the reference waits for a first negative (:153-158)
+            self._current_scores = self._propagate(self.prior_scores)
+
+    def current_scores(self):
+        return self._current_scores
+
+    def top_k(self, k, unlabeled_only=True):
+        subset = np.flatnonzero(self.is_labeled < 1) if unlabeled_only else np.arange(self.nvecs)
+        raw = self.current_scores()
+        top = subset[np.argsort(-raw[subset], kind="stable")[:k]]
+        return top, raw[top]

@@ -133,3 +133,65 @@ def test_get_weight_matrix_variants_vs_live_reference(reference):
             np.testing.assert_allclose(mine.toarray(), ref.toarray(), rtol=1e-12, atol=1e-15)
             compared += 1
     assert compared >= 3
+
+
+class OracleLP:
+    """LabelPropagation stand-in for the CPU suite (the GPU class is bit-identical to it: tests/test_lp_gpu.py)."""
+
+    def __init__(self, *, weight_matrix, reg_lambda, max_iter, epsilon=1e-5, verbose=0):
+        self.kw = dict(reg_lambda=reg_lambda, max_iter=max_iter, epsilon=epsilon)
+        self.W = weight_matrix
+
+    def fit_transform(self, *, label_ids, label_values, reg_values=None, start_value=None):
+        ids = np.asarray(label_ids).reshape(-1)
+        return orc.label_propagation_fit(self.W, label_ids=ids, label_values=np.asarray(label_values), reg_values=reg_values,
+                                         start_value=start_value, **self.kw)[0]
+
+
+@pytest.mark.parametrize("sigmoid_first,normalize", [(True, False), (False, True)])
+def test_label_propagation_ranker_vs_live_reference(reference, sigmoid_first, normalize):
+    """B200LabelPropagationRanker (host logic; propagation injected) == the reference's LabelPropagationRanker2 over a
+    feedback session: prior scores, positives only (no propagation yet), first negative, more labels, top_k."""
+    import importlib
+    from seesaw_b200 import knn_graph as kg
+    from seesaw_b200.label_propagation import B200LabelPropagationRanker
+    ref_mod = importlib.import_module("seesaw.research.knn_methods")
+    c = cases.LP["lp_reg"]
+    df = orc.compute_exact_knn(cases.lp_vectors(c), c["k"])
+    W = kg.get_weight_matrix(df, kfun=kg.rbf_kernel(c["edist"]), self_edges=False, normalized=False, symmetric=True)
+    kw = dict(weight_matrix=W, normalize_scores=normalize, sigmoid_before_propagate=sigmoid_first, calib_a=2.0, calib_b=-0.1,
+              prior_weight=1.0, normalize_epsilon=0.1 if normalize else None)
+    mine = B200LabelPropagationRanker(lp_factory=OracleLP, **kw)
+    ref = ref_mod.LabelPropagationRanker2(**kw)
+    rng = np.random.default_rng(9)
+    base = rng.standard_normal(c["n"])
+    mine.set_base_scores(base.copy())
+    ref.set_base_scores(base.copy())
+    steps = [([3, 17], [1, 1]), ([40], [0]), ([5, 77, 120], [1, 0, 0])]
+    for idxs, labels in steps:
+        mine.update(idxs, labels)
+        ref.update(idxs, labels)
+        assert np.array_equal(mine.current_scores(), ref.current_scores())
+        assert np.array_equal(mine.is_labeled, ref.is_labeled) and np.array_equal(mine.labels, ref.labels)
+        mi, ms = mine.top_k(15)
+        ri, rs = ref.top_k(15)
+        assert np.array_equal(ms, rs) and set(mi.tolist()) >= set(ri[rs > rs[-1]].tolist())
+    mine.set_base_scores(base * 0.5)           # with labels present the new prior is propagated at once
+    ref.set_base_scores(base * 0.5)
+    assert np.array_equal(mine.current_scores(), ref.current_scores())
+
+
+def test_label_propagation_ranker_vs_reference_golden(golden):
+    from seesaw_b200 import knn_graph as kg
+    from seesaw_b200.label_propagation import B200LabelPropagationRanker
+    c = cases.LP["lp_reg"]
+    W = kg.get_weight_matrix(orc.compute_exact_knn(cases.lp_vectors(c), c["k"]), kfun=kg.rbf_kernel(c["edist"]),
+                             self_edges=False, normalized=False, symmetric=True)
+    rk = B200LabelPropagationRanker(weight_matrix=W, normalize_scores=False, sigmoid_before_propagate=True, calib_a=2.0,
+                                    calib_b=-0.1, prior_weight=1.0, lp_factory=OracleLP)
+    rk.set_base_scores(np.random.default_rng(9).standard_normal(c["n"]))
+    for step, (idxs, labels) in enumerate(cases.RANKER_STEPS):
+        rk.update(idxs, labels)
+        assert np.array_equal(rk.current_scores(), golden[f"ranker/scores/{step}"]), step
+    idx, sc = rk.top_k(10)
+    assert not set(idx.tolist()) & {3, 17, 40, 5, 77, 120} and (np.diff(sc) <= 0).all()
