@@ -9,7 +9,10 @@
  * Conventions: plain pointers and sizes only; every function returns 0 on success and a
  * non-zero ssw_status otherwise, with a message available from ssw_last_error() (thread local).
  * The caller owns every host buffer; the library owns device memory until ssw_db_destroy().
- * A handle is thread-compatible (use from one thread at a time).  There is NO CPU fallback:
+ * The host-buffer entry points of a handle (ssw_scan_topk, ssw_scan_topk_sharded, ssw_rescore, ssw_score_all,
+ * ssw_topk_from_scores, ssw_db_set_boxes*, ssw_db_attach_exact) serialise on a per-handle mutex and may be
+ * called from several threads; the *_device entry points enqueue on the caller's stream and share the handle's
+ * workspace, so use them from one thread / stream at a time.  There is NO CPU fallback:
  * without a CUDA device of compute capability 10.x every compute entry point fails with
  * SSW_ERR_NO_DEVICE.
  *
@@ -67,6 +70,17 @@ int ssw_db_create_synthetic(ssw_db** out, int device, int dtype_store, int64_t n
 int ssw_db_destroy(ssw_db* db);
 int ssw_db_info(const ssw_db* db, int64_t* n_rows, int64_t* n_images, int* dim, int* dtype_store,
                 int* device);
+/* Exact mode.  The reference stores and scans float32 vectors (multiscale_tools.py:200, multiscale_index.py:171);
+ * fp16 storage halves the bytes of the scan but rounds every score.  ssw_db_attach_exact keeps the caller's
+ * float32 rows [n_rows, dim] (ORIGINAL order, host pointer) in HBM next to the fp16 copy.  From then on
+ * ssw_scan_topk / ssw_scan_topk_sharded return the float32 top-k — the fp16 scan proposes more candidates than
+ * asked, they are re-scored from the float32 rows and the first k are accepted only when an error bound proves
+ * no other image can rank among them; otherwise that query is re-scanned over the float32 rows —
+ * and ssw_rescore / ssw_score_all read the float32 rows.  Costs 2x the fp16 bytes of HBM; fp16 storage only.
+ * ssw_db_exact_info: rho = max_i ||v_i - fp16(v_i)||, vmax = max_i ||v_i||, and the number of queries answered
+ * in exact mode / of those re-scanned in float32 since creation (any pointer may be NULL). */
+int ssw_db_attach_exact(ssw_db* db, const float* vectors_f32);
+int ssw_db_exact_info(ssw_db* db, int* attached, double* rho, double* vmax, int64_t* queries, int64_t* rescans);
 /* device pointer to the stored vectors (grouped order) — for zero-copy consumers (kNN build) */
 int ssw_db_vectors_device(const ssw_db* db, void** dev_ptr);
 
@@ -154,6 +168,14 @@ int ssw_score_all_device(ssw_db* db, const float* d_query, float* d_out_scores, 
  * takes topk, as rescore_candidates does (:388-399).  Ids not in the database give row -1. */
 int ssw_db_set_boxes(ssw_db* db, const int32_t* x1, const int32_t* y1, const int32_t* x2, const int32_t* y2,
                      const int32_t* zoom_level);
+/* Same with the box columns in their own type.  The reference computes the IoU of the self-join in the dtype of
+ * vector_meta's x1,y1,x2,y2 (box_utils.py:336-350 via torchvision's _box_inter_union): float32 for indices
+ * written by the tiling pipeline (multiscale_tools.py:111: pixel / scale_factor as float32), exact integers with
+ * a float32 quotient for integer columns, float64 for float64 columns; the kernel repeats those operations in
+ * that type and order, so the per-level best-IoU patch is the reference's.  x1..y2: [n_rows] of box_dtype. */
+enum ssw_box_dtype { SSW_BOX_I32 = 0, SSW_BOX_F32 = 1, SSW_BOX_F64 = 2 };
+int ssw_db_set_boxes_typed(ssw_db* db, int box_dtype, const void* x1, const void* y1, const void* x2, const void* y2,
+                           const int32_t* zoom_level);
 int ssw_rescore(ssw_db* db, const float* query, const float* query2, const int32_t* cand_dbidx, int n_cand,
                 int agg_method, int aug_larger, double* out_score, int64_t* out_row);
 

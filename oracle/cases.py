@@ -12,6 +12,12 @@ CASES = {
     "ms_wide": dict(n_images=1500, p_lo=20, p_hi=60, dim=512, seed=21, qseed=22),
     "ms_768": dict(n_images=300, p_lo=1, p_hi=5, dim=768, seed=31, qseed=32),
 }
+# real-index shape: float32 unit vectors that are NOT fp16-representable (multiscale_tools.py:200) and the tiling
+# pipeline's float32 boxes (multiscale_tools.py:96-117) — the data the reference's own indices hold
+CASES_F32 = {
+    "msf_unit": dict(n_images=260, dim=512, seed=61, qseed=62, min_tile_size=60),
+    "msf_unit_768": dict(n_images=120, dim=768, seed=63, qseed=64, min_tile_size=120),
+}
 COARSE = dict(n=10000, dim=512, seed=0, qseed=1, xseed=2, n_excl=300, topk=10)   # BASELINE config 1
 KNN = {
     "knn_600": dict(n=600, dim=512, seed=41, k=10),
@@ -26,6 +32,19 @@ def ms_inputs(c):
     vecs = synth.synth_rows(0, int(counts.sum()), c["dim"], c["seed"], "tri", np.float32)
     q = synth.unit_queries(4, c["dim"], c["qseed"])
     return vecs, meta, q
+
+
+def msf_inputs(c):
+    meta, counts = synth.synth_pyramid_meta(c["n_images"], c["seed"] + 1000, dbidx_start=7, dbidx_stride=2,
+                                            min_tile_size=c["min_tile_size"],
+                                            sizes=((640, 480), (500, 375), (480, 640), (1280, 960), (333, 500), (224, 224), (300, 260)))
+    vecs = synth.unit_rows(int(counts.sum()), c["dim"], c["seed"])
+    q = synth.unit_queries(4, c["dim"], c["qseed"])
+    return vecs, meta, q
+
+
+MSF_QUERY_VARIANTS = (("plain_score", "all", 1, False), ("plain_score", "all", 3, True), ("avg_score", "all", 3, False),
+                      ("avg_score", "greater", 5, False), ("avg_score", "adjacent", 5, True))
 
 
 def exclude_sets(meta, seed):

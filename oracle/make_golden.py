@@ -22,7 +22,8 @@ sys.path.insert(0, HERE)
 from refstubs import import_reference  # noqa: E402
 from seesaw_b200 import synth  # noqa: E402
 
-from cases import CASES, COARSE, KNN, LP, RANKER_STEPS, ms_inputs, exclude_sets, knn_inputs, lp_vectors, lp_inputs  # noqa: E402
+from cases import (CASES, CASES_F32, COARSE, KNN, LP, MSF_QUERY_VARIANTS, RANKER_STEPS, ms_inputs, msf_inputs,  # noqa: E402
+                   exclude_sets, knn_inputs, lp_vectors, lp_inputs)
 
 
 def main():
@@ -54,6 +55,26 @@ def main():
             out[key + "/dbidxs"] = np.asarray(r["dbidxs"]).astype(np.int64)
             out[key + "/act_score"] = np.array([a.score.values[0] for a in r["activations"]], np.float64)
             out[key + "/act_box"] = np.array([a[["x1", "y1", "x2", "y2"]].values[0] for a in r["activations"]], np.int64)
+
+    # float32 unit vectors + the tiling pipeline's float32 boxes: what a real index holds
+    for name, c in CASES_F32.items():
+        vecs, meta, qs = msf_inputs(c)
+        idx = ref.multiscale.MultiscaleIndex(embedding=None, vectors=vecs, vector_meta=meta, vec_index=None)
+        xs = exclude_sets(meta, c["seed"] + 7)
+        for xname in ("none", "some"):
+            for qi in range(2):
+                r = idx._query_prelim(vector=qs[qi], topk_dbidx=50, exclude_dbidx=BitMap(xs[xname]))
+                key = f"{name}/prelim/{xname}/{qi}"
+                out[key + "/dbidx"] = r["dbidx"].values.astype(np.int64)
+                out[key + "/score"] = r["max_score"].values.astype(np.float32)
+        for agg, aug, topk, use_v2 in MSF_QUERY_VARIANTS:
+            r = idx.query(vector=qs[2], vector2=qs[3] * 0.25 if use_v2 else None, topk=topk, shortlist_size=40,
+                          exclude=BitMap(xs["some"]), agg_method=agg, aug_larger=aug, rescore_method=None)
+            key = f"{name}/query/{agg}/{aug}/{topk}/{int(use_v2)}"
+            out[key + "/dbidxs"] = np.asarray(r["dbidxs"]).astype(np.int64)
+            out[key + "/act_score"] = np.array([a.score.values[0] for a in r["activations"]], np.float64)
+            out[key + "/act_box"] = np.array([a[["x1", "y1", "x2", "y2"]].values[0] for a in r["activations"]], np.float32)
+            assert all(a.score.dtype == np.float32 for a in r["activations"]), "score column dtype"
 
     c = COARSE
     v = synth.synth_rows(0, c["n"], c["dim"], c["seed"], "tri", np.float32)
@@ -107,7 +128,7 @@ def main():
     path = os.path.join(ROOT, "tests", "golden", "reference_outputs.npz")
     np.savez_compressed(path, **out)
     with open(os.path.join(ROOT, "tests", "golden", "reference_cases.json"), "w") as f:
-        json.dump(dict(multiscale=CASES, coarse=COARSE, knn=KNN, label_propagation=LP,
+        json.dump(dict(multiscale=CASES, multiscale_f32=CASES_F32, coarse=COARSE, knn=KNN, label_propagation=LP,
                        note="outputs of the unmodified reference; regenerate with oracle/make_golden.py"), f, indent=1)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path)} bytes")
 

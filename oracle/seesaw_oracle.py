@@ -90,15 +90,37 @@ def query_prelim(vectors, dbidx_of_row, vector, topk_dbidx, exclude=None, index_
 
 
 def _pairwise_iou(boxes):
-    """IoU of every box pair of one image (box_utils.py:336-350, via torchvision's
-    _box_inter_union): boxes float [n,4] as x1,y1,x2,y2."""
+    """IoU of every box pair of one image (box_utils.py:336-350): df2tensor stacks the four columns
+    (:329-334, numpy promotion), torchvision's _box_inter_union computes area / intersection / union in
+    that dtype (float32 for the tiling pipeline's boxes, multiscale_tools.py:111; int64 for integer
+    columns), and ``inter / union`` is a true division (float32 for integer tensors, torch's default).
+    boxes [n,4] as x1,y1,x2,y2 in their own dtype."""
+    integer = np.issubdtype(boxes.dtype, np.integer)
+    boxes = boxes.astype(np.int64) if integer else boxes
     x1, y1, x2, y2 = (boxes[:, i] for i in range(4))
     area = (x2 - x1) * (y2 - y1)
     iw = np.clip(np.minimum(x2[:, None], x2[None, :]) - np.maximum(x1[:, None], x1[None, :]), 0, None)
     ih = np.clip(np.minimum(y2[:, None], y2[None, :]) - np.maximum(y1[:, None], y1[None, :]), 0, None)
     inter = iw * ih
-    union = area[:, None] + area[None, :] - inter
-    return inter / union
+    union = (area[:, None] + area[None, :]) - inter
+    with np.errstate(invalid="ignore", divide="ignore"):
+        if integer:
+            return inter.astype(np.float32) / union.astype(np.float32)
+        return inter / union
+
+
+def _pandas_group_mean_f32(values):
+    """pandas' groupby(...).mean() of one group of a float32 column (multiscale_index.py:142): group_mean
+    accumulates in the column's own float32 with Kahan compensation, in row order, and divides by the
+    count in float32 (pandas/_libs/groupby.pyx; checked against pandas itself in tests/test_oracle.py)."""
+    f = np.float32
+    sumx, comp = f(0), f(0)
+    for v in values:
+        y = f(f(v) - comp)
+        t = f(sumx + y)
+        comp = f(f(t - sumx) - y)
+        sumx = t
+    return f(sumx / f(len(values)))
 
 
 def frame_best_patch(frame: pd.DataFrame, agg_method="plain_score", aug_larger="all"):
@@ -109,7 +131,7 @@ def frame_best_patch(frame: pd.DataFrame, agg_method="plain_score", aug_larger="
         # :117-118  first row (frame order) whose score equals the max
         return int(np.flatnonzero(s == s.max())[0]), s.max()
     assert agg_method == "avg_score"
-    boxes = frame[["x1", "y1", "x2", "y2"]].to_numpy().astype(np.float64)
+    boxes = frame[["x1", "y1", "x2", "y2"]].to_numpy()     # common dtype of the four columns, as np.stack gives
     zoom = frame["zoom_level"].to_numpy()
     iou = _pairwise_iou(boxes)
     ok = iou > 0                                           # box_join(iou_gt=0), box_utils.py:357
@@ -120,7 +142,7 @@ def frame_best_patch(frame: pd.DataFrame, agg_method="plain_score", aug_larger="
     else:
         assert aug_larger == "all"
     n = len(frame)
-    out = np.full(n, np.nan)
+    out = np.full(n, np.nan, dtype=s.dtype)                # groupby(...).mean() keeps the score column's dtype (:142)
     for left in range(n):                                  # groupby(['iloc_left','zoom_level_right']).iou.idxmax()
         rights = np.flatnonzero(ok[left])
         if rights.size == 0:
@@ -129,7 +151,8 @@ def frame_best_patch(frame: pd.DataFrame, agg_method="plain_score", aug_larger="
         for z in np.unique(zoom[rights]):
             cand = rights[zoom[rights] == z]
             picked.append(cand[np.argmax(iou[left, cand])])  # first max = lowest right index
-        out[left] = np.mean(s[picked])                     # :141-143 mean over zoom levels
+        # :141-143 mean over zoom levels, ascending (groupby order), in pandas' arithmetic for the column dtype
+        out[left] = _pandas_group_mean_f32(s[picked]) if s.dtype == np.float32 else np.mean(s[picked])
     # :149-150 rows whose aggregated score equals the max; NaN rows never compare equal
     best = np.nanmax(out)
     return int(np.flatnonzero(out == best)[0]), best

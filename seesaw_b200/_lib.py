@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libseesaw_b200.so")
 
 SSW_F32, SSW_F16 = 0, 1
+SSW_BOX_I32, SSW_BOX_F32, SSW_BOX_F64 = 0, 1, 2
 SSW_MAX_TOPK = 2048
 SSW_MAX_BATCH = 64
 SSW_MAX_KNN_K1 = 64
@@ -61,6 +62,9 @@ SIGNATURES = {
                                         C.c_uint32, _p, _p, _p, _p]),
     "ssw_set_scan_mode": (C.c_int, [_p, C.c_int]),
     "ssw_db_set_boxes": (C.c_int, [_p, _p, _p, _p, _p, _p]),
+    "ssw_db_set_boxes_typed": (C.c_int, [_p, C.c_int, _p, _p, _p, _p, _p]),
+    "ssw_db_attach_exact": (C.c_int, [_p, _p]),
+    "ssw_db_exact_info": (C.c_int, [_p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), _i64p, _i64p]),
     "ssw_rescore": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, _p, _p]),
     "ssw_topk_from_scores": (C.c_int, [_p, _p, _p, C.c_int, _p, C.c_int64, _p, _p, _p, _p]),
     "ssw_score_all": (C.c_int, [_p, _p, _p]),

@@ -194,6 +194,41 @@ static int build_layout(ssw_db* db, const int32_t* dbidx_per_row, std::vector<in
   return SSW_OK;
 }
 
+// Host rows [n_rows, dim] of dtype_in in ORIGINAL order -> d_dst in the database's grouped order as dtype_dst.
+// perm: device row -> original row (empty = identity).
+static int upload_rows(ssw_db* db, const void* vectors, int dtype_in, void* d_dst, int dtype_dst,
+                       const std::vector<int64_t>& perm) {
+  const int64_t n_rows = db->n_rows;
+  const int dim = db->dim;
+  const size_t es_in = dtype_in == SSW_F16 ? 2 : 4, es_st = dtype_dst == SSW_F16 ? 2 : 4;
+  const size_t row_in = (size_t)dim * es_in;
+  const bool identity = perm.empty();
+  if (identity && dtype_in == dtype_dst) {
+    SSW_CUDA(cudaMemcpy(d_dst, vectors, (size_t)n_rows * row_in, cudaMemcpyHostToDevice));
+    return SSW_OK;
+  }
+  // chunked: gather rows on the host into pinned staging, copy, convert/place on the device
+  const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)(32u << 20) / (int64_t)row_in);
+  int rc = ensure_stage(db, (size_t)chunk_rows * row_in, (size_t)chunk_rows * row_in);
+  if (rc) return rc;
+  const uint8_t* src = static_cast<const uint8_t*>(vectors);
+  for (int64_t r0 = 0; r0 < n_rows; r0 += chunk_rows) {
+    const int64_t nr = std::min(chunk_rows, n_rows - r0);
+    uint8_t* h = static_cast<uint8_t*>(db->h_stage);
+    if (identity) {
+      memcpy(h, src + (size_t)r0 * row_in, (size_t)nr * row_in);
+    } else {
+      for (int64_t i = 0; i < nr; ++i) memcpy(h + (size_t)i * row_in, src + (size_t)perm[r0 + i] * row_in, row_in);
+    }
+    SSW_CUDA(cudaMemcpyAsync(db->d_stage, h, (size_t)nr * row_in, cudaMemcpyHostToDevice, db->stream));
+    if ((rc = launch_convert_rows(db->d_stage, dtype_in, static_cast<uint8_t*>(d_dst) + (size_t)r0 * dim * es_st, dtype_dst,
+                                  nr * dim, db->stream)))
+      return rc;
+    SSW_CUDA(cudaStreamSynchronize(db->stream));
+  }
+  return SSW_OK;
+}
+
 static int db_new(ssw_db** out, int device, int dtype_store, int64_t n_rows, int dim, int64_t row_base) {
   SSW_REQUIRE(out != nullptr, "out handle is null");
   *out = nullptr;
@@ -258,6 +293,8 @@ int ssw_db_destroy(ssw_db* db) {
   cudaFree(db->d_part);
   cudaFree(db->d_last_bits);
   cudaFree(db->d_boxes);
+  cudaFree(db->d_zoom);
+  cudaFree(db->d_exact);
   cudaFree(db->d_xchg_timed_out);
   cudaFree(db->d_tc_ws);
   cudaFree(db->d_list_keys);
@@ -289,48 +326,13 @@ int ssw_db_create(ssw_db** out, int device, const void* vectors, int dtype_in, i
     return code;
   };
   if ((rc = build_layout(db, dbidx_per_row, &perm))) return fail(rc);
-  const size_t es_in = dtype_in == SSW_F16 ? 2 : 4, es_st = dtype_store == SSW_F16 ? 2 : 4;
-  const size_t row_in = (size_t)dim * es_in;
+  const size_t es_st = dtype_store == SSW_F16 ? 2 : 4;
   cudaError_t e = cudaMalloc(&db->d_vecs, std::max<size_t>((size_t)n_rows * dim * es_st, 16));
   if (e != cudaSuccess) {
     set_error(std::string("cudaMalloc(vectors): ") + cudaGetErrorString(e));
     return fail(e == cudaErrorMemoryAllocation ? SSW_ERR_OOM : SSW_ERR_CUDA);
   }
-  const bool identity = perm.empty();
-  if (identity && dtype_in == dtype_store) {
-    e = cudaMemcpy(db->d_vecs, vectors, (size_t)n_rows * row_in, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
-      set_error(std::string("cudaMemcpy(vectors): ") + cudaGetErrorString(e));
-      return fail(SSW_ERR_CUDA);
-    }
-  } else {
-    // chunked: gather rows on the host into pinned staging, copy, convert/place on the device
-    const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)(32u << 20) / (int64_t)row_in);
-    if ((rc = ensure_stage(db, (size_t)chunk_rows * row_in, (size_t)chunk_rows * row_in))) return fail(rc);
-    const uint8_t* src = static_cast<const uint8_t*>(vectors);
-    for (int64_t r0 = 0; r0 < n_rows; r0 += chunk_rows) {
-      const int64_t nr = std::min(chunk_rows, n_rows - r0);
-      uint8_t* h = static_cast<uint8_t*>(db->h_stage);
-      if (identity) {
-        memcpy(h, src + (size_t)r0 * row_in, (size_t)nr * row_in);
-      } else {
-        for (int64_t i = 0; i < nr; ++i) memcpy(h + (size_t)i * row_in, src + (size_t)perm[r0 + i] * row_in, row_in);
-      }
-      e = cudaMemcpyAsync(db->d_stage, h, (size_t)nr * row_in, cudaMemcpyHostToDevice, db->stream);
-      if (e != cudaSuccess) {
-        set_error(std::string("cudaMemcpyAsync(stage): ") + cudaGetErrorString(e));
-        return fail(SSW_ERR_CUDA);
-      }
-      if ((rc = launch_convert_rows(db->d_stage, dtype_in, static_cast<uint8_t*>(db->d_vecs) + (size_t)r0 * dim * es_st,
-                                    dtype_store, nr * dim, db->stream)))
-        return fail(rc);
-      e = cudaStreamSynchronize(db->stream);
-      if (e != cudaSuccess) {
-        set_error(std::string("upload: ") + cudaGetErrorString(e));
-        return fail(SSW_ERR_CUDA);
-      }
-    }
-  }
+  if ((rc = upload_rows(db, vectors, dtype_in, db->d_vecs, dtype_store, perm))) return fail(rc);
   *out = db;
   return SSW_OK;
 }
@@ -439,16 +441,16 @@ struct XchgCtx {
 
 static int scan_topk_impl(ssw_db* db, const float* d_queries, int nq, int k, const uint32_t* d_exclude_bits,
                           uint64_t* d_out_key, int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row,
-                          int32_t* d_out_count, cudaStream_t st, const XchgCtx* xc = nullptr) {
+                          int32_t* d_out_count, cudaStream_t st, const XchgCtx* xc = nullptr, bool exact_rows = false) {
   const int lists = db->scan_grid;
   int rc = ensure_lists(db, nq, lists, k);
   if (rc) return rc;
-  const bool tc_ok = scan_tc_supported(db, k);
-  if (db->scan_mode == 2 && !tc_ok) {
+  const bool tc_ok = scan_tc_supported(db, k) && !exact_rows;
+  if (db->scan_mode == 2 && !tc_ok && !exact_rows) {
     set_error("tcgen05 batched scan needs fp16 storage, dim 256/512/768 and k <= 64");
     return SSW_ERR_INVALID;
   }
-  const bool use_tc = db->scan_mode == 2 || (db->scan_mode == 0 && tc_ok && nq >= 2);   // one batched pass costs about one streaming pass
+  const bool use_tc = !exact_rows && (db->scan_mode == 2 || (db->scan_mode == 0 && tc_ok && nq >= 2));   // one batched pass costs about one streaming pass
   if (use_tc) {
     if (!db->d_tc_ws) SSW_CUDA(cudaMalloc(&db->d_tc_ws, scan_tc_workspace_bytes(db->dim, db->scan_grid)));
     for (int q0 = 0; q0 < nq; q0 += SSW_MAX_BATCH) {
@@ -466,7 +468,7 @@ static int scan_topk_impl(ssw_db* db, const float* d_queries, int nq, int k, con
       rc = launch_scan1(db, d_queries + (size_t)q * db->dim, k,
                         d_exclude_bits ? d_exclude_bits + (size_t)q * db->excl_words : nullptr,
                         db->d_list_keys + (size_t)q * lists * k, db->d_list_dbidx + (size_t)q * lists * k,
-                        db->d_gthr + q, db->d_pub1 + (size_t)q * db->scan_grid, st);
+                        db->d_gthr + q, db->d_pub1 + (size_t)q * db->scan_grid, st, exact_rows);
       prof_end(db, st);
       if (rc) return rc;
     }
@@ -568,6 +570,16 @@ int ssw_merge_topk_device(int device, const uint64_t* d_keys, const int32_t* d_d
                       d_out_score, d_out_row, d_out_count, (cudaStream_t)stream);
 }
 
+// Candidates the fp16 scan is asked for in exact mode (see ssw_exact.cu): the tensor-core kernel keeps at
+// most 64 per query, the streaming kernel up to SSW_MAX_TOPK.
+static int exact_candidates(const ssw_db* db, int nq, int k) {
+  const int64_t cap = std::max<int64_t>(k, std::min<int64_t>(db->n_images, SSW_MAX_TOPK));
+  const bool tc = db->scan_mode != 1 && nq >= 2 && scan_tc_supported(db, 64) && k <= 56;
+  if (db->scan_mode == 2) return (int)std::min<int64_t>(cap, 64);
+  if (tc) return (int)std::min<int64_t>(cap, 64);
+  return (int)std::min<int64_t>(cap, (int64_t)k + std::max(16, k / 4));
+}
+
 static int scan_topk_host(ssw_db* db, const float* queries, int nq, int k, const int32_t* exclude_dbidx,
                           const int64_t* exclude_offsets, int32_t* out_dbidx, float* out_score, int64_t* out_row,
                           int32_t* out_count, const XchgCtx* xc) {
@@ -576,6 +588,7 @@ static int scan_topk_host(ssw_db* db, const float* queries, int nq, int k, const
   SSW_REQUIRE(k > 0 && k <= SSW_MAX_TOPK, "k must be in [1, SSW_MAX_TOPK]");
   SSW_REQUIRE((exclude_dbidx == nullptr) == (exclude_offsets == nullptr) || exclude_offsets != nullptr,
               "exclude_offsets is required with exclude_dbidx");
+  std::lock_guard<std::mutex> guard(db->mu);
   SSW_CUDA(cudaSetDevice(db->device));
   if (exclude_offsets) {
     SSW_REQUIRE(exclude_offsets[0] == 0, "exclude_offsets[0] must be 0");
@@ -584,17 +597,21 @@ static int scan_topk_host(ssw_db* db, const float* queries, int nq, int k, const
   const int64_t n_ids = exclude_offsets ? exclude_offsets[nq] : 0;
   SSW_REQUIRE(n_ids == 0 || exclude_dbidx != nullptr, "exclude_dbidx is null");
   const bool has_excl = exclude_offsets != nullptr && n_ids > 0;
-  // one staging block each side:  queries | offsets | ids   ->   + bitmaps | keys | dbidx | score | row | count
+  const bool exact = db->d_exact != nullptr;
+  const int kc = exact ? exact_candidates(db, nq, k) : k;
+  // one staging block each side:  queries | offsets | ids   ->   + bitmaps | keys | [exact scratch] | dbidx | score | row | count [| cert]
   auto up16 = [](size_t x) { return (x + 15) / 16 * 16; };
   const size_t q_bytes = up16((size_t)nq * db->dim * 4);
   const size_t off_bytes = up16((size_t)(nq + 1) * 8);
   const size_t ids_bytes = up16((size_t)n_ids * 4);
   const size_t in_bytes = q_bytes + off_bytes + ids_bytes;
   const size_t bits_bytes = has_excl ? up16((size_t)nq * db->excl_words * 4) : 0;
-  const size_t nk = (size_t)nq * k;
+  const size_t nk = (size_t)nq * k, nkc = (size_t)nq * kc;
   const size_t key_b = up16(nk * 8), db_b = up16(nk * 4), sc_b = up16(nk * 4), row_b = up16(nk * 8), cnt_b = up16((size_t)nq * 4);
-  const size_t out_bytes = db_b + sc_b + row_b + cnt_b;
-  const size_t dev_total = in_bytes + bits_bytes + key_b + out_bytes;
+  const size_t x16_b = exact ? up16(nkc * 8) : 0, xdb_b = exact ? up16(nkc * 4) : 0, x32_b = exact ? up16(nkc * 8) : 0;
+  const size_t cert_b = exact ? cnt_b : 0;
+  const size_t out_bytes = db_b + sc_b + row_b + cnt_b + cert_b;
+  const size_t dev_total = in_bytes + bits_bytes + key_b + x16_b + xdb_b + x32_b + out_bytes;
   int rc = ensure_stage(db, dev_total, std::max(in_bytes, out_bytes));
   if (rc) return rc;
   uint8_t* h = static_cast<uint8_t*>(db->h_stage);
@@ -614,23 +631,81 @@ static int scan_topk_host(ssw_db* db, const float* queries, int nq, int k, const
                               reinterpret_cast<const int64_t*>(d + q_bytes), nq, d_bits, st);
     if (rc) return rc;
   }
-  uint64_t* d_key = reinterpret_cast<uint64_t*>(d + in_bytes + bits_bytes);
-  uint8_t* d_out = d + in_bytes + bits_bytes + key_b;
+  uint8_t* p = d + in_bytes + bits_bytes;
+  uint64_t* d_key = reinterpret_cast<uint64_t*>(p);
+  p += key_b;
+  uint64_t* d_key16 = reinterpret_cast<uint64_t*>(p);
+  p += x16_b;
+  int32_t* d_cand = reinterpret_cast<int32_t*>(p);
+  p += xdb_b;
+  uint64_t* d_key32 = reinterpret_cast<uint64_t*>(p);
+  p += x32_b;
+  uint8_t* d_out = p;
   int32_t* d_dbidx = reinterpret_cast<int32_t*>(d_out);
   float* d_score = reinterpret_cast<float*>(d_out + db_b);
   int64_t* d_row = reinterpret_cast<int64_t*>(d_out + db_b + sc_b);
   int32_t* d_cnt = reinterpret_cast<int32_t*>(d_out + db_b + sc_b + row_b);
-  rc = scan_topk_impl(db, d_q, nq, k, d_bits, d_key, d_dbidx, d_score, d_row, d_cnt, st, xc);
-  if (rc) return rc;
-  SSW_CUDA(cudaMemcpyAsync(h, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
-  SSW_CUDA(cudaStreamSynchronize(st));
-  if (xc && db->d_xchg_timed_out) {
-    int flag = 0;
-    SSW_CUDA(cudaMemcpy(&flag, db->d_xchg_timed_out, 4, cudaMemcpyDeviceToHost));
-    if (flag) {
-      cudaMemset(db->d_xchg_timed_out, 0, 4);
-      set_error("fused exchange: a peer rank did not deliver its lists within 10 s");
-      return SSW_ERR_CUDA;
+  int32_t* d_cert = reinterpret_cast<int32_t*>(d_out + db_b + sc_b + row_b + cnt_b);
+  auto check_xchg = [&]() -> int {
+    if (xc && db->d_xchg_timed_out) {
+      int flag = 0;
+      SSW_CUDA(cudaMemcpy(&flag, db->d_xchg_timed_out, 4, cudaMemcpyDeviceToHost));
+      if (flag) {
+        cudaMemset(db->d_xchg_timed_out, 0, 4);
+        set_error("fused exchange: a peer rank did not deliver its lists within 10 s");
+        return SSW_ERR_CUDA;
+      }
+    }
+    return SSW_OK;
+  };
+  if (!exact) {
+    rc = scan_topk_impl(db, d_q, nq, k, d_bits, d_key, d_dbidx, d_score, d_row, d_cnt, st, xc);
+    if (rc) return rc;
+    SSW_CUDA(cudaMemcpyAsync(h, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    SSW_CUDA(cudaStreamSynchronize(st));
+    if ((rc = check_xchg())) return rc;
+  } else {
+    // 1. fp16 scan for kc candidates  2. fp32 re-scoring  3. ranking + certificate   (ssw_exact.cu)
+    rc = scan_topk_impl(db, d_q, nq, kc, d_bits, d_key16, d_cand, nullptr, nullptr, nullptr, st, nullptr);
+    if (rc) return rc;
+    if ((rc = launch_exact_rescore(db, d_q, nq, kc, d_cand, d_key32, st))) return rc;
+    const double err_unit = db->exact_rho + db->exact_vmax * (double)db->dim * 1.8e-7;
+    if ((rc = launch_exact_finish(d_q, db->dim, nq, kc, k, d_key16, d_key32, d_cand, err_unit, d_dbidx, d_score, d_row,
+                                  d_cnt, d_key, d_cert, st)))
+      return rc;
+    SSW_CUDA(cudaMemcpyAsync(h, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    SSW_CUDA(cudaStreamSynchronize(st));
+    const int32_t* cert = reinterpret_cast<const int32_t*>(h + db_b + sc_b + row_b + cnt_b);
+    int n_rescan = 0;
+    for (int q = 0; q < nq; ++q)
+      if (!cert[q]) {      // scores too close to call from fp16: the streaming kernel over the fp32 rows decides
+        rc = scan_topk_impl(db, d_q + (size_t)q * db->dim, 1, k, d_bits ? d_bits + (size_t)q * db->excl_words : nullptr,
+                            d_key + (size_t)q * k, d_dbidx + (size_t)q * k, d_score + (size_t)q * k, d_row + (size_t)q * k,
+                            d_cnt + q, st, nullptr, true);
+        if (rc) return rc;
+        ++n_rescan;
+      }
+    db->exact_queries += nq;
+    db->exact_rescans += n_rescan;
+    if (xc) {        // this shard's exact top-k is ONE list per query for the fused exchange
+      if (!db->d_xchg_timed_out) {
+        SSW_CUDA(cudaMalloc((void**)&db->d_xchg_timed_out, 4));
+        SSW_CUDA(cudaMemset(db->d_xchg_timed_out, 0, 4));
+      }
+      // the exchange writes the world's result over d_out while reading d_key / d_dbidx: hand it copies
+      rc = ensure_lists(db, nq, 1, k);
+      if (rc) return rc;
+      SSW_CUDA(cudaMemcpyAsync(db->d_list_keys, d_key, nk * 8, cudaMemcpyDeviceToDevice, st));
+      SSW_CUDA(cudaMemcpyAsync(db->d_list_dbidx, d_dbidx, nk * 4, cudaMemcpyDeviceToDevice, st));
+      rc = launch_exchange_merge(db->d_list_keys, db->d_list_dbidx, 1, k, k, nq, k, nullptr, xc->peers, xc->world, xc->rank,
+                                 xc->nq_cap, xc->k_cap, xc->epoch, db->d_xchg_timed_out, d_key, d_dbidx, d_score, d_row,
+                                 d_cnt, st);
+      if (rc) return rc;
+    }
+    if (n_rescan || xc) {
+      SSW_CUDA(cudaMemcpyAsync(h, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+      SSW_CUDA(cudaStreamSynchronize(st));
+      if ((rc = check_xchg())) return rc;
     }
   }
   if (out_dbidx) memcpy(out_dbidx, h, nk * 4);
@@ -640,11 +715,61 @@ static int scan_topk_host(ssw_db* db, const float* queries, int nq, int k, const
   return SSW_OK;
 }
 
+int ssw_db_attach_exact(ssw_db* db, const float* vectors) {
+  SSW_REQUIRE(db != nullptr && (vectors != nullptr || db->n_rows == 0), "null argument");
+  SSW_REQUIRE(db->dtype == SSW_F16, "an exact fp32 copy only makes sense next to fp16 storage");
+  std::lock_guard<std::mutex> guard(db->mu);
+  SSW_CUDA(cudaSetDevice(db->device));
+  if (db->d_exact) {
+    cudaFree(db->d_exact);
+    db->d_exact = nullptr;
+  }
+  std::vector<int64_t> perm;
+  if (db->d_orig_row) {
+    perm.resize(db->n_rows);
+    SSW_CUDA(cudaMemcpy(perm.data(), db->d_orig_row, (size_t)db->n_rows * 8, cudaMemcpyDeviceToHost));
+  }
+  float* d = nullptr;
+  cudaError_t e = cudaMalloc((void**)&d, std::max<size_t>((size_t)db->n_rows * db->dim * 4, 16));
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMalloc(exact fp32 copy): ") + cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? SSW_ERR_OOM : SSW_ERR_CUDA;
+  }
+  int rc = upload_rows(db, vectors, SSW_F32, d, SSW_F32, perm);
+  float* d_stats = nullptr;
+  float stats[2] = {0.f, 0.f};
+  if (!rc && cudaMalloc((void**)&d_stats, 8) != cudaSuccess) rc = SSW_ERR_CUDA;
+  if (!rc) rc = launch_row_error_stats(d, db->n_rows, db->dim, d_stats, db->stream);
+  if (!rc && cudaMemcpyAsync(stats, d_stats, 8, cudaMemcpyDeviceToHost, db->stream) != cudaSuccess) rc = SSW_ERR_CUDA;
+  if (!rc && cudaStreamSynchronize(db->stream) != cudaSuccess) rc = SSW_ERR_CUDA;
+  cudaFree(d_stats);
+  if (rc) {
+    cudaFree(d);
+    if (rc == SSW_ERR_CUDA) set_error("attaching the exact copy failed");
+    return rc;
+  }
+  db->d_exact = d;
+  db->exact_rho = std::sqrt((double)stats[0]) * (1.0 + 1e-6);
+  db->exact_vmax = std::sqrt((double)stats[1]) * (1.0 + 1e-6);
+  return SSW_OK;
+}
+
+int ssw_db_exact_info(ssw_db* db, int* attached, double* rho, double* vmax, int64_t* queries, int64_t* rescans) {
+  SSW_REQUIRE(db != nullptr, "db is null");
+  if (attached) *attached = db->d_exact != nullptr;
+  if (rho) *rho = db->exact_rho;
+  if (vmax) *vmax = db->exact_vmax;
+  if (queries) *queries = db->exact_queries;
+  if (rescans) *rescans = db->exact_rescans;
+  return SSW_OK;
+}
+
 int ssw_topk_from_scores(ssw_db* db, const float* scores, const uint8_t* row_mask, int k, const int32_t* exclude_dbidx,
                          int64_t n_exclude, int32_t* out_dbidx, float* out_score, int64_t* out_row, int32_t* out_count) {
   SSW_REQUIRE(db != nullptr && (scores != nullptr || db->n_rows == 0), "null argument");
   SSW_REQUIRE(k > 0 && k <= SSW_MAX_TOPK, "k must be in [1, SSW_MAX_TOPK]");
   SSW_REQUIRE(n_exclude >= 0 && (n_exclude == 0 || exclude_dbidx != nullptr), "bad exclude list");
+  std::lock_guard<std::mutex> guard(db->mu);
   SSW_CUDA(cudaSetDevice(db->device));
   auto up16 = [](size_t x) { return (x + 15) / 16 * 16; };
   const int64_t n = db->n_rows;
@@ -721,6 +846,7 @@ int ssw_score_all_device(ssw_db* db, const float* d_query, float* d_out_scores, 
 
 int ssw_score_all(ssw_db* db, const float* query, float* out_scores) {
   SSW_REQUIRE(db != nullptr && query != nullptr && out_scores != nullptr, "null argument");
+  std::lock_guard<std::mutex> guard(db->mu);
   SSW_CUDA(cudaSetDevice(db->device));
   const size_t q_bytes = ((size_t)db->dim * 4 + 15) / 16 * 16;
   const size_t s_bytes = (size_t)db->n_rows * 4;

@@ -159,6 +159,40 @@ __device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
   uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
   return ((uint64_t)hi << 32) | lo;
 }
+// The canonical dot product of one stored row with a query: exactly the arithmetic of the streaming scan
+// (scan1_kernel, ssw_scan.cu) for rows of type T — lane l owns the 16-byte chunks (c*32 + l), folds their
+// elements in order into ONE fp32 FMA chain starting at 0, then the lanes are summed by the xor butterfly
+// 16, 8, 4, 2, 1 (the transposed butterfly of the scan adds the same pairs in the same order).  Every kernel
+// that re-scores a row (stage 2, exact-mode re-ranking) uses this, so a row has ONE fp32 score per storage
+// type, whichever kernel computed it.  All 32 lanes receive the result.
+template <typename T>
+__device__ __forceinline__ float canon_dot(const T* __restrict__ row, const float* __restrict__ q, int dim, int lane) {
+  constexpr int EPC = 16 / (int)sizeof(T);
+  float s = 0.f;
+  const int chunks = dim / (32 * EPC);
+  for (int c = 0; c < chunks; ++c) {
+    const int base = (c * 32 + lane) * EPC;
+    const uint4 raw = *reinterpret_cast<const uint4*>(row + base);
+    if constexpr (sizeof(T) == 2) {
+      const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 t = __half22float2(h[i]);
+        s = fmaf(t.x, q[base + 2 * i], s);
+        s = fmaf(t.y, q[base + 2 * i + 1], s);
+      }
+    } else {
+      s = fmaf(__uint_as_float(raw.x), q[base + 0], s);
+      s = fmaf(__uint_as_float(raw.y), q[base + 1], s);
+      s = fmaf(__uint_as_float(raw.z), q[base + 2], s);
+      s = fmaf(__uint_as_float(raw.w), q[base + 3], s);
+    }
+  }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  return s;
+}
+
 // Pooled lower bound of a query's final k-th best score.  Every CTA publishes the best score it holds
 // (order-preserving bits, 0 = none yet); lane l passes v[m] = value of CTA l + 32m.  The CTAs are split
 // into ngp >= k groups (CTA c in group c mod ngp, ngp a power of two <= 128): the smallest group maximum

@@ -1,5 +1,6 @@
 // Internal definition of the database handle and kernel launch entry points.
 #pragma once
+#include <mutex>
 #include <utility>
 #include <vector>
 
@@ -24,7 +25,16 @@ struct ssw_db {
   int scan_grid = 0;               // CTAs of the streaming scan (one per SM)
   int64_t max_cta_images = 0;      // most images any CTA's range holds
   uint32_t* d_last_bits = nullptr; // [n_rows/32 + pad] bit r set <=> device row r is the last row of its image
-  int32_t* d_boxes = nullptr;      // [n_rows][5] x1,y1,x2,y2,zoom per device row (stage-2 rescoring; optional)
+  void* d_boxes = nullptr;         // [n_rows][4] x1,y1,x2,y2 per device row, element type box_kind (stage 2; optional)
+  int32_t* d_zoom = nullptr;       // [n_rows] zoom level per device row
+  int box_kind = 0;                // SSW_BOX_I32 / SSW_BOX_F32 / SSW_BOX_F64
+  // exact mode (ssw_db_attach_exact): the reference's own fp32 values next to the fp16 scan copy
+  float* d_exact = nullptr;        // [n_rows, dim] fp32, same (grouped) row order as d_vecs
+  double exact_rho = 0.0;          // max over rows of ||v - fp16(v)||_2
+  double exact_vmax = 0.0;         // max over rows of ||v||_2
+  int64_t exact_queries = 0;       // queries answered in exact mode / of those, re-scanned in fp32
+  int64_t exact_rescans = 0;
+  std::mutex mu;                   // serialises the host-buffer entry points (they share the staging blocks)
   std::vector<int32_t> h_img_dbidx; // host copy of d_img_dbidx (candidate id -> image index), filled on first use
   int* d_xchg_timed_out = nullptr; // set by the fused exchange kernel when a peer never answered
   void* d_tc_ws = nullptr;         // prepared A operand of the tcgen05 batched scan (one batch)
@@ -63,9 +73,18 @@ void prof_end(ssw_db* db, cudaStream_t st);
 
 // streaming single-query scan (K1); MODE 0 = fused segmented max + exclusion + top-k lists,
 // MODE 1 = plain score vector (index.score)
+// `exact`: scan the fp32 copy (db->d_exact) instead of the stored vectors
 int launch_scan1(ssw_db* db, const float* d_query, int k, const uint32_t* d_excl, uint64_t* d_list_keys,
-                 int32_t* d_list_dbidx, uint64_t* d_gthr, uint32_t* d_pub, cudaStream_t st);
+                 int32_t* d_list_dbidx, uint64_t* d_gthr, uint32_t* d_pub, cudaStream_t st, bool exact = false);
 int launch_score_all(ssw_db* db, const float* d_query, float* d_out, cudaStream_t st);
+// exact mode: fp32 re-scoring of the candidate images of a scan, and the certified final top-k
+int launch_exact_rescore(ssw_db* db, const float* d_queries, int nq, int kc, const int32_t* d_cand_dbidx,
+                         uint64_t* d_keys32, cudaStream_t st);
+int launch_exact_finish(const float* d_queries, int dim, int nq, int kc, int k, const uint64_t* d_keys16,
+                        const uint64_t* d_keys32, const int32_t* d_cand_dbidx, double err_per_unit_q,
+                        int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row, int32_t* d_out_count,
+                        uint64_t* d_out_key, int32_t* d_certified, cudaStream_t st);
+int launch_row_error_stats(const float* d_rows_f32, int64_t n_rows, int dim, float* d_stats2, cudaStream_t st);
 // tcgen05 batched scan (K2): one pass for up to 64 queries; fp16 storage, dim 256/512/768, k <= 64
 bool scan_tc_supported(const ssw_db* db, int k);
 size_t scan_tc_workspace_bytes(int dim, int grid);

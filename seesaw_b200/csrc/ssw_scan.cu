@@ -446,9 +446,9 @@ static int launch_scan1_t(ssw_db* db, const Scan1Args& a, cudaStream_t st) {
 }
 
 template <int MODE>
-static int dispatch_scan1(ssw_db* db, const Scan1Args& a, cudaStream_t st) {
+static int dispatch_scan1(ssw_db* db, const Scan1Args& a, cudaStream_t st, int dtype) {
   const int d = db->dim;
-  if (db->dtype == SSW_F16) {
+  if (dtype == SSW_F16) {
     switch (d) {
       case 256: return launch_scan1_t<__half, 1, MODE>(db, a, st);
       case 512: return launch_scan1_t<__half, 2, MODE>(db, a, st);
@@ -468,9 +468,9 @@ static int dispatch_scan1(ssw_db* db, const Scan1Args& a, cudaStream_t st) {
 }
 
 int launch_scan1(ssw_db* db, const float* d_query, int k, const uint32_t* d_excl, uint64_t* d_list_keys,
-                 int32_t* d_list_dbidx, uint64_t* d_gthr, uint32_t* d_pub, cudaStream_t st) {
+                 int32_t* d_list_dbidx, uint64_t* d_gthr, uint32_t* d_pub, cudaStream_t st, bool exact) {
   Scan1Args a{};
-  a.vecs = db->d_vecs;
+  a.vecs = exact ? static_cast<const void*>(db->d_exact) : db->d_vecs;
   a.last_bits = db->d_last_bits;
   a.row_ptr = db->d_row_ptr;
   a.img_dbidx = db->d_img_dbidx;
@@ -485,12 +485,14 @@ int launch_scan1(ssw_db* db, const float* d_query, int k, const uint32_t* d_excl
   a.scores_out = nullptr;
   a.row_base = db->row_base;
   a.k = k;
-  return dispatch_scan1<0>(db, a, st);
+  return dispatch_scan1<0>(db, a, st, exact ? (int)SSW_F32 : db->dtype);
 }
 
+// With an exact copy attached the full score vector comes from the fp32 rows (index.score feeds label
+// propagation priors and active search: the reference's values, not their fp16 roundings).
 int launch_score_all(ssw_db* db, const float* d_query, float* d_out, cudaStream_t st) {
   Scan1Args a{};
-  a.vecs = db->d_vecs;
+  a.vecs = db->d_exact ? static_cast<const void*>(db->d_exact) : db->d_vecs;
   a.last_bits = db->d_last_bits;
   a.row_ptr = db->d_row_ptr;
   a.img_dbidx = db->d_img_dbidx;
@@ -500,7 +502,7 @@ int launch_score_all(ssw_db* db, const float* d_query, float* d_out, cudaStream_
   a.scores_out = d_out;
   a.row_base = db->row_base;
   a.k = 0;
-  return dispatch_scan1<1>(db, a, st);
+  return dispatch_scan1<1>(db, a, st, db->d_exact ? (int)SSW_F32 : db->dtype);
 }
 
 // ------------------------------------------------------------------------------------------

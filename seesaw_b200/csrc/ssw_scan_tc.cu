@@ -18,12 +18,14 @@
 // so a 16x256b tcgen05.ld of half h hands thread (r = lane/4, j = lane%4) BOTH parts of one query for
 // columns 8i+2j, 8i+2j+1 (i = 0..3): hi + lo needs no shuffle and no lane is redundant.
 //
-// Epilogue cost model: per 128-row tile a thread folds 64 scores (FADD hi + lo, then a
-// depth-3 argmax tree per 8 columns: the epilogue warps run alone on their schedulers, so dependent-issue
-// latency is what a tile costs); an image boundary costs one vote, and only when some lane's partial max
-// reaches its query's threshold a quad reduction (8 SHFL) plus the owner's threshold / exclusion / list
-// work.  Everything lives in registers and shared memory: no local memory, no out-of-line calls.  A seventh
-// warp pools the CTAs' published bests into tighter thresholds for the whole life of the kernel.
+// Epilogue cost model: eight epilogue warps, two per 32-lane quarter of tensor memory
+// (warp q4 takes the quarter's half 0 = queries 16*q4 + r, warp q4 + 4 its half 1 = queries 16*q4 + 8 + r), so
+// a thread carries ONE query and every scheduler has two epilogue warps to alternate (the epilogue is bound by
+// dependent-issue latency).  Per 128-row tile a thread folds 32 scores (FADD hi + lo, then a depth-3 argmax
+// tree per 8 columns); an image boundary costs one vote, and only when some lane's partial max reaches its
+// query's threshold a quad reduction (4 SHFL) plus the owner's threshold / exclusion / list work.  Everything
+// lives in registers and shared memory: no local memory, no out-of-line calls.  One more warp pools the CTAs'
+// published bests into tighter thresholds for the whole life of the kernel.
 #include <algorithm>
 #include <cstdlib>
 
@@ -188,58 +190,6 @@ __device__ __forceinline__ uint64_t scan_tc_offer(const QShared& Q, const ScanTc
   return mk > old ? mk : old;
 }
 
-// Running state of one epilogue thread: partial maxima (over this thread's columns) of the two
-// queries of its quad for the image being walked, and what they must reach to matter.
-struct EpiState {
-  float m0, m1;       // running max, query A (half 0) / query B (half 1)
-  int c0, c1;         // column (relative to the CTA's first row) of that max
-  float thrA, thrB;   // accumulator-space thresholds
-  int cur_img;        // local image index of the image being walked (warp-uniform)
-};
-
-struct EpiCtx {
-  int j;              // lane % 4
-  bool owner;         // this thread owns query own_q (j == 0: query A, j == 1: query B)
-  int own_q;
-  float invA, invB, scaleA, scaleB;
-  int64_t r_begin;
-  int slice_base;     // first bitmap word of the CTA's exclusion slice
-};
-
-// An image ends here (warp-uniform call).
-__device__ __forceinline__ void scan_tc_boundary(EpiState& st, const EpiCtx& cx, const QShared& Q,
-                                                 const ScanTcArgs& a) {
-  const bool cand = (st.m0 >= st.thrA) | (st.m1 >= st.thrB);
-  if (__any_sync(0xffffffffu, cand)) {
-    // (score desc, column asc) max over the quad for both queries
-    uint64_t k0 = ((uint64_t)f32_ordered(st.m0) << 32) | (uint32_t)(0x7FFFFFFF - st.c0);
-    uint64_t k1 = ((uint64_t)f32_ordered(st.m1) << 32) | (uint32_t)(0x7FFFFFFF - st.c1);
-    uint64_t o0 = shfl_xor_u64(k0, 1), o1 = shfl_xor_u64(k1, 1);
-    k0 = o0 > k0 ? o0 : k0;
-    k1 = o1 > k1 ? o1 : k1;
-    o0 = shfl_xor_u64(k0, 2);
-    o1 = shfl_xor_u64(k1, 2);
-    k0 = o0 > k0 ? o0 : k0;
-    k1 = o1 > k1 ? o1 : k1;
-    if (cx.owner) {
-      const uint64_t kk = cx.j ? k1 : k0;
-      const float best = f32_from_ordered((uint32_t)(kk >> 32));
-      const float mythr = cx.j ? st.thrB : st.thrA;
-      if (best >= mythr) {
-        const int col = 0x7FFFFFFF - (int)(uint32_t)(kk & 0xFFFFFFFFu);
-        const uint64_t nthr = scan_tc_offer(Q, a, cx.own_q, best, cx.j ? cx.invB : cx.invA, cx.r_begin + col, st.cur_img,
-                                            cx.slice_base);
-        const float t = thr_to_acc(nthr, cx.j ? cx.scaleB : cx.scaleA);
-        if (cx.j) st.thrB = t; else st.thrA = t;
-      }
-    }
-    __syncwarp();
-  }
-  st.m0 = st.m1 = -INFINITY;
-  st.c0 = st.c1 = 0;
-  ++st.cur_img;
-}
-
 // Threshold warp.  Every CTA publishes the best score it holds per query (a.pub).  Split the G CTAs into
 // NGP >= k groups (CTA c in group c mod NGP): the smallest of the group maxima is a score that at least
 // k distinct images reach, hence a valid lower bound of the final k-th best — far tighter than a single
@@ -306,276 +256,6 @@ __device__ __forceinline__ void argmax8(const float* x, float& m, int& idx) {
   idx = r ? j1 : j0;
 }
 
-// 32 accumulator columns starting at column `colbase`: v0 / v1 are the 16x256b loads of half 0 / 1,
-// em has bit c set when column colbase + c is the last row of its image.
-__device__ __forceinline__ void scan_tc_group(EpiState& st, const EpiCtx& cx, const QShared& Q, const ScanTcArgs& a,
-                                              const uint32_t* v0, const uint32_t* v1, uint32_t em, int colbase) {
-  float sa[8], sb[8];       // query A / B at this thread's columns 8i + 2j + e  (index 2i + e)
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    sa[2 * i] = __uint_as_float(v0[4 * i]) + __uint_as_float(v0[4 * i + 2]);
-    sa[2 * i + 1] = __uint_as_float(v0[4 * i + 1]) + __uint_as_float(v0[4 * i + 3]);
-    sb[2 * i] = __uint_as_float(v1[4 * i]) + __uint_as_float(v1[4 * i + 2]);
-    sb[2 * i + 1] = __uint_as_float(v1[4 * i + 1]) + __uint_as_float(v1[4 * i + 3]);
-  }
-  const int cb = colbase + 2 * cx.j;
-  if (em == 0) {            // warp-uniform fast path: no image ends inside these 32 columns
-    float ma, mb;
-    int ia, ib;
-    argmax8(sa, ma, ia);
-    argmax8(sb, mb, ib);
-    if (ma > st.m0) { st.m0 = ma; st.c0 = cb + ((ia >> 1) << 3) + (ia & 1); }
-    if (mb > st.m1) { st.m1 = mb; st.c1 = cb + ((ib >> 1) << 3) + (ib & 1); }
-    return;
-  }
-  // walk the image boundaries in order (warp-uniform loop); fold in this thread's columns of each segment
-  int lo = 0;
-  for (;;) {
-    const int p = em ? __ffs(em) - 1 : 31;
-    const uint32_t seg = (0xFFFFFFFFu >> (31 - p)) & (0xFFFFFFFFu << lo);   // columns lo..p
-    const uint32_t mine = seg >> (2 * cx.j);                                // bit 8i+e <-> my column 8i+2j+e
-    float xa[8], xb[8];       // branch-free: a column outside the segment competes with -inf
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const bool on = (mine >> (8 * i + e)) & 1u;
-        xa[2 * i + e] = on ? sa[2 * i + e] : -INFINITY;
-        xb[2 * i + e] = on ? sb[2 * i + e] : -INFINITY;
-      }
-    float ma, mb;
-    int ia, ib;
-    argmax8(xa, ma, ia);
-    argmax8(xb, mb, ib);
-    if (ma > st.m0) { st.m0 = ma; st.c0 = cb + ((ia >> 1) << 3) + (ia & 1); }
-    if (mb > st.m1) { st.m1 = mb; st.c1 = cb + ((ib >> 1) << 3) + (ib & 1); }
-    if (em == 0) break;
-    em &= em - 1;
-    scan_tc_boundary(st, cx, Q, a);
-    lo = p + 1;
-    if (lo == 32) break;
-  }
-}
-
-// tcgen05.wait::ld that also names the destination registers, so no use of them can be scheduled
-// above the wait.
-__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t* x, uint32_t* y) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]),
-                 "+r"(x[8]), "+r"(x[9]), "+r"(x[10]), "+r"(x[11]), "+r"(x[12]), "+r"(x[13]), "+r"(x[14]), "+r"(x[15]),
-                 "+r"(y[0]), "+r"(y[1]), "+r"(y[2]), "+r"(y[3]), "+r"(y[4]), "+r"(y[5]), "+r"(y[6]), "+r"(y[7]),
-                 "+r"(y[8]), "+r"(y[9]), "+r"(y[10]), "+r"(y[11]), "+r"(y[12]), "+r"(y[13]), "+r"(y[14]), "+r"(y[15])
-               :
-               : "memory");
-}
-
-constexpr int kScanTcThreads = kTcThreads + 32;     // + the threshold warp
-
-template <int DIM, int NT, int NS, int NACC>
-__global__ void __launch_bounds__(kScanTcThreads, 1) scan_tc_kernel(const __grid_constant__ CUtensorMap tmap,
-                                                                 const ScanTcArgs a) {
-  using Cfg = TcCfg<DIM, NT, NACC>;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem;
-  const TcSmem S = tc_carve(smem_raw, NS, Cfg::STAGE_BYTES, &smem);
-  uint8_t* after = smem + NS * Cfg::STAGE_BYTES + ((tc_bar_bytes(NS) + 15) / 16) * 16;
-  const QShared Q = qshared_carve(after, a.k);
-  if (threadIdx.x < 64) {      // per-query list state (before the barrier inside tc_setup)
-    Q.thr[threadIdx.x] = 0;
-    Q.cnt[threadIdx.x] = 0;
-    Q.minpos[threadIdx.x] = 0;
-    Q.best[threadIdx.x] = 0;
-    if (threadIdx.x == 0) *Q.done = 0;
-  }
-  const uint32_t tmem = tc_setup(S, NS, Cfg::TMEM_ALLOC, &tmap);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  const int img0 = a.part[blockIdx.x * kScanWarps], img1 = a.part[(blockIdx.x + 1) * kScanWarps];
-  const int64_t r_begin = a.row_ptr[img0], r_end = a.row_ptr[img1];
-  const int64_t nrows = r_end - r_begin;
-  const int ntiles = (int)((nrows + NT - 1) / NT);
-
-  if (warp == 0) {
-    if (lane == 0) {
-      TcPipe p(NS);
-      for (int t = 0; t < ntiles; ++t) {
-        for (int kc = 0; kc < Cfg::KC; ++kc) {
-          mbar_wait_parked(S.empty + 8 * p.stage, p.phase ^ 1);
-          mbar_expect_tx(S.full + 8 * p.stage, Cfg::STAGE_BYTES);
-          tma_load_2d(S.stages + p.stage * Cfg::STAGE_BYTES, &tmap, kc * kTcKChunk, (int)(r_begin + (int64_t)t * NT),
-                      S.full + 8 * p.stage);
-          p.advance();
-        }
-      }
-    }
-  } else if (warp == 1) {
-    TcPipe p(NS);
-    mbar_wait_parked(S.a_ready, 0);
-    tc_fence_after();
-    for (int t = 0; t < ntiles; ++t) {
-      const uint32_t as = NACC == 2 ? (t & 1) : 0;
-      mbar_wait_parked(S.tmem_empty + 8 * as, ((NACC == 2 ? (t >> 1) : t) & 1) ^ 1);
-      tc_fence_after();
-      for (int kc = 0; kc < Cfg::KC; ++kc) {
-        mbar_wait_parked(S.full + 8 * p.stage, p.phase);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint64_t bdesc = make_bdesc_sw128(S.stages + p.stage * Cfg::STAGE_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            mma_f16_ts(tmem + Cfg::ACC_BASE + as * NT, tmem + Cfg::A_BASE + kc * 32 + k * 8, bdesc + 2 * k, Cfg::IDESC,
-                       (kc | k) != 0);
-          tc_commit(S.empty + 8 * p.stage);
-        }
-        __syncwarp();
-        p.advance();
-      }
-      if (lane == 0) tc_commit(S.tmem_full + 8 * as);
-      __syncwarp();
-    }
-  } else if (warp == 6) {
-    scan_tc_threshold_warp(Q, a, lane);
-  } else {
-    // ===== epilogue warps (warp w may touch TMEM lanes 32*(w%4) .. +31)
-    const int q4 = warp & 3;
-    const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
-    const int k = a.k;
-
-    // ---- A operand: thread t copies the prepared row of TMEM lane 32*q4 + t
-    {
-      const uint4* src = reinterpret_cast<const uint4*>(a.a_img + (size_t)(q4 * 32 + lane) * (DIM / 2));
-#pragma unroll 1
-      for (int c = 0; c < Cfg::A_COLS / 32; ++c) {
-        uint32_t rr[32];
-#pragma unroll
-        for (int x = 0; x < 8; ++x) {
-          const uint4 w = __ldg(src + c * 8 + x);
-          rr[4 * x] = w.x;
-          rr[4 * x + 1] = w.y;
-          rr[4 * x + 2] = w.z;
-          rr[4 * x + 3] = w.w;
-        }
-        tmem_st32(lane_addr + Cfg::A_BASE + c * 32, rr);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(S.a_ready);
-    }
-
-    // ---- this CTA's slice of the warp's 16 exclusion bitmaps -> shared memory
-    const int slice_base = img0 >> 5;
-    if (a.excl && a.excl_slice_words > 0 && img1 > img0) {
-      const int nw = ((img1 - 1) >> 5) - slice_base + 1;
-      for (int i = 0; i < 16; ++i) {
-        const int qs = q4 * 16 + i;
-        if (qs >= a.nq) break;
-        for (int w = lane; w < nw; w += 32)
-          Q.excl[qs * a.excl_slice_words + w] = __ldg(a.excl + (size_t)qs * a.excl_words + slice_base + w);
-      }
-      __syncwarp();
-    }
-
-    EpiCtx cx;
-    cx.slice_base = slice_base;
-    cx.j = lane & 3;
-    const int r = lane >> 2;
-    const int qA = q4 * 16 + r, qB = qA + 8;
-    cx.own_q = cx.j == 0 ? qA : qB;
-    cx.owner = cx.j < 2 && cx.own_q < a.nq;
-    cx.invA = __ldg(a.inv_scale + qA);
-    cx.invB = __ldg(a.inv_scale + qB);
-    cx.scaleA = 1.0f / cx.invA;      // powers of two: exact
-    cx.scaleB = 1.0f / cx.invB;
-    cx.r_begin = r_begin;
-    EpiState st;
-    st.m0 = st.m1 = -INFINITY;
-    st.c0 = st.c1 = 0;
-    st.thrA = st.thrB = -INFINITY;
-    st.cur_img = img0;
-
-    constexpr int NG = NT / 32;
-    static_assert(NG == 2 || NG == 4, "tile must be 64 or 128 rows");
-    // image-boundary bits of the next tile, fetched one tile ahead (NG + 1 words cover any alignment)
-    uint32_t wb[NG + 1];
-    auto fetch_bits = [&](int t) {
-      const uint32_t* p = a.last_bits + ((r_begin + (int64_t)t * NT) >> 5);
-#pragma unroll
-      for (int i = 0; i <= NG; ++i) wb[i] = __ldg(p + i);
-    };
-    if (ntiles > 0) fetch_bits(0);
-    for (int t = 0; t < ntiles; ++t) {
-      const uint32_t as = NACC == 2 ? (t & 1) : 0;
-      const int64_t row0 = r_begin + (int64_t)t * NT;
-      const int sh = (int)(row0 & 31);
-      const int valid = (int)min((int64_t)NT, r_end - row0);
-      uint32_t ends[NG];
-#pragma unroll
-      for (int g = 0; g < NG; ++g) {
-        const int rem = valid - 32 * g;
-        const uint32_t keep = rem >= 32 ? 0xFFFFFFFFu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
-        ends[g] = __funnelshift_r(wb[g], wb[g + 1], sh) & keep;
-      }
-      if (t + 1 < ntiles) fetch_bits(t + 1);
-      // the quad's register copies of the thresholds (raised by the owners and by the threshold warp)
-      st.thrA = thr_to_acc(Q.thr[qA], cx.scaleA);
-      st.thrB = thr_to_acc(Q.thr[qB], cx.scaleB);
-      mbar_wait(S.tmem_full + 8 * as, (NACC == 2 ? (t >> 1) : t) & 1);
-      tc_fence_after();
-      const uint32_t acc = lane_addr + Cfg::ACC_BASE + as * NT;
-      const int colbase = (int)(row0 - r_begin);
-      uint32_t va0[16], va1[16], vb0[16], vb1[16];
-      tmem_ld_16x256b_x4(acc, va0);
-      tmem_ld_16x256b_x4(acc + (16u << 16), va1);
-      tmem_ld_wait_regs(va0, va1);
-#pragma unroll 1
-      for (int gp = 0; gp < NG; gp += 2) {
-        uint32_t eA = ends[0], eB = ends[1];
-        if constexpr (NG == 4) {
-          eA = gp ? ends[2] : eA;
-          eB = gp ? ends[3] : eB;
-        }
-        tmem_ld_16x256b_x4(acc + 32 * (gp + 1), vb0);
-        tmem_ld_16x256b_x4(acc + (16u << 16) + 32 * (gp + 1), vb1);
-        scan_tc_group(st, cx, Q, a, va0, va1, eA, colbase + 32 * gp);
-        tmem_ld_wait_regs(vb0, vb1);
-        if (gp + 2 < NG) {
-          tmem_ld_16x256b_x4(acc + 32 * (gp + 2), va0);
-          tmem_ld_16x256b_x4(acc + (16u << 16) + 32 * (gp + 2), va1);
-        }
-        scan_tc_group(st, cx, Q, a, vb0, vb1, eB, colbase + 32 * (gp + 1));
-        if (gp + 2 < NG) tmem_ld_wait_regs(va0, va1);
-      }
-      tc_fence_before();
-      mbar_arrive(S.tmem_empty + 8 * as);
-    }
-    // ---- publish this CTA's list of every query
-    __syncwarp();
-    if (lane == 0) atomicAdd(Q.done, 1);
-    // (the warp's 16 queries x k slots spread over its 32 lanes: independent loads and stores)
-    {
-      const int nqw = min(16, a.nq - q4 * 16);
-#pragma unroll 4
-      for (int e = lane; e < nqw * k; e += 32) {
-        const int qi = q4 * 16 + e / k, sl = e % k;
-        const bool ok = sl < Q.cnt[qi];
-        const int64_t o = ((int64_t)qi * gridDim.x + blockIdx.x) * k + sl;
-        a.list_keys[o] = ok ? Q.keys[sl * 64 + qi] : 0ull;
-        a.list_dbidx[o] = ok ? __ldg(a.img_dbidx + Q.img[sl * 64 + qi]) : -1;
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, Cfg::TMEM_ALLOC);
-}
-
-// ------------------------------------------------------------------------------------------
-// Eight-warp epilogue variant.  The four-warp epilogue is bound by dependent-issue latency (one warp per
-// scheduler, nothing to switch to).  Here two warps share each 32-lane quarter of tensor memory: warp
-// q4 handles the quarter's half 0 (queries 16*q4 + r), warp q4 + 4 its half 1 (queries 16*q4 + 8 + r), so
-// a thread carries ONE query instead of two and every scheduler has two epilogue warps to alternate.
-// Everything else (operand layout, thresholds, lists, boundary walk) is the kernel above.
-// ------------------------------------------------------------------------------------------
 struct Epi1State {
   float m;            // running max of this thread's columns for its quad's query
   int c;
@@ -857,20 +537,11 @@ static int launch_scan_tc_t(ssw_db* db, const ScanTcArgs& a, cudaStream_t st) {
       smem += (size_t)64 * words * 4;
     }
   }
-  static const bool epi4 = [] { const char* e = getenv("SSW_TC_EPI4"); return e && e[0] == '1'; }();
-  if (epi4) {
-    auto kern = scan_tc_kernel<DIM, NT, NS, NACC>;
-    SSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    prof_begin(db, st);      // times the scan kernel alone (not the query preparation)
-    kern<<<db->scan_grid, kScanTcThreads, smem, st>>>(tmap, a2);
-    prof_end(db, st);
-  } else {
-    auto kern = scan_tc8_kernel<DIM, NT, NS, NACC>;
-    SSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    prof_begin(db, st);
-    kern<<<db->scan_grid, kScanTc8Threads, smem, st>>>(tmap, a2);
-    prof_end(db, st);
-  }
+  auto kern = scan_tc8_kernel<DIM, NT, NS, NACC>;
+  SSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  prof_begin(db, st);      // times the scan kernel alone (not the query preparation)
+  kern<<<db->scan_grid, kScanTc8Threads, smem, st>>>(tmap, a2);
+  prof_end(db, st);
   SSW_LAUNCHED();
   return SSW_OK;
 }
@@ -914,8 +585,7 @@ int launch_scan_tc(ssw_db* db, const float* d_queries, int nq, int k, const uint
     case 512: return launch_scan_tc_t<512, 128, 10, 2>(db, a, st);
     // 768: A takes 384 of the 512 TMEM columns; one 128-column accumulator (MMA and epilogue alternate,
     // together well under the tile's HBM time) beats two 64-column ones (twice the per-tile overhead)
-    case 768: return getenv("SSW_TC768_NT64") ? launch_scan_tc_t<768, 64, 20, 2>(db, a, st)
-                                              : launch_scan_tc_t<768, 128, 10, 1>(db, a, st);
+    case 768: return launch_scan_tc_t<768, 128, 10, 1>(db, a, st);
   }
   set_error("batched scan supports dim 256, 512 or 768");
   return SSW_ERR_INVALID;

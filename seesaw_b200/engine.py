@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib  # noqa: F401
-from ._lib import SSW_F16, SSW_F32, check, lib, ptr
+from ._lib import SSW_BOX_F32, SSW_BOX_F64, SSW_BOX_I32, SSW_F16, SSW_F32, check, lib, ptr
 from .synth import kind_id
 
 _DT = {np.dtype(np.float32): SSW_F32, np.dtype(np.float16): SSW_F16}
@@ -57,7 +57,9 @@ class PatchDatabase:
 
     # ---- construction -------------------------------------------------------------------
     @classmethod
-    def from_arrays(cls, vectors, dbidx_per_row, *, store="f16", device=0, global_row_base=0):
+    def from_arrays(cls, vectors, dbidx_per_row, *, store="f16", device=0, global_row_base=0, exact=False):
+        """``exact=True`` (fp16 storage of float32 vectors only): keep the float32 rows in HBM as well, so that
+        scans return the float32 top-k the reference computes (certified re-ranking, see ssw_db_attach_exact)."""
         vectors = np.ascontiguousarray(vectors)
         if vectors.dtype not in _DT:
             vectors = vectors.astype(np.float32)
@@ -66,7 +68,22 @@ class PatchDatabase:
         h = C.c_void_p()
         check(lib.ssw_db_create(C.byref(h), device, ptr(vectors), _DT[vectors.dtype], _dtype_id(store),
                                 vectors.shape[0], vectors.shape[1], ptr(dbidx), global_row_base))
-        return cls(h)
+        db = cls(h)
+        if exact:
+            assert vectors.dtype == np.float32 and _dtype_id(store) == SSW_F16, "exact mode: float32 vectors, fp16 storage"
+            db.attach_exact(vectors)
+        return db
+
+    def attach_exact(self, vectors_f32):
+        v = np.ascontiguousarray(vectors_f32, dtype=np.float32)
+        assert v.shape == (self.n_rows, self.dim)
+        check(lib.ssw_db_attach_exact(self._h, ptr(v)))
+
+    def exact_info(self):
+        """dict(attached, rho, vmax, queries, rescans) — see ssw_db_exact_info."""
+        a, rho, vmax, nq, nr = C.c_int(), C.c_double(), C.c_double(), C.c_int64(), C.c_int64()
+        check(lib.ssw_db_exact_info(self._h, C.byref(a), C.byref(rho), C.byref(vmax), C.byref(nq), C.byref(nr)))
+        return dict(attached=bool(a.value), rho=rho.value, vmax=vmax.value, queries=nq.value, rescans=nr.value)
 
     @classmethod
     def synthetic(cls, dbidx_per_row, dim, *, seed, kind="tri", store="f16", device=0, global_row_base=0):
@@ -117,10 +134,23 @@ class PatchDatabase:
         return dict(dbidx=out_dbidx, score=out_score, row=out_row, count=out_count)
 
     def set_boxes(self, x1, y1, x2, y2, zoom_level):
-        """vector_meta's box columns per ORIGINAL row, for the device stage 2 ('avg_score')."""
-        cols = [np.ascontiguousarray(np.asarray(c).astype(np.int32).reshape(-1)) for c in (x1, y1, x2, y2, zoom_level)]
-        assert all(c.shape[0] == self.n_rows for c in cols)
-        check(lib.ssw_db_set_boxes(self._h, *[ptr(c) for c in cols]))
+        """vector_meta's box columns per ORIGINAL row, for the device stage 2 ('avg_score').  The IoU of the
+        self-join is computed in the columns' own type like the reference's (box_utils.py:336-350): float32
+        columns (what the tiling pipeline writes) stay float32, float64 stay float64, integer columns go as
+        int32 (exact integer intersection / union, float32 quotient)."""
+        boxes = [np.asarray(c).reshape(-1) for c in (x1, y1, x2, y2)]
+        common = np.result_type(*boxes)                 # np.stack of the four columns, as df2tensor does
+        if np.issubdtype(common, np.integer):
+            kind, dt = SSW_BOX_I32, np.int32
+            assert all(np.abs(c).max(initial=0) < 2 ** 31 for c in boxes), "integer box coordinates must fit int32"
+        elif common == np.float32:
+            kind, dt = SSW_BOX_F32, np.float32
+        else:
+            kind, dt = SSW_BOX_F64, np.float64
+        cols = [np.ascontiguousarray(c.astype(dt)) for c in boxes]
+        zoom = np.ascontiguousarray(np.asarray(zoom_level).astype(np.int32).reshape(-1))
+        assert all(c.shape[0] == self.n_rows for c in cols) and zoom.shape[0] == self.n_rows
+        check(lib.ssw_db_set_boxes_typed(self._h, kind, *[ptr(c) for c in cols], ptr(zoom)))
         self.has_boxes = True
 
     _AGG = {"plain_score": 0, "avg_score": 1}

@@ -85,11 +85,18 @@ def _activation_frames(x1, y1, x2, y2, dbidx, score):
 class _GpuIndexMixin:
     """Device copy + host CSR shared by the multiscale and coarse classes."""
 
-    def _init_device(self, device, store, db=None):
+    def _init_device(self, device, store, db=None, exact="auto"):
+        """``store``: HBM type of the scanned copy ("f16" halves the bytes of every scan, "f32" is the
+        reference's own type).  ``exact`` (fp16 storage of float32 vectors): "auto" keeps the float32 rows in
+        HBM as well whenever fp16 would change a value, so every result is the reference's float32 result
+        (certified re-ranking, PatchDatabase.from_arrays); False scans and rescoring on the fp16 values alone
+        (scores within ||v - fp16(v)||.||q|| <= 2^-11 ||v||.||q|| of the reference's, ids may differ between
+        images closer than that — the "looser bound" of fp16 storage)."""
         dbidx = self.vector_meta["dbidx"].to_numpy()
         self._dbidx_of_row = dbidx.astype(np.int64)
         self.device = device
         self.store = store
+        self._exact_opt = exact
         self._batcher = None
         self._all_ids = np.sort(as_id_array(self.all_indices))     # eligible image ids, for the top-k clamp
         if db is not None:
@@ -97,13 +104,15 @@ class _GpuIndexMixin:
             assert db.n_rows == len(dbidx)
             self.db, self._store_exact = db, True
         else:
-            self.db = PatchDatabase.from_arrays(self.vectors, dbidx.astype(np.int32), store=store, device=device)
-            # stage-1 scores equal what a host rescoring of self.vectors would give (up to summation order)
-            # exactly when the HBM copy holds the same values: fp32 storage, or fp16-representable data
             v = self.vectors
-            self._store_exact = store in ("f32", "fp32", "float32") or v.dtype == np.float16 or bool(
+            f32_store = store in ("f32", "fp32", "float32")
+            # the HBM copy holds the reference's values exactly: fp32 storage, or fp16-representable data
+            same = f32_store or v.dtype == np.float16 or bool(
                 (v[: min(len(v), 4096)].astype(np.float16).astype(np.float32) == v[: min(len(v), 4096)]).all()
                 and (v.astype(np.float16).astype(np.float32) == v).all())
+            keep_f32 = (not same) and exact in ("auto", True, "device")
+            self.db = PatchDatabase.from_arrays(v, dbidx.astype(np.int32), store=store, device=device, exact=keep_f32)
+            self._store_exact = same or keep_f32
         # host CSR over ORIGINAL rows: rows of image i are _rows_sorted[_starts[i]:_starts[i+1]], ascending
         order = np.argsort(self._dbidx_of_row, kind="stable")
         sorted_ids = self._dbidx_of_row[order]
@@ -171,7 +180,8 @@ class B200MultiscaleIndex(_GpuIndexMixin, AccessMethod):
     the GPU.  Constructor and attributes follow MultiscaleIndex (multiscale_index.py:203-231)."""
 
     def __init__(self, *, embedding, vectors: np.ndarray, vector_meta: pd.DataFrame, vec_index=None,
-                 min_zoom_level=1, path: str = None, excluded=None, device: int = 0, store: str = "f16", _db=None):
+                 min_zoom_level=1, path: str = None, excluded=None, device: int = 0, store: str = "f16",
+                 exact="auto", _db=None):
         self.embedding = embedding
         self.path = path
         self.excluded = BitMap([]) if excluded is None else BitMap(as_id_array(excluded))
@@ -183,11 +193,13 @@ class B200MultiscaleIndex(_GpuIndexMixin, AccessMethod):
         self.vector_meta = vector_meta
         self.vec_index = vec_index          # accepted for interface parity; the exact GPU scan supersedes it
         self.all_indices = FrozenBitMap(self.vector_meta["dbidx"].to_numpy()) - self.excluded
-        self._init_device(device, store, db=_db)
+        self._init_device(device, store, db=_db, exact=exact)
         self._meta_cols = {c: self.vector_meta[c].to_numpy() for c in ("x1", "y1", "x2", "y2", "zoom_level")
                            if c in self.vector_meta.columns}
+        # boxes travel in their own dtype (float32 from the tiling pipeline, multiscale_tools.py:111): K7 repeats
+        # the reference's IoU arithmetic in that type
         self._boxes_on_device = len(self._meta_cols) == 5 and all(
-            np.issubdtype(v.dtype, np.integer) for v in self._meta_cols.values())
+            np.issubdtype(v.dtype, np.number) for v in self._meta_cols.values())
         if self._boxes_on_device:
             self.db.set_boxes(*[self._meta_cols[c] for c in ("x1", "y1", "x2", "y2", "zoom_level")])
 
@@ -200,7 +212,7 @@ class B200MultiscaleIndex(_GpuIndexMixin, AccessMethod):
                                    device=db.device, store="f16" if db.dtype == np.float16 else "f32", _db=db)
 
     @staticmethod
-    def from_path(index_path: str, *, use_vec_index=False, device=0, store="f16", exclude=None, **options):
+    def from_path(index_path: str, *, use_vec_index=False, device=0, store="f16", exact="auto", exclude=None, **options):
         """multiscale_index.py:234-269; reads ``info.json`` and ``vectors.sorted.cached`` directly
         (no Ray).  The embedding model is resolved lazily by the caller through ``embedding=``."""
         info = json.load(open(f"{index_path}/info.json"))
@@ -208,7 +220,8 @@ class B200MultiscaleIndex(_GpuIndexMixin, AccessMethod):
         meta = df[["dbidx", "zoom_level", "x1", "y1", "x2", "y2"]]
         vectors = _column_to_matrix(df["vectors"])
         return B200MultiscaleIndex(embedding=options.get("embedding"), vectors=vectors, vector_meta=meta,
-                                   path=index_path, excluded=info.get("excluded", None), device=device, store=store)
+                                   path=index_path, excluded=info.get("excluded", None), device=device, store=store,
+                                   exact=exact)
 
     def __len__(self):
         return len(self.all_indices)
@@ -255,7 +268,11 @@ class B200MultiscaleIndex(_GpuIndexMixin, AccessMethod):
                                       self._meta_cols["y2"][r], ids[order], np.asarray(scores)[order])
             return {"dbidxs": ids[order].astype("int"), "activations": acts}
 
-        if agg_method == "plain_score" and vector2 is None and kwargs.get("device_rescore", self._store_exact):
+        # Both stages run on the device.  With float32 vectors in fp16 storage the database keeps the float32 rows
+        # too (exact mode): stage 1 is the certified float32 top-k and stage 2 reads the float32 rows, so scores
+        # are the reference's.  ``device_rescore=False`` forces the host mirror of stage 2 (cross-check).
+        on_device = kwargs.get("device_rescore", True)
+        if agg_method == "plain_score" and vector2 is None and on_device:
             # 'plain_score' rescoring recomputes exactly what stage 1 already returned — per image the max
             # patch score and the first row attaining it (:117-118) — so the shortlist only needs the
             # reference's final ordering: ascending dbidx, then a stable sort by score (:388-399).
@@ -263,11 +280,12 @@ class B200MultiscaleIndex(_GpuIndexMixin, AccessMethod):
             return result(np.argsort(-sc.astype(np.float64), kind="stable")[:topk], cand["row"][by_id], sc)
         aug_larger = kwargs.get("aug_larger", "all")
         if (agg_method in ("plain_score", "avg_score") and aug_larger in ("all", "greater", "adjacent")
-                and kwargs.get("device_rescore", self._store_exact and (agg_method == "plain_score" or self._boxes_on_device))):
+                and on_device and (agg_method == "plain_score" or self._boxes_on_device)):
             # stage 2 on the device (K7): patch scores, IoU join and per-level averaging for the <= shortlist images
             sc, rows = self.db.rescore(qvec, ids, query2=vector2, agg_method=agg_method, aug_larger=aug_larger)
             rows = self._map_rows(rows)
-            return result(np.argsort(-sc, kind="stable")[:topk], rows, sc)   # stable by score over ascending dbidx (:388-399)
+            sc = sc.astype(np.float32)                                       # the reference's score column is float32
+            return result(np.argsort(-sc.astype(np.float64), kind="stable")[:topk], rows, sc)   # stable by score over ascending dbidx (:388-399)
         assert self.vectors is not None, "host rescoring needs the host copy of the vectors (index built with from_database)"
         groups = [self._rows_of(d) for d in ids]                      # CSR ranges, not an O(N) isin
         rows = np.concatenate(groups)
@@ -300,7 +318,7 @@ class B200MultiscaleIndex(_GpuIndexMixin, AccessMethod):
         assert self.vectors is not None, "a copying subset needs the host vectors; use share_device=True"
         return B200MultiscaleIndex(embedding=self.embedding, vectors=self.vectors[mask],
                                    vector_meta=self.vector_meta[mask].reset_index(drop=True),
-                                   device=self.device, store=self.store)
+                                   device=self.device, store=self.store, exact=self._exact_opt)
 
 
 class _SharedSubset(B200MultiscaleIndex):
@@ -319,7 +337,7 @@ class _SharedSubset(B200MultiscaleIndex):
         self._all_ids = np.sort(as_id_array(self.all_indices))
         self._complement = np.setdiff1d(parent._img_ids, keep).astype(np.int64)   # masked out of every scan
         self.db, self.device, self.store = parent.db, parent.device, parent.store
-        self._batcher, self._store_exact = None, parent._store_exact
+        self._batcher, self._store_exact, self._exact_opt = None, parent._store_exact, parent._exact_opt
         order = np.argsort(self._dbidx_of_row, kind="stable")
         self._img_ids, self._starts = np.unique(self._dbidx_of_row[order], return_index=True)
         self._starts = np.append(self._starts, len(order))

@@ -18,20 +18,34 @@ _BOX = ["x1", "y1", "x2", "y2"]
 
 
 def _iou_matrix(b):
-    """Pairwise IoU of boxes [n,4] (x1,y1,x2,y2), float64 — torchvision's _box_inter_union."""
+    """Pairwise IoU of boxes [n,4] (x1,y1,x2,y2) as box_iou computes it (box_utils.py:336-350, torchvision's
+    _box_inter_union followed by a true division) IN THE BOXES' OWN DTYPE: float32 boxes (what the tiling
+    pipeline writes, multiscale_tools.py:111) give float32 areas / intersections / unions / quotients, integer
+    boxes exact integers and a float32 quotient, float64 boxes float64 throughout."""
+    integer = np.issubdtype(b.dtype, np.integer)
+    if integer:
+        b = b.astype(np.int64)
+    elif b.dtype != np.float32:
+        b = b.astype(np.float64)
     area = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
     w = np.minimum(b[:, None, 2], b[None, :, 2]) - np.maximum(b[:, None, 0], b[None, :, 0])
     h = np.minimum(b[:, None, 3], b[None, :, 3]) - np.maximum(b[:, None, 1], b[None, :, 1])
     inter = np.clip(w, 0, None) * np.clip(h, 0, None)
-    return inter / (area[:, None] + area[None, :] - inter)
+    union = (area[:, None] + area[None, :]) - inter
+    with np.errstate(invalid="ignore", divide="ignore"):
+        if integer:
+            return inter.astype(np.float32) / union.astype(np.float32)
+        return inter / union
 
 
 def aggregate_patch_scores(scores, boxes, zoom, aug_larger="all"):
     """'avg_score' with aug_weight='level_max' (multiscale_index.py:119-147): for every patch, the
     mean over zoom levels of the score of the best-overlapping patch of that level.
-    Returns float64 [n]; NaN where a patch overlaps nothing under the aug_larger filter."""
+    Returns float32 [n] (pandas' groupby mean accumulates in float64 and hands back the score column's
+    float32); NaN where a patch overlaps nothing under the aug_larger filter."""
     n = scores.shape[0]
-    iou = _iou_matrix(boxes.astype(np.float64))
+    scores = np.asarray(scores, dtype=np.float32)
+    iou = _iou_matrix(boxes)
     allowed = iou > 0
     if aug_larger == "greater":
         allowed &= zoom[None, :] >= zoom[:, None]
@@ -39,18 +53,23 @@ def aggregate_patch_scores(scores, boxes, zoom, aug_larger="all"):
         allowed &= zoom[None, :] == zoom[:, None]
     elif aug_larger != "all":
         raise AssertionError(f"unknown aug_larger {aug_larger!r}")
-    masked = np.where(allowed, iou, -1.0)
-    total = np.zeros(n)
-    levels = np.zeros(n)
+    masked = np.where(allowed, iou, iou.dtype.type(-1.0))
+    # pandas' group_mean on the float32 score column: Kahan-compensated float32 sum over the levels in
+    # ascending order, float32 division by the count (vectorised over the left patches)
+    f = np.float32
+    sumx, comp, levels = np.zeros(n, f), np.zeros(n, f), np.zeros(n, f)
     for z in np.unique(zoom):
         cols = np.flatnonzero(zoom == z)
         sub = masked[:, cols]
         best = cols[np.argmax(sub, axis=1)]            # first maximum = lowest right position (idxmax)
         has = sub.max(axis=1) > 0
-        total += np.where(has, scores[best], 0.0)
+        y = scores[best] - comp
+        t = sumx + y
+        comp = np.where(has, (t - sumx) - y, comp)
+        sumx = np.where(has, t, sumx)
         levels += has
     with np.errstate(invalid="ignore", divide="ignore"):
-        return np.where(levels > 0, total / levels, np.nan)
+        return np.where(levels > 0, sumx / levels, f(np.nan)).astype(f)
 
 
 def best_patch(scores, boxes=None, zoom=None, agg_method="plain_score", aug_larger="all"):
@@ -60,7 +79,7 @@ def best_patch(scores, boxes=None, zoom=None, agg_method="plain_score", aug_larg
         return int(np.flatnonzero(scores == m)[0]), m
     if agg_method != "avg_score":
         raise NotImplementedError(f"agg_method {agg_method!r}")
-    agg = aggregate_patch_scores(np.asarray(scores, dtype=np.float64), boxes, zoom, aug_larger)
+    agg = aggregate_patch_scores(scores, boxes, zoom, aug_larger)
     m = np.nanmax(agg)
     return int(np.flatnonzero(agg == m)[0]), m
 

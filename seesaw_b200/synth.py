@@ -97,3 +97,61 @@ def synth_vector_meta(counts, seed: int, dbidx_start=0, dbidx_stride=1):
     return pd.DataFrame({"dbidx": dbidx.astype(np.int64), "zoom_level": zoom,
                          "x1": x1.astype(np.int64), "y1": y1.astype(np.int64),
                          "x2": (x1 + side).astype(np.int64), "y2": (y1 + side).astype(np.int64)})
+
+
+def pyramid_tiling(width: int, height: int, tile_size: int = 224, factor: float = 0.5, min_tile_size: int = 60):
+    """Patch boxes of one image as the reference's tiling pipeline lays them out (multiscale_tools.py:16-117:
+    ``pyramid`` -> ``strided_tiling`` per level -> pixel / scale_factor): a geometric pyramid of rescaled
+    copies from the smallest scale (whole image ~ one tile) to the largest, each cut into tile_size squares on
+    a half-tile stride.  Pure arithmetic on the image SIZE (no pixels); returns (x1, y1, x2, y2 as float32 in
+    original-image pixels — the dtype the pipeline writes, :111 — and zoom_level as int16), rows in the
+    pipeline's order.  tests/test_oracle.py checks it against the reference's generate_multiscale_tiling."""
+    import math
+    f = 1.0 / factor
+    size = min(width, height)
+    start_size = max(size, tile_size)
+    start_scale, end_scale = start_size / size, tile_size / size
+    ntimes = math.ceil(math.log(start_scale / end_scale) / math.log(f))
+    start_size = math.ceil(math.exp(ntimes * math.log(f) + math.log(tile_size)))
+    start_scale = start_size / size
+    scales = np.geomspace(start=start_scale, stop=end_scale, num=ntimes + 1, endpoint=True).tolist()
+    levels = sorted(range(len(scales)), key=lambda z: scales[z])          # ascending scale, zoom_level = original position
+    cols = {"x1": [], "y1": [], "x2": [], "y2": [], "zoom_level": []}
+    for pos, z in enumerate(levels):
+        sf = scales[z]
+        if not (224 / sf >= min_tile_size or pos == 0):                    # :99 keep the coarsest level at least
+            continue
+        w, h = max(math.floor(width * sf), tile_size), max(math.floor(height * sf), tile_size)
+        half = tile_size // 2
+        for sx in (0, half):
+            for sy in (0, half):
+                ii, jj = np.meshgrid(np.arange((h - sy) // tile_size), np.arange((w - sx) // tile_size), indexing="ij")
+                x1 = jj.reshape(-1) * tile_size + sx
+                y1 = ii.reshape(-1) * tile_size + sy
+                for name, v in (("x1", x1), ("y1", y1), ("x2", x1 + tile_size), ("y2", y1 + tile_size)):
+                    cols[name].append((v / sf).astype(np.float32))
+                cols["zoom_level"].append(np.full(x1.shape[0], z, np.int16))
+    return {k: np.concatenate(v) for k, v in cols.items()}
+
+
+def synth_pyramid_meta(n_images: int, seed: int, dbidx_start=0, dbidx_stride=1, min_tile_size: int = 60,
+                       sizes=((640, 480), (500, 375), (480, 640), (1024, 768), (333, 500), (800, 600), (224, 224), (300, 260))):
+    """A ``vector_meta`` frame with the float32 boxes of :func:`pyramid_tiling` for ``n_images`` images whose
+    sizes are drawn from ``sizes`` (typical photo shapes) — the box dtype and geometry of a real multiscale index."""
+    import pandas as pd
+    rng = np.random.default_rng(seed)
+    pick = rng.integers(0, len(sizes), size=n_images)
+    tilings = [pyramid_tiling(w, h, min_tile_size=min_tile_size) for (w, h) in sizes]
+    counts = np.array([len(tilings[p]["x1"]) for p in pick], dtype=np.int64)
+    ids = dbidx_start + dbidx_stride * np.arange(n_images, dtype=np.int64)
+    out = {"dbidx": np.repeat(ids, counts)}
+    for c in ("zoom_level", "x1", "y1", "x2", "y2"):
+        out[c] = np.concatenate([tilings[p][c] for p in pick])
+    return pd.DataFrame(out), counts
+
+
+def unit_rows(n_rows: int, dim: int, seed: int):
+    """L2-normalised float32 Gaussian rows — CLIP-like embeddings that are NOT fp16-representable
+    (models/model.py:14-17 normalises; multiscale_tools.py:200 stores float32)."""
+    v = np.random.default_rng(seed).standard_normal((n_rows, dim)).astype(np.float32)
+    return v / np.linalg.norm(v, axis=1, keepdims=True).astype(np.float32)

@@ -15,7 +15,7 @@ class FakeDB:
         self.dtype, self.device, self.closed, self.boxes = np.float16, 0, False, None
 
     @classmethod
-    def from_arrays(cls, vectors, dbidx_per_row, *, store="f16", device=0, global_row_base=0):
+    def from_arrays(cls, vectors, dbidx_per_row, *, store="f16", device=0, global_row_base=0, exact=False):
         return cls(vectors, dbidx_per_row)
 
     def scan_topk(self, queries, k, exclude=None):

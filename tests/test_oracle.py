@@ -157,3 +157,78 @@ def test_label_propagation_matches_reference_golden(golden, name):
     assert (got == golden[f"{name}/values"]).all()
     assert (got[ids[-1]] == 1.0) and it >= 1
     assert conv == (name != "lp_noreg")          # the fixture holds one run that hits max_iter
+
+
+@pytest.mark.parametrize("name", list(cases.CASES_F32))
+def test_float32_index_matches_reference_golden(golden, name):
+    """The data a real index holds — float32 unit vectors that are not fp16-representable and the tiling
+    pipeline's float32 boxes: stage 1 and every stage-2 variant (float32 IoU self-join, per-level idxmax,
+    float64-accumulated mean handed back as float32) equal the unmodified reference's outputs bit for bit."""
+    c = cases.CASES_F32[name]
+    vecs, meta, qs = cases.msf_inputs(c)
+    assert vecs.dtype == np.float32 and not (vecs.astype(np.float16).astype(np.float32) == vecs).all()
+    assert all(meta[col].dtype == np.float32 for col in ("x1", "y1", "x2", "y2")) and meta.zoom_level.dtype == np.int16
+    xs = cases.exclude_sets(meta, c["seed"] + 7)
+    for xname in ("none", "some"):
+        for qi in range(2):
+            r = orc.query_prelim(vecs, meta.dbidx.values, qs[qi], 50, exclude=xs[xname])
+            key = f"{name}/prelim/{xname}/{qi}"
+            assert (r["dbidx"] == golden[key + "/dbidx"]).all() and (r["max_score"] == golden[key + "/score"]).all(), key
+    for agg, aug, topk, use_v2 in cases.MSF_QUERY_VARIANTS:
+        key = f"{name}/query/{agg}/{aug}/{topk}/{int(use_v2)}"
+        r = orc.multiscale_query(vecs, meta, qs[2], topk, 40, exclude=xs["some"], vector2=qs[3] * 0.25 if use_v2 else None,
+                                 agg_method=agg, aug_larger=aug)
+        assert (r["dbidxs"] == golden[key + "/dbidxs"]).all(), key
+        sc = np.array([a.score.values[0] for a in r["activations"]], np.float64)
+        assert (sc == golden[key + "/act_score"]).all(), key            # same arithmetic, same dtype: bit-equal
+        bx = np.array([a[["x1", "y1", "x2", "y2"]].values[0] for a in r["activations"]], np.float32)
+        assert (bx == golden[key + "/act_box"]).all(), key
+
+
+def test_pyramid_tiling_equals_reference_pipeline(reference):
+    """seesaw_b200.synth.pyramid_tiling (the float32 box generator of the fixtures) against the reference's
+    generate_multiscale_tiling (multiscale_tools.py:96-117) on blank images of the same sizes."""
+    import importlib
+    import PIL.Image
+    from seesaw_b200 import synth
+    mt = importlib.import_module("seesaw.indices.multiscale.multiscale_tools")
+    for (w, h) in [(640, 480), (333, 500), (1280, 960), (224, 224), (150, 100)]:
+        for mts in (60, 224):
+            df = mt.generate_multiscale_tiling(PIL.Image.new("RGB", (w, h)), tile_size=224, factor=.5, min_tile_size=mts)
+            t = synth.pyramid_tiling(w, h, min_tile_size=mts)
+            assert len(df) == len(t["x1"])
+            for col in ("x1", "y1", "x2", "y2", "zoom_level"):
+                assert df[col].dtype == t[col].dtype and (df[col].values == t[col]).all(), (w, h, mts, col)
+
+
+def test_integer_box_iou_is_float32_quotient(reference):
+    """Integer box columns: torchvision keeps intersection / union as int64 and ``inter / union`` is torch's
+    float32 true division (box_utils.py:341-345) — the oracle's and the host mirror's IoU equal it bit for bit."""
+    import importlib
+    from seesaw_b200 import rescore
+    bu = importlib.import_module("seesaw.box_utils")
+    rng = np.random.default_rng(3)
+    x1, y1 = rng.integers(0, 900, 40), rng.integers(0, 900, 40)
+    df = pd.DataFrame({"x1": x1, "y1": y1, "x2": x1 + rng.integers(1, 700, 40), "y2": y1 + rng.integers(1, 700, 40)})
+    want = bu.box_iou(df, df)
+    assert want.dtype == np.float32
+    b = df[["x1", "y1", "x2", "y2"]].to_numpy()
+    assert (orc._pairwise_iou(b) == want).all() and (rescore._iou_matrix(b) == want).all()
+    f = df.astype(np.float32) / np.float32(1.7)
+    want = bu.box_iou(f, f)
+    b = f[["x1", "y1", "x2", "y2"]].to_numpy()
+    assert want.dtype == np.float32 and (orc._pairwise_iou(b) == want).all() and (rescore._iou_matrix(b) == want).all()
+
+
+def test_pandas_float32_group_mean_is_kahan_float32():
+    """The arithmetic score_frame2's ``groupby('iloc_left').score_right.mean()`` performs on the float32 score
+    column (multiscale_index.py:142), pinned against pandas itself: float32 Kahan sum in row order / float32
+    count.  (A float64 accumulation rounded to float32 differs on ~5% of random groups.)"""
+    rng = np.random.default_rng(0)
+    sizes = rng.integers(1, 6, size=3000)
+    g = np.repeat(np.arange(len(sizes)), sizes)
+    s = (rng.standard_normal(len(g)) * 0.1).astype(np.float32)
+    want = pd.DataFrame({"g": g, "s": s}).groupby("g").s.mean().values
+    starts = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+    got = np.array([orc._pandas_group_mean_f32(s[a:a + k]) for a, k in zip(starts, sizes)], np.float32)
+    assert want.dtype == np.float32 and (got == want).all()
