@@ -67,6 +67,10 @@ int ssw_db_create(ssw_db** out, int device, const void* vectors, int dtype_in, i
 int ssw_db_create_synthetic(ssw_db** out, int device, int dtype_store, int64_t n_rows, int dim,
                             const int32_t* dbidx_per_row, int64_t global_row_base,
                             uint64_t seed, int kind);
+/* Same as ssw_db_create with the vectors already in the memory of `device` (e.g. embeddings an encoder just
+ * produced there): [n_rows, dim] of dtype_in, rows grouped by ascending dbidx; copied / converted device to device. */
+int ssw_db_create_device(ssw_db** out, int device, const void* d_vectors, int dtype_in, int dtype_store,
+                         int64_t n_rows, int dim, const int32_t* dbidx_per_row, int64_t global_row_base);
 int ssw_db_destroy(ssw_db* db);
 int ssw_db_info(const ssw_db* db, int64_t* n_rows, int64_t* n_images, int* dim, int* dtype_store,
                 int* device);
@@ -241,6 +245,11 @@ int ssw_lp_fit(ssw_lp* lp, const int64_t* label_ids, const double* label_values,
  * returns the summed kernel time and launch count since the last read, then resets them. */
 int ssw_profile_enable(ssw_db* db, int on);
 int ssw_profile_read(ssw_db* db, double* scan_kernel_ms, int64_t* scan_kernel_launches);
+/* Work counters of the fused top-k epilogue, summed over all CTAs and queries since the last call: images that
+ * passed the cheap threshold vote and were offered to a list, and list updates (appends + replacements) — the
+ * data-dependent part of the scan (pooled thresholds).  enable != 0 switches counting on (the call
+ * returns the counts so far and resets them), 0 off.  Synchronises the device. */
+int ssw_scan_stats(ssw_db* db, int enable, int64_t* list_updates, int64_t* images_offered);
 /* number of kernels this library has launched since load (all handles) */
 int64_t ssw_kernel_launch_count(void);
 

@@ -21,7 +21,17 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("SEESAW_REFERENCE_ROOT", "/root/reference")
+def _reference_root():
+    """/root/reference in the build container; on the GPU box the verbatim copy oracle/build_ref.py made (oracle/_ref)."""
+    env = os.environ.get("SEESAW_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/seesaw"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REFERENCE_ROOT = _reference_root()
 
 
 class BitMap(set):

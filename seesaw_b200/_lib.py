@@ -42,6 +42,7 @@ SIGNATURES = {
     "ssw_version": (C.c_int, []),
     "ssw_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "ssw_db_create": (C.c_int, [C.POINTER(_p), C.c_int, _p, C.c_int, C.c_int, C.c_int64, C.c_int, _p, C.c_int64]),
+    "ssw_db_create_device": (C.c_int, [C.POINTER(_p), C.c_int, _p, C.c_int, C.c_int, C.c_int64, C.c_int, _p, C.c_int64]),
     "ssw_db_create_synthetic": (C.c_int, [C.POINTER(_p), C.c_int, C.c_int, C.c_int64, C.c_int, _p, C.c_int64,
                                           C.c_uint64, C.c_int]),
     "ssw_db_destroy": (C.c_int, [_p]),
@@ -77,6 +78,7 @@ SIGNATURES = {
     "ssw_lp_create": (C.c_int, [C.POINTER(_p), C.c_int, C.c_int64, _p, _p, _p, _p, C.c_double]),
     "ssw_lp_destroy": (C.c_int, [_p]),
     "ssw_lp_fit": (C.c_int, [_p, _p, _p, C.c_int64, _p, _p, C.c_int, C.c_double, _p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "ssw_scan_stats": (C.c_int, [_p, C.c_int, _i64p, _i64p]),
     "ssw_kernel_launch_count": (C.c_int64, []),
     "ssw_profile_enable": (C.c_int, [_p, C.c_int]),
     "ssw_profile_read": (C.c_int, [_p, C.POINTER(C.c_double), _i64p]),

@@ -98,11 +98,13 @@ static int ensure_lists(ssw_db* db, int nq, int lists, int k) {
   if (nq > db->gthr_capacity) {
     if (db->d_gthr) cudaFree(db->d_gthr);
     db->gthr_capacity = 0;
-    // one allocation: nq thresholds (8 B) then nq x grid published bests (4 B), zeroed together per call
+    // one allocation: nq thresholds (8 B), nq x grid published bests (4 B) — zeroed together per call of the
+    // streaming scan — then nq candidate counters of the batched scan (zeroed by its preparation kernel)
     uint8_t* p = nullptr;
-    SSW_CUDA(cudaMalloc((void**)&p, (size_t)nq * 8 + (size_t)nq * db->scan_grid * 4));
+    SSW_CUDA(cudaMalloc((void**)&p, (size_t)nq * 8 + (size_t)nq * db->scan_grid * 4 + (size_t)nq * 4));
     db->d_gthr = reinterpret_cast<uint64_t*>(p);
     db->d_pub1 = reinterpret_cast<uint32_t*>(p + (size_t)nq * 8);
+    db->d_cand_cnt = reinterpret_cast<int32_t*>(p + (size_t)nq * 8 + (size_t)nq * db->scan_grid * 4);
     db->gthr_capacity = nq;
   }
   return SSW_OK;
@@ -296,6 +298,7 @@ int ssw_db_destroy(ssw_db* db) {
   cudaFree(db->d_zoom);
   cudaFree(db->d_exact);
   cudaFree(db->d_xchg_timed_out);
+  cudaFree(db->d_scan_stats);
   cudaFree(db->d_tc_ws);
   cudaFree(db->d_list_keys);
   cudaFree(db->d_list_dbidx);
@@ -333,6 +336,40 @@ int ssw_db_create(ssw_db** out, int device, const void* vectors, int dtype_in, i
     return fail(e == cudaErrorMemoryAllocation ? SSW_ERR_OOM : SSW_ERR_CUDA);
   }
   if ((rc = upload_rows(db, vectors, dtype_in, db->d_vecs, dtype_store, perm))) return fail(rc);
+  *out = db;
+  return SSW_OK;
+}
+
+int ssw_db_create_device(ssw_db** out, int device, const void* d_vectors, int dtype_in, int dtype_store, int64_t n_rows,
+                         int dim, const int32_t* dbidx_per_row, int64_t global_row_base) {
+  SSW_REQUIRE(d_vectors != nullptr || n_rows == 0, "d_vectors is null");
+  SSW_REQUIRE(dbidx_per_row != nullptr || n_rows == 0, "dbidx_per_row is null");
+  SSW_REQUIRE(dtype_in == SSW_F16 || dtype_in == SSW_F32, "dtype_in must be SSW_F32 or SSW_F16");
+  ssw_db* db = nullptr;
+  int rc = db_new(&db, device, dtype_store, n_rows, dim, global_row_base);
+  if (rc) return rc;
+  auto fail = [&](int code) {
+    ssw_db_destroy(db);
+    return code;
+  };
+  for (int64_t i = 1; i < n_rows; ++i)
+    if (dbidx_per_row[i] < dbidx_per_row[i - 1]) {
+      set_error("device-resident vectors must be grouped by ascending dbidx");
+      return fail(SSW_ERR_INVALID);
+    }
+  if ((rc = build_layout(db, dbidx_per_row, nullptr))) return fail(rc);
+  const size_t es = dtype_store == SSW_F16 ? 2 : 4;
+  cudaError_t e = cudaMalloc(&db->d_vecs, std::max<size_t>((size_t)n_rows * dim * es, 16));
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMalloc(vectors): ") + cudaGetErrorString(e));
+    return fail(e == cudaErrorMemoryAllocation ? SSW_ERR_OOM : SSW_ERR_CUDA);
+  }
+  if ((rc = launch_convert_rows(d_vectors, dtype_in, db->d_vecs, dtype_store, n_rows * dim, db->stream))) return fail(rc);
+  e = cudaStreamSynchronize(db->stream);
+  if (e != cudaSuccess) {
+    set_error(std::string("device copy: ") + cudaGetErrorString(e));
+    return fail(SSW_ERR_CUDA);
+  }
   *out = db;
   return SSW_OK;
 }
@@ -411,6 +448,27 @@ int ssw_profile_read(ssw_db* db, double* scan_kernel_ms, int64_t* scan_kernel_la
   return SSW_OK;
 }
 
+int ssw_scan_stats(ssw_db* db, int enable, int64_t* list_updates, int64_t* images_offered) {
+  SSW_REQUIRE(db != nullptr, "db is null");
+  SSW_CUDA(cudaSetDevice(db->device));
+  unsigned long long v[2] = {0, 0};
+  if (db->d_scan_stats) {
+    SSW_CUDA(cudaDeviceSynchronize());
+    SSW_CUDA(cudaMemcpy(v, db->d_scan_stats, 16, cudaMemcpyDeviceToHost));
+    SSW_CUDA(cudaMemset(db->d_scan_stats, 0, 16));
+  }
+  if (enable && !db->d_scan_stats) {
+    SSW_CUDA(cudaMalloc((void**)&db->d_scan_stats, 16));
+    SSW_CUDA(cudaMemset(db->d_scan_stats, 0, 16));
+  } else if (!enable && db->d_scan_stats) {
+    cudaFree(db->d_scan_stats);
+    db->d_scan_stats = nullptr;
+  }
+  if (list_updates) *list_updates = (int64_t)v[0];
+  if (images_offered) *images_offered = (int64_t)v[1];
+  return SSW_OK;
+}
+
 int ssw_set_scan_mode(ssw_db* db, int mode) {
   SSW_REQUIRE(db != nullptr, "db is null");
   SSW_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0, 1 or 2");
@@ -458,7 +516,7 @@ static int scan_topk_impl(ssw_db* db, const float* d_queries, int nq, int k, con
       rc = launch_scan_tc(db, d_queries + (size_t)q0 * db->dim, nb, k,
                           d_exclude_bits ? d_exclude_bits + (size_t)q0 * db->excl_words : nullptr,
                           db->d_list_keys + (size_t)q0 * lists * k, db->d_list_dbidx + (size_t)q0 * lists * k,
-                          db->d_gthr + q0, db->d_tc_ws, st);
+                          db->d_cand_cnt + q0, db->d_gthr + q0, db->d_tc_ws, st);
       if (rc) return rc;
     }
   } else {
@@ -480,10 +538,13 @@ static int scan_topk_impl(ssw_db* db, const float* d_queries, int nq, int k, con
     }
     return launch_exchange_merge(db->d_list_keys, db->d_list_dbidx, lists, k, (int64_t)lists * k, nq, k, db->d_gthr,
                                  xc->peers, xc->world, xc->rank, xc->nq_cap, xc->k_cap, xc->epoch, db->d_xchg_timed_out,
-                                 d_out_key, d_out_dbidx, d_out_score, d_out_row, d_out_count, st);
+                                 d_out_key, d_out_dbidx, d_out_score, d_out_row, d_out_count, st, use_tc && !db->profiling,
+                                 use_tc ? db->d_cand_cnt : nullptr);
   }
+  // after the batched scan the merge is a programmatic dependent launch (the scan triggers it early)
   return launch_merge(db->d_list_keys, db->d_list_dbidx, lists, k, (int64_t)lists * k, nq, k, db->d_gthr,
-                      d_out_key, d_out_dbidx, d_out_score, d_out_row, d_out_count, st);
+                      d_out_key, d_out_dbidx, d_out_score, d_out_row, d_out_count, st, use_tc && !db->profiling,
+                      use_tc ? db->d_cand_cnt : nullptr);
 }
 
 int ssw_scan_topk_sharded_device(ssw_db* db, const float* d_queries, int nq, int k, const uint32_t* d_exclude_bits,

@@ -36,6 +36,7 @@ struct ssw_db {
   int64_t exact_rescans = 0;
   std::mutex mu;                   // serialises the host-buffer entry points (they share the staging blocks)
   std::vector<int32_t> h_img_dbidx; // host copy of d_img_dbidx (candidate id -> image index), filled on first use
+  unsigned long long* d_scan_stats = nullptr;  // [2] list updates / images offered, counted by the scan kernels (ssw_scan_stats)
   int* d_xchg_timed_out = nullptr; // set by the fused exchange kernel when a peer never answered
   void* d_tc_ws = nullptr;         // prepared A operand of the tcgen05 batched scan (one batch)
 
@@ -47,6 +48,7 @@ struct ssw_db {
   int32_t* d_list_dbidx = nullptr;
   uint64_t* d_gthr = nullptr;      // [nq] shared lower bound on the k-th best key, followed by
   uint32_t* d_pub1 = nullptr;      // [nq][grid] best score per CTA of the streaming scan (same allocation)
+  int32_t* d_cand_cnt = nullptr;   // [nq] compacted candidates per query of the batched scan (same allocation)
   size_t list_capacity = 0;        // entries
   int gthr_capacity = 0;
   // staging for the host-pointer API
@@ -88,20 +90,21 @@ int launch_row_error_stats(const float* d_rows_f32, int64_t n_rows, int dim, flo
 // tcgen05 batched scan (K2): one pass for up to 64 queries; fp16 storage, dim 256/512/768, k <= 64
 bool scan_tc_supported(const ssw_db* db, int k);
 size_t scan_tc_workspace_bytes(int dim, int grid);
-int launch_scan_tc(ssw_db* db, const float* d_queries, int nq, int k, const uint32_t* d_excl, uint64_t* d_list_keys,
-                   int32_t* d_list_dbidx, uint64_t* d_gthr, void* workspace, cudaStream_t st);
+// d_cand_keys / d_cand_dbidx: [nq][grid * k] compacted candidates, d_cand_cnt [nq] their number per query
+int launch_scan_tc(ssw_db* db, const float* d_queries, int nq, int k, const uint32_t* d_excl, uint64_t* d_cand_keys,
+                   int32_t* d_cand_dbidx, int32_t* d_cand_cnt, uint64_t* d_gthr, void* workspace, cudaStream_t st);
 // merge kernel (K4)
 int launch_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_lists, int64_t list_stride,
                  int64_t query_stride, int nq, int k, const uint64_t* d_thr, uint64_t* d_out_key,
                  int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row, int32_t* d_out_count,
-                 cudaStream_t st);
+                 cudaStream_t st, bool pdl = false, const int32_t* d_counts = nullptr);
 // fused shard merge + peer exchange + world merge (multi-GPU); peers[] are peer-mapped exchange buffers
 size_t xchg_bytes(int world, int nq_cap, int k_cap);
 int launch_exchange_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_lists, int64_t list_stride,
                           int64_t query_stride, int nq, int k, const uint64_t* d_thr, void* const* peers, int world,
                           int rank, int nq_cap, int k_cap, uint32_t epoch, int* d_timed_out, uint64_t* d_out_key,
                           int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row, int32_t* d_out_count,
-                          cudaStream_t st);
+                          cudaStream_t st, bool pdl = false, const int32_t* d_counts = nullptr);
 int launch_image_max(ssw_db* db, const float* d_scores, const uint8_t* d_row_mask, const uint32_t* d_excl,
                      int64_t n_padded, uint64_t* d_keys, int32_t* d_dbidx, cudaStream_t st);
 int launch_exclude_build(ssw_db* db, const int32_t* d_ids, const int64_t* d_offsets, int nq, uint32_t* d_bits,

@@ -42,6 +42,7 @@ struct Scan1Args {
   float* scores_out;
   int64_t row_base;
   int k;
+  unsigned long long* stats;  // [2] list updates / images offered (null = not counted)
 };
 
 constexpr int kStages = 3;
@@ -286,12 +287,14 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scan1_kernel(const Scan1Ar
     uint64_t thr = *L.thr;
     thr = thr > g_cached ? thr : g_cached;
     thr = shfl_u64(thr, 0);
+    if (a.stats && lane == 0) atomicAdd(a.stats + 1, 1ull);
     if ((key >> 32) < (thr >> 32)) return;
     const uint32_t drow = key_row(key);
     const int64_t orow = a.orig_row ? a.orig_row[drow] : (int64_t)drow;
     key = (key & 0xFFFFFFFF00000000ull) | (uint64_t)(0xFFFFFFFFu - (uint32_t)(a.row_base + orow));
     if (key <= thr) return;
     if (a.excl && ((a.excl[img >> 5] >> (img & 31)) & 1u)) return;
+    if (a.stats && lane == 0) atomicAdd(a.stats, 1ull);
     list_insert(L, a.k, lane, key, a.img_dbidx[img], a.g_thr);
   };
 
@@ -485,6 +488,7 @@ int launch_scan1(ssw_db* db, const float* d_query, int k, const uint32_t* d_excl
   a.scores_out = nullptr;
   a.row_base = db->row_base;
   a.k = k;
+  a.stats = db->d_scan_stats;
   return dispatch_scan1<0>(db, a, st, exact ? (int)SSW_F32 : db->dtype);
 }
 
@@ -518,6 +522,7 @@ struct MergeArgs {
   int n_lists;
   int64_t list_stride, query_stride;
   int k;
+  const int32_t* counts;     // non-null: query q's candidates are ONE compacted list of counts[q] entries (n_lists = 1)
   const uint64_t* thr;
   uint64_t* out_key;
   int32_t* out_dbidx;
@@ -580,15 +585,17 @@ struct MergeSmem {
 // shared memory; returns their number (<= kMergeCap).  When more survive than fit, the exact k-th largest
 // key is found by radix select over the lists in global memory and only keys >= it are gathered (exactly k:
 // every key embeds a distinct row).  `cg`: read through L2 (lists written by a peer GPU).
+// `len` = entries per list (the per-CTA lists hold k; a compacted list holds what its counter says), `k` = how
+// many the caller wants.
 template <bool CG>
 __device__ __forceinline__ int merge_gather(const MergeSmem& M, const uint64_t* kq, const int32_t* dq, int n_lists,
-                                            int64_t list_stride, uint32_t k, uint64_t thr) {
+                                            int64_t list_stride, uint32_t len, uint32_t k, uint64_t thr) {
   const int tid = threadIdx.x;
-  const uint32_t total = (uint32_t)n_lists * k;
+  const uint32_t total = (uint32_t)n_lists * len;
   if (thr == 0) thr = 1;   // key 0 == empty slot
   auto ldk = [&](int64_t off) { return CG ? __ldcg(kq + off) : kq[off]; };
   auto ldd = [&](int64_t off) { return CG ? __ldcg(dq + off) : dq[off]; };
-  const bool dense = list_stride == (int64_t)k;      // lists back to back: entry e sits at offset e
+  const bool dense = list_stride == (int64_t)len || n_lists == 1;      // lists back to back: entry e sits at offset e
   auto gather = [&](uint64_t lo) {
     if (tid == 0) *M.cnt = 0;
     __syncthreads();
@@ -599,7 +606,7 @@ __device__ __forceinline__ int merge_gather(const MergeSmem& M, const uint64_t* 
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const uint32_t e = e0 + u * kMergeThreads;
-        off[u] = dense ? (int64_t)e : (int64_t)(e / k) * list_stride + (e % k);
+        off[u] = dense ? (int64_t)e : (int64_t)(e / len) * list_stride + (e % len);
         key[u] = e < total ? ldk(off[u]) : 0ull;
       }
 #pragma unroll
@@ -627,7 +634,7 @@ __device__ __forceinline__ int merge_gather(const MergeSmem& M, const uint64_t* 
       __syncthreads();
       const uint64_t prefix = *M.prefix;
       for (uint32_t e = tid; e < total; e += kMergeThreads) {
-        const int64_t off = (int64_t)(e / k) * list_stride + (e % k);
+        const int64_t off = dense ? (int64_t)e : (int64_t)(e / len) * list_stride + (e % len);
         const uint64_t key = ldk(off);
         if (key < thr) continue;
         const bool match = (d == 7) || ((key >> (8 * (d + 1))) == (prefix >> (8 * (d + 1))));
@@ -642,7 +649,25 @@ __device__ __forceinline__ int merge_gather(const MergeSmem& M, const uint64_t* 
   return min(n, kMergeCap);
 }
 
+// Few candidates (total <= kMergeThreads): copy every slot into shared memory as it lies — no filter, no
+// shared-memory atomics (hundreds of atomicAdds on one counter serialise and cost more than the whole rest of
+// the merge); empty slots carry key 0 and are skipped by the ranking.  Returns total.
+template <bool CG>
+__device__ __forceinline__ int merge_load_direct(const MergeSmem& M, const uint64_t* kq, const int32_t* dq, int n_lists,
+                                                 int64_t list_stride, uint32_t len) {
+  const uint32_t total = (uint32_t)n_lists * len;
+  const bool dense = list_stride == (int64_t)len || n_lists == 1;
+  for (uint32_t e = threadIdx.x; e < total; e += kMergeThreads) {
+    const int64_t off = dense ? (int64_t)e : (int64_t)(e / len) * list_stride + (e % len);
+    M.sk[e] = CG ? __ldcg(kq + off) : kq[off];
+    M.sd[e] = CG ? __ldcg(dq + off) : dq[off];
+  }
+  __syncthreads();
+  return (int)total;
+}
+
 // The n gathered survivors -> their best min(n, k), sorted best-first in (ok, od); returns that count.
+// Keys equal to 0 (empty slots of a direct load) never rank.
 __device__ __forceinline__ int merge_select_sort(const MergeSmem& M, int n, int k) {
   const int tid = threadIdx.x;
   int m;
@@ -654,8 +679,8 @@ __device__ __forceinline__ int merge_select_sort(const MergeSmem& M, int n, int 
       M.od[i] = -1;
     }
     __syncthreads();
-    if (tid < n) {
-      const uint64_t mine = M.sk[tid];
+    const uint64_t mine = tid < n ? M.sk[tid] : 0ull;
+    if (mine != 0ull) {
       int rank = 0;
 #pragma unroll 4
       for (int j = 0; j < n; ++j) rank += M.sk[j] > mine;
@@ -664,8 +689,8 @@ __device__ __forceinline__ int merge_select_sort(const MergeSmem& M, int n, int 
         M.od[rank] = M.sd[tid];
       }
     }
-    __syncthreads();
-    return min(n, k);
+    const int valid = __syncthreads_count(mine != 0ull);
+    return min(valid, k);
   }
   if (n <= k) {
     m = n;
@@ -767,9 +792,15 @@ __device__ __forceinline__ void merge_write(const MergeSmem& M, const MergeArgs&
 
 __global__ void __launch_bounds__(kMergeThreads, 1) merge_topk_kernel(const MergeArgs a) {
   SSW_MERGE_SMEM(M);
+  pdl_wait();        // launched as a programmatic dependent of the batched scan: its lists are complete from here
   const int q = blockIdx.x;
-  const int n = merge_gather<false>(M, a.keys + (int64_t)q * a.query_stride, a.dbidx + (int64_t)q * a.query_stride,
-                                    a.n_lists, a.list_stride, (uint32_t)a.k, a.thr ? a.thr[q] : 0ull);
+  const int nl = a.counts ? 1 : a.n_lists;
+  const uint32_t len = a.counts ? (uint32_t)a.counts[q] : (uint32_t)a.k;
+  const uint64_t* kq = a.keys + (int64_t)q * a.query_stride;
+  const int32_t* dq = a.dbidx + (int64_t)q * a.query_stride;
+  const int n = (uint64_t)nl * len <= (uint64_t)kMergeThreads
+                    ? merge_load_direct<false>(M, kq, dq, nl, a.list_stride, len)
+                    : merge_gather<false>(M, kq, dq, nl, a.list_stride, len, (uint32_t)a.k, a.thr ? a.thr[q] : 0ull);
   const int m = merge_select_sort(M, n, a.k);
   merge_write(M, a, q, m);
 }
@@ -777,12 +808,12 @@ __global__ void __launch_bounds__(kMergeThreads, 1) merge_topk_kernel(const Merg
 int launch_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_lists, int64_t list_stride,
                  int64_t query_stride, int nq, int k, const uint64_t* d_thr, uint64_t* d_out_key,
                  int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row, int32_t* d_out_count,
-                 cudaStream_t st) {
-  MergeArgs a{d_keys, d_dbidx, n_lists, list_stride, query_stride, k, d_thr,
+                 cudaStream_t st, bool pdl, const int32_t* d_counts) {
+  MergeArgs a{d_keys, d_dbidx, n_lists, list_stride, query_stride, k, d_counts, d_thr,
               d_out_key, d_out_dbidx, d_out_score, d_out_row, d_out_count};
   const size_t smem = (size_t)(kMergeCap + kMergeOut) * 12;
   SSW_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  merge_topk_kernel<<<nq, kMergeThreads, smem, st>>>(a);
+  SSW_CUDA(launch_kernel(merge_topk_kernel, dim3(nq), dim3(kMergeThreads), smem, st, pdl, a));
   SSW_LAUNCHED();
   return SSW_OK;
 }
@@ -817,9 +848,15 @@ __global__ void __launch_bounds__(kMergeThreads, 1) exchange_merge_kernel(const 
   const MergeArgs& a = x.m;
   const int q = blockIdx.x, tid = threadIdx.x;
   const int par = (int)(x.epoch & 1u);
+  pdl_wait();
   // ---- 1. this shard's top-k
-  int n = merge_gather<false>(M, a.keys + (int64_t)q * a.query_stride, a.dbidx + (int64_t)q * a.query_stride,
-                              a.n_lists, a.list_stride, (uint32_t)a.k, a.thr ? a.thr[q] : 0ull);
+  const int nl = a.counts ? 1 : a.n_lists;
+  const uint32_t len = a.counts ? (uint32_t)a.counts[q] : (uint32_t)a.k;
+  const uint64_t* kq = a.keys + (int64_t)q * a.query_stride;
+  const int32_t* dq = a.dbidx + (int64_t)q * a.query_stride;
+  int n = (uint64_t)nl * len <= (uint64_t)kMergeThreads
+              ? merge_load_direct<false>(M, kq, dq, nl, a.list_stride, len)
+              : merge_gather<false>(M, kq, dq, nl, a.list_stride, len, (uint32_t)a.k, a.thr ? a.thr[q] : 0ull);
   int m = merge_select_sort(M, n, a.k);
   // ---- 2. store it into slot `rank` of every rank's buffer (own included), then raise the flags
   const size_t slot = (((size_t)par * x.world + x.rank) * x.nq_cap + q);
@@ -865,7 +902,9 @@ __global__ void __launch_bounds__(kMergeThreads, 1) exchange_merge_kernel(const 
   const size_t q0 = ((size_t)par * x.world) * x.nq_cap + q;
   const uint64_t* wk = reinterpret_cast<const uint64_t*>(mine) + q0 * x.k_cap;
   const int32_t* wd = reinterpret_cast<const int32_t*>(mine + xchg_keys_bytes(x.world, x.nq_cap, x.k_cap)) + q0 * x.k_cap;
-  n = merge_gather<true>(M, wk, wd, x.world, (int64_t)x.nq_cap * x.k_cap, (uint32_t)a.k, 0ull);
+  n = (uint64_t)x.world * a.k <= (uint64_t)kMergeThreads
+          ? merge_load_direct<true>(M, wk, wd, x.world, (int64_t)x.nq_cap * x.k_cap, (uint32_t)a.k)
+          : merge_gather<true>(M, wk, wd, x.world, (int64_t)x.nq_cap * x.k_cap, (uint32_t)a.k, (uint32_t)a.k, 0ull);
   m = merge_select_sort(M, n, a.k);
   merge_write(M, a, q, m);
 }
@@ -874,10 +913,10 @@ int launch_exchange_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_
                           int64_t query_stride, int nq, int k, const uint64_t* d_thr, void* const* peers, int world,
                           int rank, int nq_cap, int k_cap, uint32_t epoch, int* d_timed_out, uint64_t* d_out_key,
                           int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row, int32_t* d_out_count,
-                          cudaStream_t st) {
+                          cudaStream_t st, bool pdl, const int32_t* d_counts) {
   XchgArgs x{};
   x.timed_out = d_timed_out;
-  x.m = MergeArgs{d_keys, d_dbidx, n_lists, list_stride, query_stride, k, d_thr,
+  x.m = MergeArgs{d_keys, d_dbidx, n_lists, list_stride, query_stride, k, d_counts, d_thr,
                   d_out_key, d_out_dbidx, d_out_score, d_out_row, d_out_count};
   for (int i = 0; i < world; ++i) x.peers[i] = peers[i];
   x.world = world;
@@ -887,7 +926,7 @@ int launch_exchange_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_
   x.epoch = epoch;
   const size_t smem = (size_t)(kMergeCap + kMergeOut) * 12;
   SSW_CUDA(cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  exchange_merge_kernel<<<nq, kMergeThreads, smem, st>>>(x);
+  SSW_CUDA(launch_kernel(exchange_merge_kernel, dim3(nq), dim3(kMergeThreads), smem, st, pdl, x));
   SSW_LAUNCHED();
   return SSW_OK;
 }

@@ -35,7 +35,8 @@
 namespace ssw {
 
 struct ScanTcArgs {
-  const uint32_t* a_img;     // [128][DIM/2] packed fp16 pairs: image of the A operand, one row per TMEM lane
+  const uint32_t* a_img;     // [DIM/8][128][4] packed fp16 pairs: image of the A operand in 16-byte pieces, piece p of
+                             // TMEM lane L at ((p * 128 + L) * 4): a warp copying one piece of 32 lanes reads 512 contiguous bytes
   const float* inv_scale;    // [64] 2^-e of every query slot (scores = accumulator * inv_scale)
   int nq;
   int k;
@@ -47,11 +48,13 @@ struct ScanTcArgs {
   const int32_t* img_dbidx;
   const int64_t* orig_row;   // null when identity
   const int32_t* part;       // [grid*8 + 1] image partition of the streaming scan, 8 entries per CTA
-  uint64_t* list_keys;       // [nq][grid][k]
-  int32_t* list_dbidx;
+  uint64_t* cand_keys;       // [nq][grid * k] compacted candidates of every query: each CTA appends the entries of
+  int32_t* cand_dbidx;       //   its list that still reach the shared bound when it finishes
+  int32_t* cand_cnt;         // [nq] entries appended so far
   uint64_t* g_thr;           // [nq]
   uint32_t* pub;             // [64][grid] best score (order-preserving bits) every CTA holds per query
   int64_t row_base;
+  unsigned long long* stats; // [2] list updates / images offered to a list, summed over the grid (null = not counted)
 };
 
 constexpr int kTcMaxK = 64;   // per-query list length the batched epilogue keeps in shared memory
@@ -62,7 +65,8 @@ constexpr int kTcMaxK = 64;   // per-query list length the batched epilogue keep
 // ------------------------------------------------------------------------------------------
 __global__ void scan_tc_prep_kernel(const float* __restrict__ q, int nq, int dim, uint32_t* __restrict__ a_img,
                                     float* __restrict__ inv_scale, uint64_t* __restrict__ g_thr,
-                                    uint32_t* __restrict__ pub, int n_pub) {
+                                    int32_t* __restrict__ cand_cnt, uint32_t* __restrict__ pub, int n_pub) {
+  pdl_launch_dependents();      // the scan kernel may set itself up (barriers, TMEM, tensor map) while this runs
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pub; i += gridDim.x * blockDim.x) pub[i] = 0u;
   const int L = blockIdx.x;                       // TMEM lane
   const int q4 = L >> 5, h = (L >> 4) & 1, r = L & 7;
@@ -98,10 +102,13 @@ __global__ void scan_tc_prep_kernel(const float* __restrict__ q, int nq, int dim
     h0 = __float2half_rn(x0 - __half2float(h0));
     h1 = __float2half_rn(x1 - __half2float(h1));
   }
-  a_img[(size_t)L * (dim / 2) + t] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+  a_img[((size_t)(t >> 2) * 128 + L) * 4 + (t & 3)] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
   if (t == 0 && !is_lo) {
     inv_scale[qa] = ldexpf(1.0f, -e);
-    if (ok) g_thr[qa] = 0ull;
+    if (ok) {
+      g_thr[qa] = 0ull;
+      cand_cnt[qa] = 0;
+    }
   }
 }
 
@@ -113,10 +120,11 @@ struct QShared {
   int32_t* cnt;         // [64]
   int32_t* minpos;      // [64]
   uint32_t* best;       // [64] order-preserving score bits of the best candidate held (published to the other CTAs)
-  int* done;            // epilogue warps that have finished (the threshold warp leaves at 4)
+  int* done;            // epilogue warps that have finished (the threshold warp leaves at 8)
+  uint32_t* upd;        // [64] list updates of this CTA (appends + replacements), [64] images offered (past the vote)
   uint32_t* excl;       // [64][slice_words] this CTA's slice of the exclusion bitmaps (optional)
 };
-__host__ __device__ constexpr size_t qshared_bytes(int k) { return (size_t)k * 64 * 12 + 64 * (8 + 4 + 4 + 4) + 16; }
+__host__ __device__ constexpr size_t qshared_bytes(int k) { return (size_t)k * 64 * 12 + 64 * (8 + 4 + 4 + 4 + 8) + 16; }
 
 __device__ __forceinline__ QShared qshared_carve(uint8_t* base, int k) {
   QShared q;
@@ -127,7 +135,8 @@ __device__ __forceinline__ QShared qshared_carve(uint8_t* base, int k) {
   q.minpos = q.cnt + 64;
   q.best = reinterpret_cast<uint32_t*>(q.minpos + 64);
   q.done = reinterpret_cast<int*>(q.best + 64);
-  q.excl = reinterpret_cast<uint32_t*>(q.done + 4);
+  q.upd = reinterpret_cast<uint32_t*>(q.done + 4);
+  q.excl = q.upd + 128;
   return q;
 }
 
@@ -150,6 +159,7 @@ __device__ __forceinline__ uint64_t scan_tc_offer(const QShared& Q, const ScanTc
   uint32_t xw = 0;
   if (a.excl && a.excl_slice_words > 0) xw = Q.excl[q * a.excl_slice_words + (img >> 5) - slice_base];
   uint64_t key = make_key(best * inv_scale, (uint32_t)drow);
+  ++Q.upd[64 + q];
   if ((key >> 32) < (thr >> 32)) return thr;
   const int64_t orow = a.orig_row ? a.orig_row[drow] : drow;
   key = (key & 0xFFFFFFFF00000000ull) | (uint64_t)(0xFFFFFFFFu - (uint32_t)(a.row_base + orow));
@@ -163,6 +173,7 @@ __device__ __forceinline__ uint64_t scan_tc_offer(const QShared& Q, const ScanTc
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(a.pub + (size_t)q * gridDim.x + blockIdx.x),
                  "r"((uint32_t)(key >> 32)) : "memory");
   }
+  ++Q.upd[q];
   if (cnt < k) {
     Q.keys[cnt * 64 + q] = key;
     Q.img[cnt * 64 + q] = img;
@@ -337,6 +348,17 @@ __device__ __forceinline__ void tmem_ld_wait_regs16(uint32_t* x) {
                : "memory");
 }
 
+// ... and for two register blocks at once
+__device__ __forceinline__ void tmem_ld_wait_regs32(uint32_t* x, uint32_t* y) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]),
+                 "+r"(x[8]), "+r"(x[9]), "+r"(x[10]), "+r"(x[11]), "+r"(x[12]), "+r"(x[13]), "+r"(x[14]), "+r"(x[15]),
+                 "+r"(y[0]), "+r"(y[1]), "+r"(y[2]), "+r"(y[3]), "+r"(y[4]), "+r"(y[5]), "+r"(y[6]), "+r"(y[7]),
+                 "+r"(y[8]), "+r"(y[9]), "+r"(y[10]), "+r"(y[11]), "+r"(y[12]), "+r"(y[13]), "+r"(y[14]), "+r"(y[15])
+               :
+               : "memory");
+}
+
 constexpr int kScanTc8Threads = 64 + 8 * 32 + 32;   // producer, MMA, 8 epilogue warps, threshold warp
 
 template <int DIM, int NT, int NS, int NACC>
@@ -353,10 +375,16 @@ __global__ void __launch_bounds__(kScanTc8Threads, 1) scan_tc8_kernel(const __gr
     Q.cnt[threadIdx.x] = 0;
     Q.minpos[threadIdx.x] = 0;
     Q.best[threadIdx.x] = 0;
+    Q.upd[threadIdx.x] = 0;
+    Q.upd[64 + threadIdx.x] = 0;
     if (threadIdx.x == 0) *Q.done = 0;
   }
-  const uint32_t tmem = tc_setup(S, NS, Cfg::TMEM_ALLOC, &tmap, 256);
+  const uint32_t tmem = tc_setup(S, NS, Cfg::TMEM_ALLOC, &tmap, 256, 256);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // everything above overlapped the tail of the query-preparation kernel (programmatic dependent launch); from
+  // here on its outputs (A image, scales, zeroed thresholds / published bests) are read
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int img0 = a.part[blockIdx.x * kScanWarps], img1 = a.part[(blockIdx.x + 1) * kScanWarps];
   const int64_t r_begin = a.row_ptr[img0], r_end = a.row_ptr[img1];
@@ -408,20 +436,26 @@ __global__ void __launch_bounds__(kScanTc8Threads, 1) scan_tc8_kernel(const __gr
     const int q4 = warp & 3, h = (warp - 2) >> 2;
     const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
     const int k = a.k;
-    if (h == 0) {          // A operand: the first warp of every quarter copies its 32 TMEM lanes
-      const uint4* src = reinterpret_cast<const uint4*>(a.a_img + (size_t)(q4 * 32 + lane) * (DIM / 2));
+    {      // A operand: the two warps of a quarter copy half of the columns of its 32 TMEM lanes each, two
+           // 32-column chunks per round (16 coalesced 16-byte loads in flight, then two tcgen05.st)
+      constexpr int NCH = Cfg::A_COLS / 32;           // 32-column chunks of the operand
+      static_assert(NCH % 4 == 0, "chunks must split evenly over two warps, two per round");
+      const uint4* src = reinterpret_cast<const uint4*>(a.a_img) + q4 * 32 + lane;
 #pragma unroll 1
-      for (int c = 0; c < Cfg::A_COLS / 32; ++c) {
-        uint32_t rr[32];
+      for (int c = h * (NCH / 2); c < (h + 1) * (NCH / 2); c += 2) {
+        uint32_t rr[2][32];
 #pragma unroll
-        for (int x = 0; x < 8; ++x) {
-          const uint4 w = __ldg(src + c * 8 + x);
-          rr[4 * x] = w.x;
-          rr[4 * x + 1] = w.y;
-          rr[4 * x + 2] = w.z;
-          rr[4 * x + 3] = w.w;
-        }
-        tmem_st32(lane_addr + Cfg::A_BASE + c * 32, rr);
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int x = 0; x < 8; ++x) {
+            const uint4 w = __ldg(src + (size_t)((c + u) * 8 + x) * 128);
+            rr[u][4 * x] = w.x;
+            rr[u][4 * x + 1] = w.y;
+            rr[u][4 * x + 2] = w.z;
+            rr[u][4 * x + 3] = w.w;
+          }
+        tmem_st32(lane_addr + Cfg::A_BASE + c * 32, rr[0]);
+        tmem_st32(lane_addr + Cfg::A_BASE + (c + 1) * 32, rr[1]);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -482,37 +516,73 @@ __global__ void __launch_bounds__(kScanTc8Threads, 1) scan_tc8_kernel(const __gr
       tc_fence_after();
       const uint32_t acc = lane_addr + half_addr + Cfg::ACC_BASE + as * NT;
       const int colbase = (int)(row0 - r_begin);
-      uint32_t va[16], vb[16];
-      tmem_ld_16x256b_x4(acc, va);
-      tmem_ld_wait_regs16(va);
+      if constexpr (NACC == 1) {
+        // One accumulator (dim 768: the A operand takes 384 of the 512 TMEM columns).  Drain the whole tile into
+        // registers first and hand the accumulator back at once, so the next tile's MMAs run under this tile's
+        // epilogue arithmetic instead of after it.
+        static_assert(NG == 4, "single-accumulator variant is written for 128-row tiles");
+        uint32_t v[NG][16];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) tmem_ld_16x256b_x4(acc + 32 * g, v[g]);
+        tmem_ld_wait_regs32(v[0], v[1]);
+        tmem_ld_wait_regs32(v[2], v[3]);
+        tc_fence_before();
+        mbar_arrive(S.tmem_empty + 8 * as);
+#pragma unroll
+        for (int g = 0; g < NG; ++g) scan_tc8_group(st, cx, Q, a, v[g], ends[g], colbase + 32 * g);
+      } else {
+        uint32_t va[16], vb[16];
+        tmem_ld_16x256b_x4(acc, va);
+        tmem_ld_wait_regs16(va);
 #pragma unroll 1
-      for (int gp = 0; gp < NG; gp += 2) {
-        uint32_t eA = ends[0], eB = ends[1];
-        if constexpr (NG == 4) {
-          eA = gp ? ends[2] : eA;
-          eB = gp ? ends[3] : eB;
+        for (int gp = 0; gp < NG; gp += 2) {
+          uint32_t eA = ends[0], eB = ends[1];
+          if constexpr (NG == 4) {
+            eA = gp ? ends[2] : eA;
+            eB = gp ? ends[3] : eB;
+          }
+          tmem_ld_16x256b_x4(acc + 32 * (gp + 1), vb);
+          scan_tc8_group(st, cx, Q, a, va, eA, colbase + 32 * gp);
+          tmem_ld_wait_regs16(vb);
+          if (gp + 2 < NG) tmem_ld_16x256b_x4(acc + 32 * (gp + 2), va);
+          scan_tc8_group(st, cx, Q, a, vb, eB, colbase + 32 * (gp + 1));
+          if (gp + 2 < NG) tmem_ld_wait_regs16(va);
         }
-        tmem_ld_16x256b_x4(acc + 32 * (gp + 1), vb);
-        scan_tc8_group(st, cx, Q, a, va, eA, colbase + 32 * gp);
-        tmem_ld_wait_regs16(vb);
-        if (gp + 2 < NG) tmem_ld_16x256b_x4(acc + 32 * (gp + 2), va);
-        scan_tc8_group(st, cx, Q, a, vb, eB, colbase + 32 * (gp + 1));
-        if (gp + 2 < NG) tmem_ld_wait_regs16(va);
+        tc_fence_before();
+        mbar_arrive(S.tmem_empty + 8 * as);
       }
-      tc_fence_before();
-      mbar_arrive(S.tmem_empty + 8 * as);
     }
     __syncwarp();
     if (lane == 0) atomicAdd(Q.done, 1);
+    if (a.stats && lane < 8 && q4 * 16 + h * 8 + lane < a.nq) {
+      atomicAdd(a.stats, (unsigned long long)Q.upd[q4 * 16 + h * 8 + lane]);
+      atomicAdd(a.stats + 1, (unsigned long long)Q.upd[64 + q4 * 16 + h * 8 + lane]);
+    }
+    // ---- publish: of every query's list only the entries that still reach the shared bound, appended to the
+    //      query's compacted candidate array (one atomic per warp and 32 slots) — the merge reads tens to
+    //      hundreds of keys per query instead of grid x k slots
     {
       const int nqw = min(8, a.nq - (q4 * 16 + h * 8));
-#pragma unroll 4
-      for (int e = lane; e < nqw * k; e += 32) {
-        const int qi = q4 * 16 + h * 8 + e / k, sl = e % k;
-        const bool ok = sl < Q.cnt[qi];
-        const int64_t o = ((int64_t)qi * gridDim.x + blockIdx.x) * k + sl;
-        a.list_keys[o] = ok ? Q.keys[sl * 64 + qi] : 0ull;
-        a.list_dbidx[o] = ok ? __ldg(a.img_dbidx + Q.img[sl * 64 + qi]) : -1;
+      const int64_t cap = (int64_t)gridDim.x * k;
+      for (int qq = 0; qq < nqw; ++qq) {
+        const int qi = q4 * 16 + h * 8 + qq;
+        const int cntq = Q.cnt[qi];
+        const uint64_t thr = ld_relaxed_u64(a.g_thr + qi);
+        for (int s0 = 0; s0 < cntq; s0 += 32) {
+          const int sl = s0 + lane;
+          const uint64_t key = sl < cntq ? Q.keys[sl * 64 + qi] : 0ull;
+          const bool pass = key != 0ull && key >= thr;
+          const uint32_t mask = __ballot_sync(0xffffffffu, pass);
+          if (mask == 0) continue;
+          int base = 0;
+          if (lane == 0) base = atomicAdd(a.cand_cnt + qi, __popc(mask));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (pass) {
+            const int64_t o = (int64_t)qi * cap + base + __popc(mask & ((1u << lane) - 1u));
+            a.cand_keys[o] = key;
+            a.cand_dbidx[o] = __ldg(a.img_dbidx + Q.img[sl * 64 + qi]);
+          }
+        }
       }
     }
   }
@@ -540,7 +610,9 @@ static int launch_scan_tc_t(ssw_db* db, const ScanTcArgs& a, cudaStream_t st) {
   auto kern = scan_tc8_kernel<DIM, NT, NS, NACC>;
   SSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prof_begin(db, st);      // times the scan kernel alone (not the query preparation)
-  kern<<<db->scan_grid, kScanTc8Threads, smem, st>>>(tmap, a2);
+  // programmatic dependent launch: the kernel's set-up runs under the tail of the preparation kernel (an event
+  // record between the two would serialise them, so not while profiling)
+  SSW_CUDA(launch_kernel(kern, dim3(db->scan_grid), dim3(kScanTc8Threads), smem, st, !db->profiling, tmap, a2));
   prof_end(db, st);
   SSW_LAUNCHED();
   return SSW_OK;
@@ -554,12 +626,12 @@ size_t scan_tc_workspace_bytes(int dim, int grid) { return (size_t)128 * (dim / 
 
 // One pass over the database for queries [0, nq), nq <= 64.  `workspace` holds the prepared A operand
 // (scan_tc_workspace_bytes); the preparation kernel also zeroes the queries' shared thresholds.
-int launch_scan_tc(ssw_db* db, const float* d_queries, int nq, int k, const uint32_t* d_excl, uint64_t* d_list_keys,
-                   int32_t* d_list_dbidx, uint64_t* d_gthr, void* workspace, cudaStream_t st) {
+int launch_scan_tc(ssw_db* db, const float* d_queries, int nq, int k, const uint32_t* d_excl, uint64_t* d_cand_keys,
+                   int32_t* d_cand_dbidx, int32_t* d_cand_cnt, uint64_t* d_gthr, void* workspace, cudaStream_t st) {
   uint32_t* a_img = static_cast<uint32_t*>(workspace);
   float* inv_scale = reinterpret_cast<float*>(a_img + (size_t)128 * (db->dim / 2));
   uint32_t* pub = reinterpret_cast<uint32_t*>(inv_scale + 64);
-  scan_tc_prep_kernel<<<128, db->dim / 2, 0, st>>>(d_queries, nq, db->dim, a_img, inv_scale, d_gthr, pub,
+  scan_tc_prep_kernel<<<128, db->dim / 2, 0, st>>>(d_queries, nq, db->dim, a_img, inv_scale, d_gthr, d_cand_cnt, pub,
                                                      64 * db->scan_grid);
   SSW_LAUNCHED();
   ScanTcArgs a{};
@@ -574,11 +646,13 @@ int launch_scan_tc(ssw_db* db, const float* d_queries, int nq, int k, const uint
   a.img_dbidx = db->d_img_dbidx;
   a.orig_row = db->d_orig_row;
   a.part = db->d_part;
-  a.list_keys = d_list_keys;
-  a.list_dbidx = d_list_dbidx;
+  a.cand_keys = d_cand_keys;
+  a.cand_dbidx = d_cand_dbidx;
+  a.cand_cnt = d_cand_cnt;
   a.g_thr = d_gthr;
   a.pub = pub;
   a.row_base = db->row_base;
+  a.stats = db->d_scan_stats;
   // shared memory: NS stages of NT*128 B + 64 lists of k (key, image) pairs (k <= 64 -> <= 48 KB)
   switch (db->dim) {
     case 256: return launch_scan_tc_t<256, 128, 10, 2>(db, a, st);

@@ -227,7 +227,7 @@ __host__ __device__ constexpr int tc_bar_bytes(int ns) { return 16 * ns + 16 + 1
 
 // Called by every thread at kernel start.  Returns the TMEM base address.
 __device__ __forceinline__ uint32_t tc_setup(const TcSmem& s, int ns, uint32_t tmem_cols, const CUtensorMap* tmap,
-                                             uint32_t epilogue_threads = 128) {
+                                             uint32_t epilogue_threads = 128, uint32_t a_writer_threads = 128) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(tmap);
@@ -239,7 +239,7 @@ __device__ __forceinline__ uint32_t tc_setup(const TcSmem& s, int ns, uint32_t t
       mbar_init(s.tmem_full + 8 * i, 1);
       mbar_init(s.tmem_empty + 8 * i, epilogue_threads);
     }
-    mbar_init(s.a_ready, 128);
+    mbar_init(s.a_ready, a_writer_threads);
     fence_mbar_init();
     fence_proxy_async();
   }

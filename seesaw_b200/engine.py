@@ -86,6 +86,20 @@ class PatchDatabase:
         return dict(attached=bool(a.value), rho=rho.value, vmax=vmax.value, queries=nq.value, rescans=nr.value)
 
     @classmethod
+    def from_device_tensor(cls, d_vectors, dbidx_per_row, *, store="f16", global_row_base=0):
+        """Vectors already on the GPU (a float16 / float32 CUDA tensor [n_rows, dim], rows grouped by ascending
+        dbidx): copied / converted device to device, no trip through the host."""
+        import torch
+        assert d_vectors.is_cuda and d_vectors.is_contiguous() and d_vectors.dtype in (torch.float16, torch.float32)
+        dbidx = np.ascontiguousarray(dbidx_per_row, dtype=np.int32).reshape(-1)
+        assert d_vectors.ndim == 2 and d_vectors.shape[0] == dbidx.shape[0]
+        h = C.c_void_p()
+        check(lib.ssw_db_create_device(C.byref(h), d_vectors.device.index or 0, C.c_void_p(d_vectors.data_ptr()),
+                                       SSW_F16 if d_vectors.dtype == torch.float16 else SSW_F32, _dtype_id(store),
+                                       d_vectors.shape[0], d_vectors.shape[1], ptr(dbidx), global_row_base))
+        return cls(h)
+
+    @classmethod
     def synthetic(cls, dbidx_per_row, dim, *, seed, kind="tri", store="f16", device=0, global_row_base=0):
         dbidx = np.ascontiguousarray(dbidx_per_row, dtype=np.int32).reshape(-1)
         h = C.c_void_p()
@@ -118,13 +132,25 @@ class PatchDatabase:
         check(lib.ssw_profile_read(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def scan_stats(self, enable=True):
+        """(list updates, images offered to a list) counted by the scan kernels since the last call; see ssw_scan_stats."""
+        u, o = C.c_int64(), C.c_int64()
+        check(lib.ssw_scan_stats(self._h, int(bool(enable)), C.byref(u), C.byref(o)))
+        return u.value, o.value
+
     # ---- host-buffer API (what the reference-facing classes call) --------------------------
     def scan_topk(self, queries, k, exclude=None):
         """queries [nq, dim] or [dim] fp32; exclude: list of nq iterables of dbidx (or None).
         Returns dict(dbidx int32 [nq,k], score fp32, row int64, count int32 [nq])."""
         q = np.ascontiguousarray(np.asarray(queries, dtype=np.float32).reshape(-1, self.dim))
+        ids, offsets = exclude_lists_to_csr(exclude, q.shape[0])
+        return self.scan_topk_csr(q, k, ids, offsets)
+
+    def scan_topk_csr(self, q, k, exclude_ids=None, exclude_offsets=None):
+        """:meth:`scan_topk` with the per-query exclude lists already in the C ABI's form: ``exclude_ids`` int32
+        (all lists back to back) and ``exclude_offsets`` int64 [nq+1]; ``q`` float32 C-contiguous [nq, dim]."""
         nq = q.shape[0]
-        ids, offsets = exclude_lists_to_csr(exclude, nq)
+        ids, offsets = exclude_ids, exclude_offsets
         out_dbidx = np.empty((nq, k), np.int32)
         out_score = np.empty((nq, k), np.float32)
         out_row = np.empty((nq, k), np.int64)

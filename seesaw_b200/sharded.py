@@ -115,19 +115,21 @@ class ShardedPatchDatabase:
     def scan_topk(self, queries, k, exclude=None):
         """Host-buffer form (numpy in, numpy out) of the sharded step through the fused exchange: what a
         session front end calls on every rank.  Same dict as PatchDatabase.scan_topk."""
-        import ctypes as C
-
-        from ._lib import check, lib, ptr
         from .engine import exclude_lists_to_csr
+        q = np.ascontiguousarray(np.asarray(queries, dtype=np.float32).reshape(-1, self.local.dim))
+        ids, offsets = exclude_lists_to_csr(exclude, q.shape[0])
+        return self.scan_topk_csr(q, k, ids, offsets)
+
+    def scan_topk_csr(self, q, k, exclude_ids=None, exclude_offsets=None):
+        """:meth:`scan_topk` with the exclude lists already in the C ABI's CSR form (see PatchDatabase.scan_topk_csr)."""
+        from ._lib import check, lib, ptr
         assert self._xchg is not None, "call enable_fused_exchange() first"
         x = self._xchg
-        q = np.ascontiguousarray(np.asarray(queries, dtype=np.float32).reshape(-1, self.local.dim))
         nq = q.shape[0]
-        ids, offsets = exclude_lists_to_csr(exclude, nq)
         out = dict(dbidx=np.empty((nq, k), np.int32), score=np.empty((nq, k), np.float32),
                    row=np.empty((nq, k), np.int64), count=np.empty(nq, np.int32))
         x["epoch"] += 1
-        check(lib.ssw_scan_topk_sharded(self.local._h, ptr(q), nq, int(k), ptr(ids), ptr(offsets), x["peers"],
+        check(lib.ssw_scan_topk_sharded(self.local._h, ptr(q), nq, int(k), ptr(exclude_ids), ptr(exclude_offsets), x["peers"],
                                         self.world_size, self.rank, x["nq_cap"], x["k_cap"], x["epoch"],
                                         ptr(out["dbidx"]), ptr(out["score"]), ptr(out["row"]), ptr(out["count"])))
         return out
