@@ -239,9 +239,19 @@ int ssw_lp_fit(ssw_lp* lp, const int64_t* label_ids, const double* label_values,
                const double* reg_values, const double* start_value, int max_iter, double epsilon,
                double* out_values, int* out_iterations, int* out_converged);
 
+/* Same iteration with the prior term handed over ready-made: lambda_reg_values[n] = reg_lambda * reg_values AS THE
+ * CALLER'S ARITHMETIC PRODUCED IT (the reference multiplies in the dtype of reg_values — float32 priors from
+ * index.score give a float32 product, label_propagation.py:31 — and only then adds in float64), and x0[n] the start
+ * iterate (start_value, else reg_values, else zeros; labels are clamped by the library).  NULL prior = zeros. */
+int ssw_lp_fit_scaled(ssw_lp* lp, const int64_t* label_ids, const double* label_values, int64_t n_labels,
+                      const double* lambda_reg_values, const double* x0, int max_iter, double epsilon,
+                      double* out_values, int* out_iterations, int* out_converged);
+
 /* ---- introspection for benchmarks / tests ---------------------------------------------- */
-/* With profiling on, every launch of the dominant scan kernel (K1 streaming or K2 tcgen05) is
- * bracketed by CUDA events on its own stream.  ssw_profile_read synchronises those events and
+/* With profiling on, launches of the dominant scan kernel (K1 streaming or K2 tcgen05) are bracketed by CUDA
+ * events on their own stream: every launch for on == 1, every on-th launch for on > 1 (an event between two
+ * kernels rules out their programmatic dependent launch, so a sampled step runs without that overlap and the
+ * others with it).  ssw_profile_read synchronises those events and
  * returns the summed kernel time and launch count since the last read, then resets them. */
 int ssw_profile_enable(ssw_db* db, int on);
 int ssw_profile_read(ssw_db* db, double* scan_kernel_ms, int64_t* scan_kernel_launches);

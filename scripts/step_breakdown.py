@@ -62,6 +62,11 @@ for n_img in args.images:
               f"wall {wall:7.1f} us  HBM-ideal {ideal_us:6.1f} us  ideal/step {ideal_us / step:.3f}", flush=True)
 
     run(lambda: db.scan_topk_device(d_q, K, bits, decoded=True), "device API (merge kernel)")
+    db.scan_stats(True)
+    for _ in range(10):
+        db.scan_topk_device(d_q, K, bits, decoded=True)
+    upd, off = db.scan_stats(False)
+    print(f"rows={db.n_rows:>9} per query and CTA and launch: {upd / 10 / NQ / 148:.1f} list updates, {off / 10 / NQ / 148:.1f} images offered", flush=True)
     sdb.enable_fused_exchange(nq_cap=NQ, k_cap=64)
     run(lambda: sdb.scan_topk_device(d_q, K, d_exclude_bits=bits), "fused exchange, world=1")
     run(lambda: sdb.scan_topk(q_host, K, exclude=ex), "host API (sharded, world=1)")

@@ -79,6 +79,7 @@ SIGNATURES = {
     "ssw_lp_destroy": (C.c_int, [_p]),
     "ssw_lp_fit": (C.c_int, [_p, _p, _p, C.c_int64, _p, _p, C.c_int, C.c_double, _p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ssw_scan_stats": (C.c_int, [_p, C.c_int, _i64p, _i64p]),
+    "ssw_lp_fit_scaled": (C.c_int, [_p, _p, _p, C.c_int64, _p, _p, C.c_int, C.c_double, _p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ssw_kernel_launch_count": (C.c_int64, []),
     "ssw_profile_enable": (C.c_int, [_p, C.c_int]),
     "ssw_profile_read": (C.c_int, [_p, C.POINTER(C.c_double), _i64p]),

@@ -58,7 +58,10 @@ int ensure_device(int device, int* sm_count) {
 }
 
 void prof_begin(ssw_db* db, cudaStream_t st) {
+  db->prof_sampled = false;
   if (!db->profiling) return;
+  if (db->prof_stride > 1 && (db->prof_counter++ % db->prof_stride) != 0) return;   // sample every prof_stride-th launch
+  db->prof_sampled = true;
   std::pair<cudaEvent_t, cudaEvent_t> ev;
   if (!db->prof_free.empty()) {
     ev = db->prof_free.back();
@@ -71,7 +74,7 @@ void prof_begin(ssw_db* db, cudaStream_t st) {
   db->prof_pending.push_back(ev);
 }
 void prof_end(ssw_db* db, cudaStream_t st) {
-  if (!db->profiling || db->prof_pending.empty()) return;
+  if (!db->prof_sampled || db->prof_pending.empty()) return;
   cudaEventRecord(db->prof_pending.back().second, st);
 }
 
@@ -426,6 +429,9 @@ int ssw_db_vectors_device(const ssw_db* db, void** dev_ptr) {
 int ssw_profile_enable(ssw_db* db, int on) {
   SSW_REQUIRE(db != nullptr, "db is null");
   db->profiling = on != 0;
+  db->prof_stride = on > 1 ? on : 1;
+  db->prof_counter = 0;
+  db->prof_sampled = false;
   return SSW_OK;
 }
 
@@ -458,8 +464,13 @@ int ssw_scan_stats(ssw_db* db, int enable, int64_t* list_updates, int64_t* image
     SSW_CUDA(cudaMemset(db->d_scan_stats, 0, 16));
   }
   if (enable && !db->d_scan_stats) {
-    SSW_CUDA(cudaMalloc((void**)&db->d_scan_stats, 16));
-    SSW_CUDA(cudaMemset(db->d_scan_stats, 0, 16));
+#ifdef SSW_TRACE
+    const size_t stats_bytes = 128 + 192 * 16 * 8;      // + the development timeline of every CTA
+#else
+    const size_t stats_bytes = 16;
+#endif
+    SSW_CUDA(cudaMalloc((void**)&db->d_scan_stats, stats_bytes));
+    SSW_CUDA(cudaMemset(db->d_scan_stats, 0, stats_bytes));
   } else if (!enable && db->d_scan_stats) {
     cudaFree(db->d_scan_stats);
     db->d_scan_stats = nullptr;
@@ -468,6 +479,16 @@ int ssw_scan_stats(ssw_db* db, int enable, int64_t* list_updates, int64_t* image
   if (images_offered) *images_offered = (int64_t)v[1];
   return SSW_OK;
 }
+
+#ifdef SSW_TRACE
+// development only: copy the CTA timelines (clock64 stamps, 16 per CTA) of the last traced launch
+int ssw_scan_trace_read(ssw_db* db, long long* out, int n_ctas) {
+  SSW_REQUIRE(db != nullptr && db->d_scan_stats != nullptr && n_ctas <= 192, "tracing is off");
+  SSW_CUDA(cudaDeviceSynchronize());
+  SSW_CUDA(cudaMemcpy(out, reinterpret_cast<long long*>(db->d_scan_stats) + 16, (size_t)n_ctas * 16 * 8, cudaMemcpyDeviceToHost));
+  return SSW_OK;
+}
+#endif
 
 int ssw_set_scan_mode(ssw_db* db, int mode) {
   SSW_REQUIRE(db != nullptr, "db is null");
@@ -538,12 +559,12 @@ static int scan_topk_impl(ssw_db* db, const float* d_queries, int nq, int k, con
     }
     return launch_exchange_merge(db->d_list_keys, db->d_list_dbidx, lists, k, (int64_t)lists * k, nq, k, db->d_gthr,
                                  xc->peers, xc->world, xc->rank, xc->nq_cap, xc->k_cap, xc->epoch, db->d_xchg_timed_out,
-                                 d_out_key, d_out_dbidx, d_out_score, d_out_row, d_out_count, st, use_tc && !db->profiling,
+                                 d_out_key, d_out_dbidx, d_out_score, d_out_row, d_out_count, st, use_tc && !db->prof_sampled,
                                  use_tc ? db->d_cand_cnt : nullptr);
   }
   // after the batched scan the merge is a programmatic dependent launch (the scan triggers it early)
   return launch_merge(db->d_list_keys, db->d_list_dbidx, lists, k, (int64_t)lists * k, nq, k, db->d_gthr,
-                      d_out_key, d_out_dbidx, d_out_score, d_out_row, d_out_count, st, use_tc && !db->profiling,
+                      d_out_key, d_out_dbidx, d_out_score, d_out_row, d_out_count, st, use_tc && !db->prof_sampled,
                       use_tc ? db->d_cand_cnt : nullptr);
 }
 

@@ -58,6 +58,9 @@ struct ssw_db {
   size_t h_stage_bytes = 0;
   // optional per-launch timing of the scan kernel (ssw_profile_enable)
   bool profiling = false;
+  int prof_stride = 1;             // bracket every prof_stride-th scan-kernel launch
+  int64_t prof_counter = 0;
+  bool prof_sampled = false;       // the launch being enqueued is bracketed (no programmatic dependent launch around it)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pending;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_free;
 };

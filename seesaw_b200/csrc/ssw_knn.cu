@@ -2,8 +2,8 @@
 //
 // Replaces   all_pairs = 1. - V @ V.T ; np.argsort(all_pairs, axis=-1)[:, :k+1]
 // (seesaw/knn_graph.py:170-182, compute_exact_knn).  The N x N matrix is never materialised:
-// a CTA keeps a 128-row block of V resident as the A operand (tensor memory in the TS variants, shared
-// memory in the CTA-pair N=256 variant that is the default), streams every row of V through shared
+// a CTA keeps a 128-row block of V resident as the A operand (shared memory in the CTA-pair N=256 kernel that is
+// the default, tensor memory in the single-CTA TS kernel used for dim 768 and large k1), streams every row of V through shared
 // memory as B (TMA, SWIZZLE_128B), accumulates the dot products in TMEM and the four epilogue warps
 // (one thread per output row) turn each accumulator tile into d = fp32(1 - dot) and keep the k1
 // smallest (d, column) pairs of their row — one max tree and one compare per 32 columns in the
@@ -28,7 +28,6 @@ struct KnnArgs {
   int64_t row_begin, row_end;   // output rows [row_begin, row_end)
   int32_t* out_idx;     // [(row_end-row_begin), k1]
   float* out_dist;
-  int debug;            // dev only (SSW_KNN_DEBUG): 1 = epilogue skips the accumulator reads
   unsigned int* wave_sync;  // one counter: TMA producers of all CTAs meet here between row blocks
 };
 
@@ -154,6 +153,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_kernel(const __grid_constan
         }
       }
     }
+    __syncwarp();       // the idle lanes must not reach the closing barrier ahead of lane 0
   } else if (warp == 1) {
     // ===== MMA issuer =====
     TcPipe p(NS);
@@ -228,11 +228,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_kernel(const __grid_constan
         const int64_t col0 = (int64_t)t * NT;
         const uint32_t acc = lane_addr + Cfg::ACC_BASE + as * NT;
         uint32_t va[32], vb[32];
-        if (a.debug & 1) {
-          tc_fence_before();
-          if (a.debug & 2) mbar_arrive_leader(S.tmem_empty + 8 * as); else mbar_arrive(S.tmem_empty + 8 * as);
-          continue;
-        }
         tmem_ld32(acc, va);
         tmem_ld_wait_regs32(va);
 #pragma unroll 1
@@ -271,189 +266,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) knn_kernel(const __grid_constan
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, Cfg::TMEM_ALLOC);
-}
-
-// ------------------------------------------------------------------------------------------
-// K3 on CTA pairs: the same algorithm with tcgen05.mma.cta_group::2.  A pair owns 256 output rows
-// (128 per CTA, A and accumulators in each CTA's own tensor memory); every CTA loads only its 64-row
-// half of each 128-row B tile, so the L2 -> SM traffic that bounds the single-CTA kernel (ncu: 9.3 TB/s
-// of TMA reads at 58 % tensor pipe) is halved.  Barriers: full / tmem_empty / a_ready collect arrivals
-// from both CTAs in the even CTA (the MMA issuer); empty / tmem_full are signalled in both CTAs by
-// multicast commits.
-// ------------------------------------------------------------------------------------------
-template <int DIM, int NS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
-    knn2_kernel(const __grid_constant__ CUtensorMap tmap, const KnnArgs a) {
-  constexpr int NT = 128;                         // B tile rows per MMA (64 per CTA)
-  constexpr int STAGE_BYTES = (NT / 2) * 128;
-  using Cfg = TcCfg<DIM, NT>;
-  constexpr uint32_t IDESC2 = make_idesc_f16(256, NT);
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem;
-  const TcSmem S = tc_carve(smem_raw, NS, STAGE_BYTES, &smem);
-  uint64_t* lists = reinterpret_cast<uint64_t*>(smem + NS * STAGE_BYTES + ((tc_bar_bytes(NS) + 15) / 16) * 16);
-  KnnRowState* states = reinterpret_cast<KnnRowState*>(lists + (size_t)a.k1 * 128);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const bool leader = rank == 0;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap);
-    for (int i = 0; i < NS; ++i) {
-      mbar_init(S.full + 8 * i, 1);
-      mbar_init(S.empty + 8 * i, 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(S.tmem_full + 8 * i, 1);
-      mbar_init(S.tmem_empty + 8 * i, 256);
-    }
-    mbar_init(S.a_ready, 256);
-    fence_mbar_init();
-    fence_proxy_async();
-  }
-  if (warp == 1) tmem_alloc_2sm(S.tmem_ptr, 512);
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  uint32_t tmem;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(S.tmem_ptr));
-
-  const int64_t npairs = gridDim.x / 2, pair = blockIdx.x / 2;
-  const int64_t nblocks2 = (a.row_end - a.row_begin + 255) / 256;
-  const int ntiles = (int)((a.n + NT - 1) / NT);
-
-  if (warp == 0) {
-    // ===== TMA producer (both CTAs: each loads its half of every B tile) =====
-    if (lane == 0) {
-      TcPipe p(NS);
-      for (int64_t b = pair; b < nblocks2; b += npairs) {
-        for (int t = 0; t < ntiles; ++t) {
-          for (int kc = 0; kc < Cfg::KC; ++kc) {
-            mbar_wait_parked(S.empty + 8 * p.stage, p.phase ^ 1);
-            if (leader) mbar_expect_tx(S.full + 8 * p.stage, 2 * STAGE_BYTES);
-            tma_load_2d_2sm(S.stages + p.stage * STAGE_BYTES, &tmap, kc * kTcKChunk, t * NT + (int)rank * (NT / 2),
-                            S.full + 8 * p.stage);
-            p.advance();
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer (even CTA only) =====
-    if (leader) {
-      TcPipe p(NS);
-      uint32_t it = 0, blk_phase = 0;
-      for (int64_t b = pair; b < nblocks2; b += npairs) {
-        mbar_wait_parked(S.a_ready, blk_phase);
-        blk_phase ^= 1;
-        tc_fence_after();
-        for (int t = 0; t < ntiles; ++t, ++it) {
-          const uint32_t as = it & 1;
-          mbar_wait_parked(S.tmem_empty + 8 * as, ((it >> 1) & 1) ^ 1);
-          tc_fence_after();
-          for (int kc = 0; kc < Cfg::KC; ++kc) {
-            mbar_wait_parked(S.full + 8 * p.stage, p.phase);
-            tc_fence_after();
-            if (lane == 0) {
-              const uint64_t bdesc = make_bdesc_sw128(S.stages + p.stage * STAGE_BYTES);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                mma_f16_ts_2sm(tmem + Cfg::ACC_BASE + as * NT, tmem + Cfg::A_BASE + kc * 32 + k * 8, bdesc + 2 * k, IDESC2,
-                               (kc | k) != 0);
-              tc_commit_2sm(S.empty + 8 * p.stage);
-            }
-            __syncwarp();
-            p.advance();
-          }
-          if (lane == 0) tc_commit_2sm(S.tmem_full + 8 * as);
-          __syncwarp();
-        }
-      }
-    }
-  } else {
-    // ===== epilogue: one thread per output row (both CTAs) =====
-    const int q4 = warp & 3;
-    const int lrow = q4 * 32 + lane;
-    const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
-    uint64_t* mylist = lists + lrow;
-    KnnRowState* st = states + lrow;
-    const int k1 = a.k1;
-    uint32_t it = 0;
-    for (int64_t b = pair; b < nblocks2; b += npairs) {
-      const int64_t row = a.row_begin + b * 256 + (int64_t)rank * 128 + lrow;
-      const bool row_ok = row < a.row_end;
-      {
-        const uint4* src = reinterpret_cast<const uint4*>(a.v + (row_ok ? row : 0) * (int64_t)DIM);
-#pragma unroll 1
-        for (int c = 0; c < Cfg::A_COLS / 32; ++c) {
-          uint32_t r[32];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint4 w = row_ok ? __ldg(src + c * 8 + j) : make_uint4(0, 0, 0, 0);
-            r[4 * j] = w.x;
-            r[4 * j + 1] = w.y;
-            r[4 * j + 2] = w.z;
-            r[4 * j + 3] = w.w;
-          }
-          tmem_st32(lane_addr + Cfg::A_BASE + c * 32, r);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive_leader(S.a_ready);
-      }
-      st->cnt = 0;
-      st->maxpos = 0;
-      st->maxkey = ~0ull;
-      float thr = INFINITY, thr_dot = row_ok ? -INFINITY : INFINITY;   // padding rows (zero vectors) skip everything
-      for (int t = 0; t < ntiles; ++t, ++it) {
-        const uint32_t as = it & 1;
-        mbar_wait(S.tmem_full + 8 * as, (it >> 1) & 1);
-        tc_fence_after();
-        const int64_t col0 = (int64_t)t * NT;
-        const uint32_t acc = lane_addr + Cfg::ACC_BASE + as * NT;
-        uint32_t va[32], vb[32];
-        if (a.debug & 1) {
-          tc_fence_before();
-          if (a.debug & 2) mbar_arrive_leader(S.tmem_empty + 8 * as); else mbar_arrive(S.tmem_empty + 8 * as);
-          continue;
-        }
-        tmem_ld32(acc, va);
-        tmem_ld_wait_regs32(va);
-#pragma unroll 1
-        for (int c0 = 0; c0 < NT; c0 += 64) {
-          tmem_ld32(acc + c0 + 32, vb);
-          knn_group(va, thr, thr_dot, st, mylist, k1, col0 + c0, a.n);
-          tmem_ld_wait_regs32(vb);
-          if (c0 + 64 < NT) tmem_ld32(acc + c0 + 64, va);
-          knn_group(vb, thr, thr_dot, st, mylist, k1, col0 + c0 + 32, a.n);
-          if (c0 + 64 < NT) tmem_ld_wait_regs32(va);
-        }
-        tc_fence_before();
-        mbar_arrive_leader(S.tmem_empty + 8 * as);
-      }
-      const int cnt = st->cnt;
-      if (row_ok) {
-        for (int i = 1; i < cnt; ++i) {
-          const uint64_t x = mylist[i * 128];
-          int j = i - 1;
-          while (j >= 0 && mylist[j * 128] > x) {
-            mylist[(j + 1) * 128] = mylist[j * 128];
-            --j;
-          }
-          mylist[(j + 1) * 128] = x;
-        }
-        const int64_t o = (row - a.row_begin) * k1;
-        for (int i = 0; i < k1; ++i) {
-          const uint64_t x = i < cnt ? mylist[i * 128] : 0;
-          a.out_idx[o + i] = i < cnt ? (int32_t)(x & 0xFFFFFFFFu) : -1;
-          a.out_dist[o + i] = i < cnt ? f32_from_ordered((uint32_t)(x >> 32)) : INFINITY;
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  cluster_sync_all();
-  if (warp == 1) tmem_dealloc_2sm(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -559,6 +371,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
         if (a.wave_sync) atomicAdd(a.wave_sync, 1u);       // all loads of this row block are issued
       }
     }
+    __syncwarp();       // the idle lanes must not reach the closing barrier ahead of lane 0
   } else if (warp == 1) {
     // ===== MMA issuer (even CTA only) =====
     if (leader) {
@@ -619,11 +432,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
         const int64_t col0 = (int64_t)t * NT;
         const uint32_t acc = lane_addr + as * NT;
         uint32_t va[32], vb[32];
-        if (a.debug & 1) {
-          tc_fence_before();
-          mbar_arrive_leader(tmem_empty + 8 * as);
-          continue;
-        }
         tmem_ld32(acc, va);
         tmem_ld_wait_regs32(va);
 #pragma unroll 1
@@ -713,23 +521,6 @@ static int launch_knn_t(int sm_count, const KnnArgs& a, cudaStream_t st) {
   return go(knn_kernel<DIM, NT, 8>, 8);
 }
 
-template <int DIM>
-static int launch_knn2_t(int sm_count, const KnnArgs& a, cudaStream_t st) {
-  constexpr int NS = 16;
-  const size_t list_bytes = (size_t)a.k1 * 128 * 8 + 128 * sizeof(KnnRowState);
-  CUtensorMap tmap;
-  int rc = make_tmap_f16_rows(&tmap, a.v, a.n, DIM, 64);       // box = this CTA's 64-row half of a B tile
-  if (rc) return rc;
-  const int64_t nblocks2 = (a.row_end - a.row_begin + 255) / 256;
-  const int grid = 2 * (int)std::min<int64_t>(sm_count / 2, nblocks2);
-  const size_t smem = (size_t)NS * 64 * 128 + ((tc_bar_bytes(NS) + 15) / 16) * 16 + list_bytes + tc_smem_slack;
-  auto kern = knn2_kernel<DIM, NS>;
-  SSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, kTcThreads, smem, st>>>(tmap, a);
-  SSW_LAUNCHED();
-  return SSW_OK;
-}
-
 // SS / N = 256 variant: needs >= 3 B stages next to the resident A block and the candidate lists
 template <int DIM>
 static int launch_knn3_t(int sm_count, const KnnArgs& a, cudaStream_t st, bool* launched) {
@@ -748,10 +539,8 @@ static int launch_knn3_t(int sm_count, const KnnArgs& a, cudaStream_t st, bool* 
   SSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // inter-block meeting point of the producers: one word per launch, allocated and freed in stream order
   unsigned int* sync_word = nullptr;
-  if (!getenv("SSW_KNN_NOSYNC")) {
-    SSW_CUDA(cudaMallocAsync((void**)&sync_word, 128, st));
-    SSW_CUDA(cudaMemsetAsync(sync_word, 0, 4, st));
-  }
+  SSW_CUDA(cudaMallocAsync((void**)&sync_word, 128, st));
+  SSW_CUDA(cudaMemsetAsync(sync_word, 0, 4, st));
   KnnArgs a2 = a;
   a2.wave_sync = sync_word;
   kern<<<grid, kTcThreads, smem, st>>>(tmap, a2, NS);
@@ -767,32 +556,13 @@ static int launch_knn3_t(int sm_count, const KnnArgs& a, cudaStream_t st, bool* 
 }
 
 static int launch_knn(int sm_count, const KnnArgs& a, int dim, cudaStream_t st) {
-  // CTA pairs (tcgen05 cta_group::2) for the dims whose A block leaves room for two 128-column accumulators;
-  // SSW_KNN_1CTA=1 selects the single-CTA kernel (kept for dim 768 and as a cross-check)
-  static const bool one_cta = [] { const char* e = getenv("SSW_KNN_1CTA"); return e && e[0] == '1'; }();
-  static const bool ts_pairs = [] { const char* e = getenv("SSW_KNN_TS"); return e && e[0] == '1'; }();
-  if (!one_cta && !ts_pairs && (dim == 256 || dim == 512)) {
+  // CTA pairs with N = 256 SS MMAs (knn3_kernel) whenever the resident A block, three B stages and the candidate
+  // lists fit in shared memory (dim 256 / 512, any k1 <= 64 at dim 256, k1 <= ~40 at dim 512); otherwise the
+  // single-CTA TS kernel (dim 768, large k1)
+  if (dim == 256 || dim == 512) {
     bool launched = false;
     const int rc = dim == 256 ? launch_knn3_t<256>(sm_count, a, st, &launched) : launch_knn3_t<512>(sm_count, a, st, &launched);
     if (rc || launched) return rc;
-  }
-  if (!one_cta) {
-    if (dim == 256) return launch_knn2_t<256>(sm_count, a, st);
-    if (dim == 512) return launch_knn2_t<512>(sm_count, a, st);
-  }
-  if (getenv("SSW_KNN_N256") && dim == 512) {     // dev experiment: one 256-column accumulator, N = 256 MMAs
-    using Cfg = TcCfg<512, 256, 1>;
-    CUtensorMap tmap;
-    int rc = make_tmap_f16_rows(&tmap, a.v, a.n, 512, 256);
-    if (rc) return rc;
-    const size_t list_bytes = (size_t)a.k1 * 128 * 8 + 128 * sizeof(KnnRowState);
-    const int64_t nblocks = (a.row_end - a.row_begin + 127) / 128;
-    const size_t smem = (size_t)6 * Cfg::STAGE_BYTES + ((tc_bar_bytes(6) + 15) / 16) * 16 + list_bytes + tc_smem_slack;
-    auto kern = knn_kernel<512, 256, 6, 1>;
-    SSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(int)std::min<int64_t>(sm_count, nblocks), kTcThreads, smem, st>>>(tmap, a);
-    SSW_LAUNCHED();
-    return SSW_OK;
   }
   switch (dim) {
     case 256: return launch_knn_t<256, 128>(sm_count, a, st);
@@ -906,8 +676,7 @@ int ssw_knn_build_device(int device, const void* d_vectors_f16, int64_t n, int d
   int rc = ensure_device(device, &sms);
   if (rc) return rc;
   if (row_begin == row_end) return SSW_OK;
-  KnnArgs a{static_cast<const __half*>(d_vectors_f16), n, k1, row_begin, row_end, d_out_idx, d_out_dist, 0, nullptr};
-  if (const char* e = getenv("SSW_KNN_DEBUG")) a.debug = atoi(e);
+  KnnArgs a{static_cast<const __half*>(d_vectors_f16), n, k1, row_begin, row_end, d_out_idx, d_out_dist, nullptr};
   return launch_knn(sms, a, dim, (cudaStream_t)stream);
 }
 

@@ -34,7 +34,7 @@ namespace ssw {
 
 __global__ void lp_step_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                const double* __restrict__ data, const double* __restrict__ x_old,
-                               const double* __restrict__ reg, const double* __restrict__ wsum, double lambda,
+                               const double* __restrict__ lreg, const double* __restrict__ wsum, double lambda,
                                const int32_t* __restrict__ slot, const double* __restrict__ label_values,
                                double* __restrict__ x_new, unsigned long long* diff_max) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -42,7 +42,7 @@ __global__ void lp_step_kernel(int64_t n, const int64_t* __restrict__ indptr, co
   if (i < n) {
     double y = 0.0;
     for (int64_t j = indptr[i]; j < indptr[i + 1]; ++j) y = __dadd_rn(y, __dmul_rn(data[j], x_old[indices[j]]));
-    const double w = __dadd_rn(y, __dmul_rn(lambda, reg[i]));
+    const double w = __dadd_rn(y, lreg[i]);        // lreg = reg_lambda * reg_values, multiplied by the caller
     double v = __ddiv_rn(w, __dadd_rn(wsum[i], lambda));
     const int32_t s = slot[i];
     if (s >= 0) v = label_values[s];
@@ -139,16 +139,29 @@ int ssw_lp_fit(ssw_lp* lp, const int64_t* label_ids, const double* label_values,
                const double* reg_values, const double* start_value, int max_iter, double epsilon, double* out_values,
                int* out_iterations, int* out_converged) {
   SSW_REQUIRE(lp != nullptr && out_values != nullptr, "null argument");
-  SSW_REQUIRE(n_labels >= 0 && (n_labels == 0 || (label_ids != nullptr && label_values != nullptr)), "bad labels");
   SSW_REQUIRE(reg_values != nullptr || lp->reg_lambda == 0.0, "reg_values is required when reg_lambda > 0");
+  // host-side setup exactly as fit_transform (label_propagation.py:45-62), float64 throughout
+  const int64_t n = lp->n;
+  std::vector<double> x0(n, 0.0), lreg(n, 0.0);
+  if (reg_values)
+    for (int64_t i = 0; i < n; ++i) lreg[i] = lp->reg_lambda * reg_values[i];
+  if (start_value) memcpy(x0.data(), start_value, (size_t)n * 8);
+  else if (reg_values) memcpy(x0.data(), reg_values, (size_t)n * 8);
+  return ssw_lp_fit_scaled(lp, label_ids, label_values, n_labels, lreg.data(), x0.data(), max_iter, epsilon, out_values,
+                           out_iterations, out_converged);
+}
+
+int ssw_lp_fit_scaled(ssw_lp* lp, const int64_t* label_ids, const double* label_values, int64_t n_labels,
+                      const double* lambda_reg_values, const double* x0_in, int max_iter, double epsilon,
+                      double* out_values, int* out_iterations, int* out_converged) {
+  SSW_REQUIRE(lp != nullptr && out_values != nullptr && x0_in != nullptr, "null argument");
+  SSW_REQUIRE(n_labels >= 0 && (n_labels == 0 || (label_ids != nullptr && label_values != nullptr)), "bad labels");
+  SSW_REQUIRE(lambda_reg_values != nullptr || lp->reg_lambda == 0.0, "the prior term is required when reg_lambda > 0");
   SSW_REQUIRE(max_iter >= 0, "max_iter must be non-negative");
   SSW_CUDA(cudaSetDevice(lp->device));
   const int64_t n = lp->n;
-  // host-side setup exactly as fit_transform (label_propagation.py:45-62)
-  std::vector<double> x0(n, 0.0), reg(n, 0.0);
-  if (reg_values) memcpy(reg.data(), reg_values, (size_t)n * 8);
-  if (start_value) memcpy(x0.data(), start_value, (size_t)n * 8);
-  else if (reg_values) memcpy(x0.data(), reg_values, (size_t)n * 8);
+  std::vector<double> x0(x0_in, x0_in + n), reg(n, 0.0);
+  if (lambda_reg_values) memcpy(reg.data(), lambda_reg_values, (size_t)n * 8);
   std::vector<int32_t> slot(n, -1);
   for (int64_t t = 0; t < n_labels; ++t) {
     SSW_REQUIRE(label_ids[t] >= 0 && label_ids[t] < n, "label id out of range");

@@ -57,6 +57,16 @@ struct ScanTcArgs {
   unsigned long long* stats; // [2] list updates / images offered to a list, summed over the grid (null = not counted)
 };
 
+// Development-only timeline (make EXTRA=-DSSW_TRACE): clock64 stamps of one CTA's phases into a.stats[16 + ...]
+#ifdef SSW_TRACE
+#define SSW_TR(slot, cond)                                                                                  \
+  do {                                                                                                      \
+    if (a.stats && (cond)) reinterpret_cast<long long*>(a.stats)[16 + blockIdx.x * 16 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define SSW_TR(slot, cond) do { } while (0)
+#endif
+
 constexpr int kTcMaxK = 64;   // per-query list length the batched epilogue keeps in shared memory
 
 // ------------------------------------------------------------------------------------------
@@ -184,15 +194,20 @@ __device__ __forceinline__ uint64_t scan_tc_offer(const QShared& Q, const ScanTc
     Q.keys[mp * 64 + q] = key;
     Q.img[mp * 64 + q] = img;
   }
+  // new minimum of the full list: eight independent loads in flight, then a compare chain
   uint64_t mk = ~0ull;
   int mp = 0;
-#pragma unroll 2
-  for (int s = 0; s < k; ++s) {
-    const uint64_t x = Q.keys[s * 64 + q];
-    if (x < mk) {
-      mk = x;
-      mp = s;
-    }
+#pragma unroll 1
+  for (int s0 = 0; s0 < k; s0 += 8) {
+    uint64_t x[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) x[u] = s0 + u < k ? Q.keys[(s0 + u) * 64 + q] : ~0ull;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (x[u] < mk) {
+        mk = x[u];
+        mp = s0 + u;
+      }
   }
   Q.minpos[q] = mp;
   // the threshold warp raises Q.thr concurrently: merge with an atomic max
@@ -205,22 +220,28 @@ __device__ __forceinline__ uint64_t scan_tc_offer(const QShared& Q, const ScanTc
 // NGP >= k groups (CTA c in group c mod NGP): the smallest of the group maxima is a score that at least
 // k distinct images reach, hence a valid lower bound of the final k-th best — far tighter than a single
 // CTA's own k-th best early in the scan, when almost every image would otherwise enter its CTA's list
-// (expected list updates per query and CTA drop from k*ln(n/k) to a handful).  One warp per CTA sweeps
-// the queries for the whole life of the kernel and raises the thresholds the epilogue warps read each
-// tile; it never touches the epilogue's critical path.
-__device__ __forceinline__ void scan_tc_threshold_warp(const QShared& Q, const ScanTcArgs& a, int lane, int n_epi = 4) {
+// (expected list updates per query and CTA drop from k*ln(n/k) to a handful).
+// What a list update costs is serial work of one epilogue thread, and how many there are depends on how STALE
+// the bound is (a CTA timeline showed the first half of a 66-tile range running 25 % slower than the second:
+// every CTA used to re-pool all 64 queries from the 38 KB of published bests, ~12 us per sweep under a
+// saturated memory system).  So the pooling is split: CTA b pools only the 8 queries of group (b mod 8) — one
+// batch of loads, ~1.5 us — and folds the result into the shared bound g_thr; EVERY CTA's threshold warp then
+// just reads the 64 shared bounds (two coalesced 8-byte loads per lane) each round and raises the thresholds
+// the epilogue warps read.  The warp runs for the whole life of the kernel, off the epilogue's critical path.
+__device__ __forceinline__ void scan_tc_threshold_warp(const QShared& Q, const ScanTcArgs& a, int lane, int n_epi) {
   constexpr int VMAX = 6;                       // up to 192 CTAs
+  constexpr int QB = 8;                         // queries pooled per CTA (loads in flight together)
   const int G = gridDim.x;
   int ngp = 1;
   while (ngp < a.k) ngp <<= 1;                  // k <= 64
   const bool pooled = G >= ngp && G <= 32 * VMAX;
+  const int n_groups = (a.nq + QB - 1) / QB;
+  const int q0 = ((int)blockIdx.x % n_groups) * QB;
   volatile int* done = Q.done;
-  constexpr int QB = 8;                         // queries whose loads are in flight together
+  uint64_t seen0 = 0, seen1 = 0;                // what this lane last folded into Q.thr[lane], Q.thr[lane + 32]
   while (*done < n_epi) {
-#pragma unroll 1
-    for (int q0 = 0; q0 < a.nq && *done < n_epi; q0 += QB) {      // leave promptly once the epilogue is through
+    if (pooled) {
       uint32_t v[QB][VMAX];
-      uint64_t g[QB];
 #pragma unroll
       for (int u = 0; u < QB; ++u) {
         const int q = q0 + u;
@@ -228,27 +249,30 @@ __device__ __forceinline__ void scan_tc_threshold_warp(const QShared& Q, const S
         for (int m = 0; m < VMAX; ++m) {
           const int c = lane + 32 * m;
           v[u][m] = 0u;
-          if (pooled && q < a.nq && c < G)
+          if (q < a.nq && c < G)
             asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v[u][m]) : "l"(a.pub + (size_t)q * G + c) : "memory");
         }
-        g[u] = 0;
-        if (lane == 0 && q < a.nq) g[u] = ld_relaxed_u64(a.g_thr + q);
       }
 #pragma unroll
       for (int u = 0; u < QB; ++u) {
         const int q = q0 + u;
         if (q >= a.nq) break;
-        uint32_t t = 0;
-        if (pooled) t = pooled_group_min<VMAX>(v[u], ngp, lane);
-        if (lane == 0) {
-          const uint64_t tkey = (uint64_t)t << 32;
-          if (blockIdx.x == 0 && tkey > g[u]) atomicMax(reinterpret_cast<unsigned long long*>(a.g_thr + q), (unsigned long long)tkey);
-          const uint64_t best = tkey > g[u] ? tkey : g[u];
-          if (best != 0) atomicMax(reinterpret_cast<unsigned long long*>(Q.thr + q), (unsigned long long)best);
-        }
+        const uint32_t t = pooled_group_min<VMAX>(v[u], ngp, lane);
+        if (lane == 0 && t != 0) atomicMax(reinterpret_cast<unsigned long long*>(a.g_thr + q), (unsigned long long)t << 32);
       }
     }
-    if (*done < n_epi) __nanosleep(1000);
+    const uint64_t g0 = lane < a.nq ? ld_relaxed_u64(a.g_thr + lane) : 0ull;
+    const uint64_t g1 = lane + 32 < a.nq ? ld_relaxed_u64(a.g_thr + lane + 32) : 0ull;
+    if (g0 > seen0) {
+      atomicMax(reinterpret_cast<unsigned long long*>(Q.thr + lane), (unsigned long long)g0);
+      seen0 = g0;
+    }
+    if (g1 > seen1) {
+      atomicMax(reinterpret_cast<unsigned long long*>(Q.thr + lane + 32), (unsigned long long)g1);
+      seen1 = g1;
+    }
+    __syncwarp();
+    if (*done < n_epi) __nanosleep(200);
   }
 }
 
@@ -312,6 +336,21 @@ __device__ __forceinline__ void scan_tc8_group(Epi1State& st, const Epi1Ctx& cx,
     sa[2 * i] = __uint_as_float(v[4 * i]) + __uint_as_float(v[4 * i + 2]);
     sa[2 * i + 1] = __uint_as_float(v[4 * i + 1]) + __uint_as_float(v[4 * i + 3]);
   }
+  // Fast path (almost every group once the thresholds are up): if none of the warp's 256 scores reaches its
+  // query's threshold, no image can become a candidate THROUGH these columns — a running maximum below the
+  // threshold is never looked at — so nothing is folded and only the image boundaries are walked (one vote each).
+  // An image whose maximum does reach the threshold has its arg-max column in a group that takes the full path
+  // below, with the exact (max, lowest column) bookkeeping.
+  {
+    const float mx = fmaxf(fmaxf(fmaxf(sa[0], sa[1]), fmaxf(sa[2], sa[3])), fmaxf(fmaxf(sa[4], sa[5]), fmaxf(sa[6], sa[7])));
+    if (!__any_sync(0xffffffffu, mx >= st.thr)) {
+      while (em) {
+        em &= em - 1;
+        scan_tc8_boundary(st, cx, Q, a);
+      }
+      return;
+    }
+  }
   const int cb = colbase + 2 * cx.j;
   float ma;
   int ia;
@@ -370,6 +409,7 @@ __global__ void __launch_bounds__(kScanTc8Threads, 1) scan_tc8_kernel(const __gr
   const TcSmem S = tc_carve(smem_raw, NS, Cfg::STAGE_BYTES, &smem);
   uint8_t* after = smem + NS * Cfg::STAGE_BYTES + ((tc_bar_bytes(NS) + 15) / 16) * 16;
   const QShared Q = qshared_carve(after, a.k);
+  SSW_TR(0, threadIdx.x == 0);
   if (threadIdx.x < 64) {
     Q.thr[threadIdx.x] = 0;
     Q.cnt[threadIdx.x] = 0;
@@ -383,8 +423,10 @@ __global__ void __launch_bounds__(kScanTc8Threads, 1) scan_tc8_kernel(const __gr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // everything above overlapped the tail of the query-preparation kernel (programmatic dependent launch); from
   // here on its outputs (A image, scales, zeroed thresholds / published bests) are read
+  SSW_TR(1, threadIdx.x == 0);
   pdl_launch_dependents();
   pdl_wait();
+  SSW_TR(2, threadIdx.x == 0);
 
   const int img0 = a.part[blockIdx.x * kScanWarps], img1 = a.part[(blockIdx.x + 1) * kScanWarps];
   const int64_t r_begin = a.row_ptr[img0], r_end = a.row_ptr[img1];
@@ -394,6 +436,7 @@ __global__ void __launch_bounds__(kScanTc8Threads, 1) scan_tc8_kernel(const __gr
   if (warp == 0) {
     if (lane == 0) {
       TcPipe p(NS);
+      SSW_TR(3, true);
       for (int t = 0; t < ntiles; ++t) {
         for (int kc = 0; kc < Cfg::KC; ++kc) {
           mbar_wait_parked(S.empty + 8 * p.stage, p.phase ^ 1);
@@ -402,12 +445,16 @@ __global__ void __launch_bounds__(kScanTc8Threads, 1) scan_tc8_kernel(const __gr
                       S.full + 8 * p.stage);
           p.advance();
         }
+        SSW_TR(4, t == 0);
       }
+      SSW_TR(5, true);
     }
+    __syncwarp();       // the idle lanes must not reach the closing __syncthreads ahead of lane 0
   } else if (warp == 1) {
     TcPipe p(NS);
     mbar_wait_parked(S.a_ready, 0);
     tc_fence_after();
+    SSW_TR(6, lane == 0);
     for (int t = 0; t < ntiles; ++t) {
       const uint32_t as = NACC == 2 ? (t & 1) : 0;
       mbar_wait_parked(S.tmem_empty + 8 * as, ((NACC == 2 ? (t >> 1) : t) & 1) ^ 1);
@@ -428,7 +475,9 @@ __global__ void __launch_bounds__(kScanTc8Threads, 1) scan_tc8_kernel(const __gr
       }
       if (lane == 0) tc_commit(S.tmem_full + 8 * as);
       __syncwarp();
+      SSW_TR(7, lane == 0 && t == 0);
     }
+    SSW_TR(8, lane == 0);
   } else if (warp == 10) {
     scan_tc_threshold_warp(Q, a, lane, 8);
   } else {
@@ -436,16 +485,30 @@ __global__ void __launch_bounds__(kScanTc8Threads, 1) scan_tc8_kernel(const __gr
     const int q4 = warp & 3, h = (warp - 2) >> 2;
     const uint32_t lane_addr = tmem + ((uint32_t)(q4 * 32) << 16);
     const int k = a.k;
-    {      // A operand: the two warps of a quarter copy half of the columns of its 32 TMEM lanes each, two
-           // 32-column chunks per round (16 coalesced 16-byte loads in flight, then two tcgen05.st)
+    // ---- this warp's 8 exclusion bitmaps, CTA slice: loads issued now, stored after the A operand copy (their
+    //      latency hides under it instead of adding 8 dependent round trips before the first tile)
+    const int slice_base = img0 >> 5;
+    const int nw = (a.excl && a.excl_slice_words > 0 && img1 > img0) ? ((img1 - 1) >> 5) - slice_base + 1 : 0;
+    uint32_t xs[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int qs = q4 * 16 + h * 8 + i, w = lane + 32 * u;
+        xs[i][u] = (qs < a.nq && w < nw) ? __ldg(a.excl + (size_t)qs * a.excl_words + slice_base + w) : 0u;
+      }
+    {      // A operand: the two warps of a quarter copy half of the columns of its 32 TMEM lanes each; all of a
+           // warp's 16-byte pieces are requested at once (coalesced: a piece of 32 lanes is 512 contiguous bytes)
       constexpr int NCH = Cfg::A_COLS / 32;           // 32-column chunks of the operand
-      static_assert(NCH % 4 == 0, "chunks must split evenly over two warps, two per round");
+      constexpr int PER = NCH / 2;                    // chunks per warp
+      constexpr int RND = PER > 4 ? 3 : PER;          // chunks per round (registers: 32 per chunk)
+      static_assert(NCH % 2 == 0 && PER % RND == 0, "chunks must split evenly over two warps and the rounds");
       const uint4* src = reinterpret_cast<const uint4*>(a.a_img) + q4 * 32 + lane;
 #pragma unroll 1
-      for (int c = h * (NCH / 2); c < (h + 1) * (NCH / 2); c += 2) {
-        uint32_t rr[2][32];
+      for (int c = h * PER; c < (h + 1) * PER; c += RND) {
+        uint32_t rr[RND][32];
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
+        for (int u = 0; u < RND; ++u)
 #pragma unroll
           for (int x = 0; x < 8; ++x) {
             const uint4 w = __ldg(src + (size_t)((c + u) * 8 + x) * 128);
@@ -454,21 +517,24 @@ __global__ void __launch_bounds__(kScanTc8Threads, 1) scan_tc8_kernel(const __gr
             rr[u][4 * x + 2] = w.z;
             rr[u][4 * x + 3] = w.w;
           }
-        tmem_st32(lane_addr + Cfg::A_BASE + c * 32, rr[0]);
-        tmem_st32(lane_addr + Cfg::A_BASE + (c + 1) * 32, rr[1]);
+#pragma unroll
+        for (int u = 0; u < RND; ++u) tmem_st32(lane_addr + Cfg::A_BASE + (c + u) * 32, rr[u]);
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(S.a_ready);
     }
-    const int slice_base = img0 >> 5;
-    if (a.excl && a.excl_slice_words > 0 && img1 > img0) {
-      const int nw = ((img1 - 1) >> 5) - slice_base + 1;
+    if (nw > 0) {
+#pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int qs = q4 * 16 + h * 8 + i;
-        if (qs >= a.nq) break;
-        for (int w = lane; w < nw; w += 32)
-          Q.excl[qs * a.excl_slice_words + w] = __ldg(a.excl + (size_t)qs * a.excl_words + slice_base + w);
+        if (qs < a.nq) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+            if (lane + 32 * u < nw) Q.excl[qs * a.excl_slice_words + lane + 32 * u] = xs[i][u];
+          for (int w = lane + 64; w < nw; w += 32)      // slices beyond 2048 images per CTA: plain loop
+            Q.excl[qs * a.excl_slice_words + w] = __ldg(a.excl + (size_t)qs * a.excl_words + slice_base + w);
+        }
       }
       __syncwarp();
     }
@@ -514,6 +580,8 @@ __global__ void __launch_bounds__(kScanTc8Threads, 1) scan_tc8_kernel(const __gr
       st.thr = thr_to_acc(Q.thr[qA], cx.scale);
       mbar_wait(S.tmem_full + 8 * as, (NACC == 2 ? (t >> 1) : t) & 1);
       tc_fence_after();
+      SSW_TR(9, warp == 2 && lane == 0 && t == 0);
+      SSW_TR(12, warp == 2 && lane == 0 && t == ntiles / 2);
       const uint32_t acc = lane_addr + half_addr + Cfg::ACC_BASE + as * NT;
       const int colbase = (int)(row0 - r_begin);
       if constexpr (NACC == 1) {
@@ -553,41 +621,59 @@ __global__ void __launch_bounds__(kScanTc8Threads, 1) scan_tc8_kernel(const __gr
       }
     }
     __syncwarp();
+    SSW_TR(10, warp == 2 && lane == 0);
     if (lane == 0) atomicAdd(Q.done, 1);
     if (a.stats && lane < 8 && q4 * 16 + h * 8 + lane < a.nq) {
       atomicAdd(a.stats, (unsigned long long)Q.upd[q4 * 16 + h * 8 + lane]);
       atomicAdd(a.stats + 1, (unsigned long long)Q.upd[64 + q4 * 16 + h * 8 + lane]);
     }
     // ---- publish: of every query's list only the entries that still reach the shared bound, appended to the
-    //      query's compacted candidate array (one atomic per warp and 32 slots) — the merge reads tens to
-    //      hundreds of keys per query instead of grid x k slots
+    //      query's compacted candidate array — the merge reads tens to hundreds of keys per query instead of
+    //      grid x k slots.  The warp's 8 queries reserve their ranges with 8 atomics in flight together (one
+    //      round trip, not eight).
     {
       const int nqw = min(8, a.nq - (q4 * 16 + h * 8));
       const int64_t cap = (int64_t)gridDim.x * k;
-      for (int qq = 0; qq < nqw; ++qq) {
+      uint64_t key[8][2];
+      uint32_t mask[8][2];
+      int n_pass = 0;                                   // lane qq: entries of query qq that pass
+#pragma unroll
+      for (int qq = 0; qq < 8; ++qq) {
         const int qi = q4 * 16 + h * 8 + qq;
-        const int cntq = Q.cnt[qi];
-        const uint64_t thr = ld_relaxed_u64(a.g_thr + qi);
-        for (int s0 = 0; s0 < cntq; s0 += 32) {
-          const int sl = s0 + lane;
-          const uint64_t key = sl < cntq ? Q.keys[sl * 64 + qi] : 0ull;
-          const bool pass = key != 0ull && key >= thr;
-          const uint32_t mask = __ballot_sync(0xffffffffu, pass);
-          if (mask == 0) continue;
-          int base = 0;
-          if (lane == 0) base = atomicAdd(a.cand_cnt + qi, __popc(mask));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (pass) {
-            const int64_t o = (int64_t)qi * cap + base + __popc(mask & ((1u << lane) - 1u));
-            a.cand_keys[o] = key;
-            a.cand_dbidx[o] = __ldg(a.img_dbidx + Q.img[sl * 64 + qi]);
+        const int cntq = qq < nqw ? Q.cnt[qi] : 0;
+        const uint64_t thr = qq < nqw ? ld_relaxed_u64(a.g_thr + qi) : ~0ull;
+        int tot = 0;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {                   // k <= 64: two slots per lane
+          const int sl = lane + 32 * u;
+          key[qq][u] = sl < cntq ? Q.keys[sl * 64 + qi] : 0ull;
+          mask[qq][u] = __ballot_sync(0xffffffffu, key[qq][u] != 0ull && key[qq][u] >= thr);
+          tot += __popc(mask[qq][u]);
+        }
+        if (lane == qq) n_pass = tot;
+      }
+      int base = 0;
+      if (lane < nqw && n_pass > 0) base = atomicAdd(a.cand_cnt + q4 * 16 + h * 8 + lane, n_pass);
+#pragma unroll
+      for (int qq = 0; qq < 8; ++qq) {
+        const int qi = q4 * 16 + h * 8 + qq;
+        int o = __shfl_sync(0xffffffffu, base, qq);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if ((mask[qq][u] >> lane) & 1u) {
+            const int64_t at = (int64_t)qi * cap + o + __popc(mask[qq][u] & ((1u << lane) - 1u));
+            a.cand_keys[at] = key[qq][u];
+            a.cand_dbidx[at] = __ldg(a.img_dbidx + Q.img[(lane + 32 * u) * 64 + qi]);
           }
+          o += __popc(mask[qq][u]);
         }
       }
     }
   }
+  SSW_TR(11, warp == 2 && lane == 0);
   tc_fence_before();
   __syncthreads();
+  SSW_TR(13, threadIdx.x == 0);
   if (warp == 1) tmem_dealloc(tmem, Cfg::TMEM_ALLOC);
 }
 
@@ -612,7 +698,7 @@ static int launch_scan_tc_t(ssw_db* db, const ScanTcArgs& a, cudaStream_t st) {
   prof_begin(db, st);      // times the scan kernel alone (not the query preparation)
   // programmatic dependent launch: the kernel's set-up runs under the tail of the preparation kernel (an event
   // record between the two would serialise them, so not while profiling)
-  SSW_CUDA(launch_kernel(kern, dim3(db->scan_grid), dim3(kScanTc8Threads), smem, st, !db->profiling, tmap, a2));
+  SSW_CUDA(launch_kernel(kern, dim3(db->scan_grid), dim3(kScanTc8Threads), smem, st, !db->prof_sampled, tmap, a2));
   prof_end(db, st);
   SSW_LAUNCHED();
   return SSW_OK;

@@ -122,9 +122,9 @@ class PatchDatabase:
         """0 auto, 1 streaming SIMT kernel, 2 tcgen05 batched kernel."""
         check(lib.ssw_set_scan_mode(self._h, int(mode)))
 
-    def profile(self, on=True):
-        """Bracket every scan-kernel launch with CUDA events (read back with :meth:`profile_read`)."""
-        check(lib.ssw_profile_enable(self._h, int(bool(on))))
+    def profile(self, on=True, every=1):
+        """Bracket every ``every``-th scan-kernel launch with CUDA events (read back with :meth:`profile_read`)."""
+        check(lib.ssw_profile_enable(self._h, int(every) if on else 0))
 
     def profile_read(self):
         """(summed scan-kernel milliseconds, launches) since the last read."""

@@ -8,7 +8,8 @@ The weight matrix is what the reference's ``get_weight_matrix`` (seesaw/knn_grap
 edge table of ``seesaw_b200.knn_graph.compute_exact_knn`` — that one-time scipy step stays on the host.  The
 per-feedback-round loop (``_step``: one SpMV, a scale and a clamp per iteration, up to max_iter iterations
 over ~2·k·N non-zeros) runs as CUDA kernel K6 in IEEE float64 with scipy's summation order, so the returned
-vector is bit-identical to the reference's."""
+vector is bit-identical to the reference's.  The rankers that drive it (research/knn_methods.py, out of this build's
+scope) are used as they are: :func:`use_in_reference` rebinds the one class they instantiate."""
 from __future__ import annotations
 
 import ctypes as C
@@ -49,21 +50,36 @@ class B200LabelPropagation:
             pass
 
     def fit_transform(self, *, label_ids, label_values, reg_values=None, start_value=None):
+        """label_propagation.py:45-83.  The prior term ``reg_lambda * reg_values`` is formed HERE with numpy, i.e. in
+        the dtype of ``reg_values`` exactly as the reference's ``_step`` forms it (:31 — float32 priors from
+        ``index.score`` give a float32 product that is then added in float64), and handed to the kernel ready-made."""
+        n = self.n
         if reg_values is not None:
-            assert reg_values.shape[0] == self.n                 # :47
+            assert reg_values.shape[0] == n                      # :47
             self.reg_values = reg_values
         else:
             assert self.reg_lambda == 0                          # :50
-            self.reg_values = np.zeros(self.n)
+            self.reg_values = np.zeros(n)
+        if start_value is not None:                              # :53-58
+            x0 = start_value.copy()
+        elif reg_values is not None:
+            x0 = self.reg_values.copy()
+        else:
+            x0 = np.zeros(n)
         ids = np.ascontiguousarray(np.asarray(label_ids).reshape(-1), dtype=np.int64)
+        x0[ids] = label_values                                   # :60 (in x0's own dtype, like the reference)
         vals = np.ascontiguousarray(np.broadcast_to(np.asarray(label_values, dtype=np.float64), ids.shape))
-        reg = None if reg_values is None else np.ascontiguousarray(reg_values, dtype=np.float64)
-        start = None if start_value is None else np.ascontiguousarray(start_value, dtype=np.float64)
-        out = np.empty(self.n, np.float64)
+        lreg = np.ascontiguousarray(np.asarray(self.reg_lambda * self.reg_values, dtype=np.float64).reshape(-1))
+        x0 = np.ascontiguousarray(x0, dtype=np.float64).reshape(-1)
+        out = np.empty(n, np.float64)
         it, conv = C.c_int(), C.c_int()
-        check(lib.ssw_lp_fit(self._h, ptr(ids), ptr(vals), len(ids), ptr(reg), ptr(start), int(self.max_iter),
-                             float(self.epsilon), ptr(out), C.byref(it), C.byref(conv)))
+        check(lib.ssw_lp_fit_scaled(self._h, ptr(ids), ptr(vals), len(ids), ptr(lreg), ptr(x0), int(self.max_iter),
+                                    float(self.epsilon), ptr(out), C.byref(it), C.byref(conv)))
         self.iterations, self.converged = it.value, bool(conv.value)
+        # every iterate is a weighted average of neighbours and prior (:35-40); the reference asserts it per step
+        low, high = min(0, self.reg_values.min()), max(1., self.reg_values.max())
+        assert (out >= low).all(), "averaged scores should lie at or above 0"
+        assert (out <= high).all(), "averaged scores should lie at or below 1"
         if self.converged and self.verbose > 0:
             print(f"prop. converged after {it.value} iterations")
         if not self.converged:
@@ -71,70 +87,12 @@ class B200LabelPropagation:
         return out
 
 
-def normalize_scores(scores, epsilon):
-    """research/knn_methods.py:87-95: affine map of the scores onto [epsilon, 1 - epsilon] (all equal -> 0.5)."""
-    assert epsilon < 0.5
-    lo, hi = scores.min(), scores.max()
-    if hi - lo == 0:
-        return scores - scores + 0.5
-    return (scores - lo) / (hi - lo) * (1 - 2 * epsilon) + epsilon
-
-
-class B200LabelPropagationRanker:
-    """The ``knn_model`` of KnnProp2 (seesaw/loops/graph_based.py:70-113) — LabelPropagationRanker2 with its base
-    class (research/knn_methods.py:97-199): prior scores from the text query, user labels clamped, propagation over
-    the kNN graph on the GPU (:class:`B200LabelPropagation`), ``top_k`` over the unlabeled rows.  Same constructor
-    keywords and methods; ``top_k`` breaks exact score ties by ascending row (the reference's argsort is unstable)."""
-
-    def __init__(self, *, weight_matrix, normalize_scores, sigmoid_before_propagate, calib_a, calib_b, prior_weight,
-                 normalize_epsilon=None, verbose=0, device=0, lp_factory=None, **other):
-        self.nvecs = weight_matrix.shape[0]
-        self.normalize_scores = normalize_scores
-        if normalize_scores:
-            assert normalize_epsilon is not None
-            self.epsilon = normalize_epsilon
-        self.calib_a, self.calib_b, self.prior_weight = calib_a, calib_b, prior_weight
-        self.sigmoid_before_propagate = sigmoid_before_propagate
-        self.is_labeled = np.zeros(self.nvecs)
-        self.labels = np.zeros(self.nvecs)
-        self.prior_scores = None
-        self._current_scores = None
-        self.weight_matrix = weight_matrix
-        make = lp_factory or (lambda **kw: B200LabelPropagation(device=device, **kw))
-        self.lp = make(reg_lambda=prior_weight, weight_matrix=weight_matrix, max_iter=300, verbose=verbose)   # :186-187
-
-    def set_base_scores(self, init_scores):
-        assert self.nvecs == init_scores.shape[0]
-        if self.normalize_scores:
-            init_scores = normalize_scores(init_scores, epsilon=self.epsilon)
-        if self.sigmoid_before_propagate:
-            from scipy.special import expit          # the reference's sigmoid (research/knn_methods.py:6)
-            init_scores = expit(self.calib_a * (init_scores + self.calib_b))
-        self.prior_scores = init_scores
-        if self.is_labeled.sum() == 0:                      # no labels yet: nothing to propagate (:136-139)
-            self._current_scores = self.prior_scores
-        else:
-            self._current_scores = self._propagate(self.prior_scores)
-
-    def _propagate(self, scores):
-        ids = np.flatnonzero(self.is_labeled.reshape(-1))
-        return self.lp.fit_transform(label_ids=ids, label_values=self.labels.reshape(-1)[ids],
-                                     reg_values=self.prior_scores, start_value=scores)
-
-    def update(self, idxs, labels):
-        for idx, label in zip(idxs, labels):
-            label = float(label)
-            assert np.isclose(label, 0) or np.isclose(label, 1)
-            self.labels[int(idx)] = label
-            self.is_labeled[int(idx)] = 1
-        if (self.labels[self.is_labeled > 0] == 0).sum() > 0:    # the reference waits for a first negative (:153-158)
-            self._current_scores = self._propagate(self.prior_scores)
-
-    def current_scores(self):
-        return self._current_scores
-
-    def top_k(self, k, unlabeled_only=True):
-        subset = np.flatnonzero(self.is_labeled < 1) if unlabeled_only else np.arange(self.nvecs)
-        raw = self.current_scores()
-        top = subset[np.argsort(-raw[subset], kind="stable")[:k]]
-        return top, raw[top]
+def use_in_reference():
+    """Inside the reference's environment: make its label-propagation rankers run their loop on the GPU.
+    ``LabelPropagationRanker2`` (the knn_model of KnnProp2, seesaw/research/knn_methods.py:176-199) builds
+    ``LabelPropagation(reg_lambda=, weight_matrix=, max_iter=, verbose=)`` from its module's namespace; rebinding that
+    one name swaps the loop and nothing else.  Returns the previous binding."""
+    import seesaw.research.knn_methods as km       # noqa: raises outside the reference's environment
+    previous = km.LabelPropagation
+    km.LabelPropagation = B200LabelPropagation
+    return previous
