@@ -199,10 +199,16 @@ int ssw_topk_from_scores(ssw_db* db, const float* scores, const uint8_t* row_mas
  * for rows [row_begin,row_end) of vectors [n, dim]: the k1 = min(n_neighbors+1, n) columns j
  * minimising (fp32(1 - dot(i,j)), j), self included when it ranks.  out_idx/out_dist are
  * [(row_end-row_begin), k1] host buffers.  The caller runs post_process_graph_df unchanged
- * (knn_graph.py:142-168).  dtype_in fp32 input is rounded to fp16 for the tensor cores
- * (exact for fp16-valued data). */
+ * (knn_graph.py:142-168).  The tensor cores multiply fp16 values.  For float32 input that is not
+ * fp16-representable they only PROPOSE candidates (k1 + max(16, k1), at most SSW_MAX_KNN_K1); the distances are then
+ * recomputed from the float32 rows, the first k1 accepted when an error bound proves no other column can rank among
+ * them, and rows that cannot be certified (near-duplicates) re-scanned against all columns in float32 — the result
+ * is the float32 neighbour list the reference computes, under column tie-breaking (ssw_knn_exact.cu). */
 int ssw_knn_build(int device, const void* vectors, int dtype_in, int64_t n, int dim, int k1,
                   int64_t row_begin, int64_t row_end, int32_t* out_idx, float* out_dist);
+/* After ssw_knn_build / ssw_knn_graph on this thread: rows whose candidates were re-ranked in float32, rows of those
+ * that needed the full float32 re-scan, and rho = max_i ||v_i - fp16(v_i)|| (0: the fp16 pass was already exact). */
+int ssw_knn_exact_stats(int64_t* rows_refined, int64_t* rows_rescanned, double* rho);
 /* d_vectors_f16: [n, dim] fp16 already in HBM; outputs device [(row_end-row_begin), k1]. */
 int ssw_knn_build_device(int device, const void* d_vectors_f16, int64_t n, int dim, int k1,
                          int64_t row_begin, int64_t row_end, int32_t* d_out_idx, float* d_out_dist,

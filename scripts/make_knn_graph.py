@@ -28,8 +28,12 @@ def main(argv=None):
     assert os.path.exists(inpath)
     outpath = os.path.expandvars(args.outputpath)
     assert not os.path.exists(outpath), "output path already exists."
-    col = pq.read_table(inpath, columns=[args.column]).column(args.column).to_pylist()
-    vectors = np.ascontiguousarray(np.asarray(col, dtype=np.float32))
+    # flatten the Arrow list column without materialising Python objects (a 1M x 512 column is 5e8 of them)
+    col = pq.read_table(inpath, columns=[args.column]).column(args.column).combine_chunks()
+    n = len(col)
+    flat = col.flatten().to_numpy(zero_copy_only=False)
+    assert n > 0 and flat.shape[0] % n == 0, "ragged vector column"
+    vectors = np.ascontiguousarray(flat.reshape(n, flat.shape[0] // n), dtype=np.float32)
     knng, _ = KNNGraph.from_vectors(vectors, n_neighbors=args.k, device=args.device)
     knng.save(outpath, overwrite=True)
     return knng

@@ -71,6 +71,7 @@ SIGNATURES = {
     "ssw_score_all": (C.c_int, [_p, _p, _p]),
     "ssw_score_all_device": (C.c_int, [_p, _p, _p, _p]),
     "ssw_knn_build": (C.c_int, [C.c_int, _p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64, _p, _p]),
+    "ssw_knn_exact_stats": (C.c_int, [_i64p, _i64p, C.POINTER(C.c_double)]),
     "ssw_knn_build_device": (C.c_int, [C.c_int, _p, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64, _p, _p, _p]),
     "ssw_knn_graph": (C.c_int, [C.c_int, _p, C.c_int, C.c_int64, C.c_int, C.c_int, _p, _p, _p, _p, C.c_int64, _i64p]),
     "ssw_knn_edges_workspace_bytes": (C.c_int, [C.c_int64, _i64p]),

@@ -300,7 +300,7 @@ int ssw_db_destroy(ssw_db* db) {
   cudaFree(db->d_boxes);
   cudaFree(db->d_zoom);
   cudaFree(db->d_exact);
-  cudaFree(db->d_xchg_timed_out);
+  if (db->d_xchg_timed_out) cudaFreeHost(db->d_xchg_timed_out);
   cudaFree(db->d_scan_stats);
   cudaFree(db->d_tc_ws);
   cudaFree(db->d_list_keys);
@@ -553,9 +553,9 @@ static int scan_topk_impl(ssw_db* db, const float* d_queries, int nq, int k, con
     }
   }
   if (xc) {
-    if (!db->d_xchg_timed_out) {
-      SSW_CUDA(cudaMalloc((void**)&db->d_xchg_timed_out, 4));
-      SSW_CUDA(cudaMemset(db->d_xchg_timed_out, 0, 4));
+    if (!db->d_xchg_timed_out) {      // pinned host word the kernel writes directly (UVA): read without a CUDA call
+      SSW_CUDA(cudaHostAlloc((void**)&db->d_xchg_timed_out, 4, cudaHostAllocMapped));
+      *db->d_xchg_timed_out = 0;
     }
     return launch_exchange_merge(db->d_list_keys, db->d_list_dbidx, lists, k, (int64_t)lists * k, nq, k, db->d_gthr,
                                  xc->peers, xc->world, xc->rank, xc->nq_cap, xc->k_cap, xc->epoch, db->d_xchg_timed_out,
@@ -729,11 +729,10 @@ static int scan_topk_host(ssw_db* db, const float* queries, int nq, int k, const
   int32_t* d_cnt = reinterpret_cast<int32_t*>(d_out + db_b + sc_b + row_b);
   int32_t* d_cert = reinterpret_cast<int32_t*>(d_out + db_b + sc_b + row_b + cnt_b);
   auto check_xchg = [&]() -> int {
-    if (xc && db->d_xchg_timed_out) {
-      int flag = 0;
-      SSW_CUDA(cudaMemcpy(&flag, db->d_xchg_timed_out, 4, cudaMemcpyDeviceToHost));
+    if (xc && db->d_xchg_timed_out) {      // read after the stream synchronised
+      const int flag = *static_cast<volatile int*>(db->d_xchg_timed_out);
       if (flag) {
-        cudaMemset(db->d_xchg_timed_out, 0, 4);
+        *db->d_xchg_timed_out = 0;
         set_error("fused exchange: a peer rank did not deliver its lists within 10 s");
         return SSW_ERR_CUDA;
       }
@@ -770,9 +769,9 @@ static int scan_topk_host(ssw_db* db, const float* queries, int nq, int k, const
     db->exact_queries += nq;
     db->exact_rescans += n_rescan;
     if (xc) {        // this shard's exact top-k is ONE list per query for the fused exchange
-      if (!db->d_xchg_timed_out) {
-        SSW_CUDA(cudaMalloc((void**)&db->d_xchg_timed_out, 4));
-        SSW_CUDA(cudaMemset(db->d_xchg_timed_out, 0, 4));
+      if (!db->d_xchg_timed_out) {      // pinned host word the kernel writes directly (UVA): read without a CUDA call
+        SSW_CUDA(cudaHostAlloc((void**)&db->d_xchg_timed_out, 4, cudaHostAllocMapped));
+        *db->d_xchg_timed_out = 0;
       }
       // the exchange writes the world's result over d_out while reading d_key / d_dbidx: hand it copies
       rc = ensure_lists(db, nq, 1, k);

@@ -37,7 +37,7 @@ struct ssw_db {
   std::mutex mu;                   // serialises the host-buffer entry points (they share the staging blocks)
   std::vector<int32_t> h_img_dbidx; // host copy of d_img_dbidx (candidate id -> image index), filled on first use
   unsigned long long* d_scan_stats = nullptr;  // [2] list updates / images offered, counted by the scan kernels (ssw_scan_stats)
-  int* d_xchg_timed_out = nullptr; // set by the fused exchange kernel when a peer never answered
+  int* d_xchg_timed_out = nullptr; // pinned, device-visible host word: set by the fused exchange kernel when a peer never answered
   void* d_tc_ws = nullptr;         // prepared A operand of the tcgen05 batched scan (one batch)
 
   int64_t excl_words = 0;          // uint32 words of one exclusion bitmap (n_images bits, padded)

@@ -660,11 +660,73 @@ __global__ void __launch_bounds__(kEdgeBlock) knn_edge_write_kernel(const int32_
   }
 }
 
+int knn_exact_refine(const float* d_v32, int64_t n, int dim, int k1, int kc, int64_t row_begin, int64_t rows,
+                     const int32_t* d_cand_idx, const float* d_cand_dist, double err, int32_t* d_out_idx, float* d_out_dist,
+                     cudaStream_t st, int64_t* rows_rescanned);
+
+static thread_local int64_t t_knn_exact_rows = 0, t_knn_rescanned = 0;
+static thread_local double t_knn_rho = 0.0;
+
 }  // namespace ssw
 
 using namespace ssw;
 
 extern "C" {
+
+int ssw_knn_build_device(int device, const void* d_vectors_f16, int64_t n, int dim, int k1, int64_t row_begin,
+                         int64_t row_end, int32_t* d_out_idx, float* d_out_dist, void* stream);
+
+// Candidates of rows [row_begin, row_end) with the vectors already on the device: d_v16 = the fp16 copy the tensor
+// cores multiply, d_v32 = the caller's float32 values (or null).  With float32 values that are not fp16-representable
+// the tensor-core pass proposes kc > k1 candidates and ssw_knn_exact.cu re-ranks / certifies them in float32.
+static int knn_candidates_on_device(int device, const float* d_v32, const void* d_v16, int64_t n, int dim, int k1,
+                                    int64_t row_begin, int64_t row_end, int32_t* d_idx, float* d_dist, cudaStream_t st) {
+  t_knn_exact_rows = t_knn_rescanned = 0;
+  t_knn_rho = 0.0;
+  double rho = 0.0, vmax = 0.0;
+  if (d_v32) {
+    float* d_stats = nullptr;
+    float stats[2] = {0.f, 0.f};
+    SSW_CUDA(cudaMalloc((void**)&d_stats, 8));
+    int rc = launch_row_error_stats(d_v32, n, dim, d_stats, st);
+    if (!rc && cudaMemcpyAsync(stats, d_stats, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = SSW_ERR_CUDA;
+    if (!rc && cudaStreamSynchronize(st) != cudaSuccess) rc = SSW_ERR_CUDA;
+    cudaFree(d_stats);
+    if (rc) return rc;
+    rho = std::sqrt((double)stats[0]) * (1.0 + 1e-6);
+    vmax = std::sqrt((double)stats[1]) * (1.0 + 1e-6);
+  }
+  t_knn_rho = rho;
+  if (rho == 0.0)       // fp16 input, or float32 values the fp16 copy holds exactly: the tensor-core result is the answer
+    return ssw_knn_build_device(device, d_v16, n, dim, k1, row_begin, row_end, d_idx, d_dist, st);
+  const int64_t rows = row_end - row_begin;
+  const int kc = (int)std::min<int64_t>(std::min<int64_t>(n, SSW_MAX_KNN_K1), (int64_t)k1 + std::max(16, k1));
+  int32_t* d_cidx = nullptr;
+  float* d_cdist = nullptr;
+  SSW_CUDA(cudaMalloc((void**)&d_cidx, std::max<size_t>((size_t)rows * kc, 1) * 4));
+  cudaError_t e = cudaMalloc((void**)&d_cdist, std::max<size_t>((size_t)rows * kc, 1) * 4);
+  if (e != cudaSuccess) {
+    cudaFree(d_cidx);
+    set_error(std::string("cudaMalloc(candidates): ") + cudaGetErrorString(e));
+    return SSW_ERR_OOM;
+  }
+  int rc = ssw_knn_build_device(device, d_v16, n, dim, kc, row_begin, row_end, d_cidx, d_cdist, st);
+  const double err = 2.0 * rho * vmax + vmax * vmax * (double)dim * 1.8e-7 + 3e-7;
+  int64_t rescanned = 0;
+  if (!rc) rc = knn_exact_refine(d_v32, n, dim, k1, kc, row_begin, rows, d_cidx, d_cdist, err, d_idx, d_dist, st, &rescanned);
+  cudaFree(d_cidx);
+  cudaFree(d_cdist);
+  t_knn_exact_rows = rows;
+  t_knn_rescanned = rescanned;
+  return rc;
+}
+
+int ssw_knn_exact_stats(int64_t* rows_refined, int64_t* rows_rescanned, double* rho) {
+  if (rows_refined) *rows_refined = t_knn_exact_rows;
+  if (rows_rescanned) *rows_rescanned = t_knn_rescanned;
+  if (rho) *rho = t_knn_rho;
+  return SSW_OK;
+}
 
 int ssw_knn_build_device(int device, const void* d_vectors_f16, int64_t n, int dim, int k1, int64_t row_begin,
                          int64_t row_end, int32_t* d_out_idx, float* d_out_dist, void* stream) {
@@ -719,7 +781,9 @@ int ssw_knn_build(int device, const void* vectors, int dtype_in, int64_t n, int 
   }
   if ((rc = chk(cudaMalloc((void**)&d_idx, std::max<size_t>(nout, 1) * 4), "cudaMalloc(out_idx)"))) return rc;
   if ((rc = chk(cudaMalloc((void**)&d_dist, std::max<size_t>(nout, 1) * 4), "cudaMalloc(out_dist)"))) return rc;
-  rc = ssw_knn_build_device(device, d_v, n, dim, k1, row_begin, row_end, d_idx, d_dist, st);
+  SSW_REQUIRE(k1 >= 1 && k1 <= SSW_MAX_KNN_K1 && k1 <= n, "k1 must be in [1, min(n, SSW_MAX_KNN_K1)]");
+  rc = knn_candidates_on_device(device, dtype_in == SSW_F32 ? static_cast<const float*>(d_in) : nullptr, d_v, n, dim, k1, row_begin,
+                                row_end, d_idx, d_dist, st);
   if (rc) {
     cleanup();
     return rc;
@@ -819,7 +883,8 @@ int ssw_knn_graph(int device, const void* vectors, int dtype_in, int64_t n, int 
   KG_TRY(cudaMalloc((void**)&d_rank, cap * 4));
   KG_TRY(cudaMalloc((void**)&d_total, 8));
   KG_TRY(cudaMalloc(&d_ws, (size_t)ws_bytes));
-  rc = ssw_knn_build_device(device, d_v, n, dim, k1, 0, n, d_idx, d_dist, nullptr);
+  rc = knn_candidates_on_device(device, dtype_in == SSW_F32 ? static_cast<const float*>(d_in) : nullptr, d_v, n, dim, k1, 0, n,
+                                d_idx, d_dist, nullptr);
   if (!rc) rc = ssw_knn_edges_device(device, d_idx, d_dist, n, k1, 0, d_src, d_dst, d_edist, d_rank, d_total, d_ws, nullptr);
   if (rc) {
     cleanup();

@@ -21,8 +21,9 @@ from ._lib import SSW_F16, SSW_F32, SSW_MAX_KNN_K1, check, lib, ptr
 
 def knn_candidates(vectors, n_neighbors, *, device=0, rows=None):
     """The k1 = min(n_neighbors+1, N) columns minimising (fp32(1 - dot), column) for every row in
-    ``rows`` (default: all), self included when it ranks.  fp32 input is rounded to fp16 for the
-    tensor cores (exact for fp16-valued data).  Returns (idx int32 [rows,k1], dist fp32 [rows,k1])."""
+    ``rows`` (default: all), self included when it ranks.  The tensor cores multiply fp16 values; float32 input
+    that is not fp16-representable is re-ranked / certified from the float32 rows on the device, so the result is the
+    float32 neighbour list (see :func:`knn_exact_stats`).  Returns (idx int32 [rows,k1], dist fp32 [rows,k1])."""
     v = np.ascontiguousarray(vectors)
     if v.dtype not in (np.float16, np.float32):
         v = v.astype(np.float32)
@@ -82,16 +83,36 @@ def edges_from_candidates(idx, dist, nvec, src_offset=0):
 
 
 def post_process_graph_df(df, nvec):
-    """Generic form for an arbitrary edge table (e.g. from an approximate method), same contract
-    as the reference function."""
-    df = df.assign(src_vertex=df.src_vertex.astype("int32"), dst_vertex=df.dst_vertex.astype("int32"),
-                   distance=np.clip(df.distance.values.astype("float32"), 0.0, None))
-    df = df[df.src_vertex != df.dst_vertex]
-    df = df.assign(dst_rank=df.groupby("src_vertex").distance.rank("first").astype("int32"))
+    """The contract of the reference's post_process_graph_df (knn_graph.py:142-168) for an ARBITRARY edge table (e.g.
+    from an approximate method): int32 / float32 columns, distances clipped at 0, self edges dropped, ``dst_rank`` =
+    1.. by (distance, table order) within each source, one rank-0 zero-distance self edge per vertex, rows ordered
+    by (src_vertex, dst_rank).  Array code: one stable lexsort instead of a pandas groupby-rank."""
+    src = df["src_vertex"].to_numpy().astype(np.int32)
+    dst = df["dst_vertex"].to_numpy().astype(np.int32)
+    dist = np.clip(df["distance"].to_numpy().astype(np.float32), 0.0, None)
+    keep = src != dst
+    src, dst, dist = src[keep], dst[keep], dist[keep]
+    order = np.lexsort((np.arange(len(src)), dist, src))          # by source, then distance, then table order
+    src, dst, dist = src[order], dst[order], dist[order]
+    first = np.concatenate([[0], np.flatnonzero(np.diff(src)) + 1]) if len(src) else np.zeros(0, np.int64)
+    run = np.repeat(first, np.diff(np.append(first, len(src))))
+    rank = (np.arange(len(src)) - run + 1).astype(np.int32)
     me = np.arange(nvec, dtype=np.int32)
-    selfs = pd.DataFrame({"src_vertex": me, "dst_vertex": me, "distance": np.zeros(nvec, np.float32),
-                          "dst_rank": np.zeros(nvec, np.int32)})
-    return pd.concat([df, selfs], ignore_index=True).sort_values(["src_vertex", "dst_rank"]).reset_index(drop=True)
+    src = np.concatenate([src, me])
+    dst = np.concatenate([dst, me])
+    dist = np.concatenate([dist, np.zeros(nvec, np.float32)])
+    rank = np.concatenate([rank, np.zeros(nvec, np.int32)])
+    order = np.lexsort((rank, src))
+    return pd.DataFrame({"src_vertex": src[order], "dst_vertex": dst[order], "distance": dist[order], "dst_rank": rank[order]})
+
+
+def knn_exact_stats():
+    """After compute_exact_knn / knn_candidates on float32 vectors: dict(rows_refined, rows_rescanned, rho) — how many
+    rows had their tensor-core candidates re-ranked in float32, how many of those needed the full float32 re-scan, and
+    the largest fp16 rounding residual of a vector (0: the fp16 pass was exact).  See ssw_knn_exact_stats."""
+    a, b, rho = C.c_int64(), C.c_int64(), C.c_double()
+    check(lib.ssw_knn_exact_stats(C.byref(a), C.byref(b), C.byref(rho)))
+    return dict(rows_refined=a.value, rows_rescanned=b.value, rho=rho.value)
 
 
 def compute_exact_knn(vectors, n_neighbors, *, device=0):
@@ -114,26 +135,37 @@ def compute_exact_knn(vectors, n_neighbors, *, device=0):
     return pd.DataFrame({"src_vertex": src[:t], "dst_vertex": dst[:t], "distance": dis[:t], "dst_rank": rank[:t]})
 
 
+class _DistanceKernel:
+    """Edge weight as a function of the cosine distance — the ``kfun`` argument of get_weight_matrix."""
+
+    def __init__(self, edist, hard):
+        assert edist > 0
+        self.edist, self.hard = float(edist), hard
+
+    def __call__(self, distances):
+        d = np.asarray(distances)
+        if self.hard:                                     # knn_graph.py:24-30: 0/1 weights, cut at edist
+            return (d <= self.edist).astype("float32")
+        assert d.min() >= -0.0001 and d.max() <= 2.0001   # cosine distances (knn_graph.py:15-16)
+        return np.exp(-(d.astype("float64") * (1.0 / self.edist)))      # knn_graph.py:8-22
+
+
 def rbf_kernel(edist):
-    """knn_graph.py:8-22: cosine distance -> weight exp(-distance / edist), float64."""
-    assert edist > 0
-    spread = 1.0 / edist
-
-    def kernel(arr):
-        assert arr.min() >= -0.0001 and arr.max() <= 2.0001
-        return np.exp(-(arr.astype("float64") * spread))
-
-    return kernel
+    """exp(-distance / edist) in float64 (knn_graph.py:8-22)."""
+    return _DistanceKernel(edist, hard=False)
 
 
 def knn_kernel(edist=2.1):
-    """knn_graph.py:24-30: 0/1 weights, neighbours beyond ``edist`` discarded."""
-    assert edist > 0.0
+    """1 for neighbours within ``edist``, else 0 (knn_graph.py:24-30)."""
+    return _DistanceKernel(edist, hard=True)
 
-    def kernel(arr):
-        return (arr <= edist).astype("float32")
 
-    return kernel
+def compute_knn_from_nndescent(vectors, *, n_neighbors, n_jobs=-1, low_memory=False, device=0, **kwargs):
+    """Drop-in for the reference's NN-descent graph builder (knn_graph.py:193-211), same signature and the same edge
+    table.  pynndescent is approximate (and unpinned in the reference's lock file); the tensor-core build is exact at
+    a fraction of its cost, so this routes to :func:`compute_exact_knn` — recall 1.0.  ``n_jobs`` / ``low_memory`` /
+    pynndescent keywords are accepted and ignored."""
+    return compute_exact_knn(vectors, n_neighbors, device=device)
 
 
 def get_weight_matrix(df, *, kfun, self_edges=False, normalized, laplacian=False, symmetric=True):
@@ -191,41 +223,118 @@ def get_lookup_ranges(sorted_col, nvecs):
     return np.concatenate([[0], np.cumsum(counts)])
 
 
-class KNNGraph:
-    def __init__(self, knn_df, nvecs=None):
-        self.knn_df = knn_df
-        ks = knn_df.groupby("src_vertex").dst_rank.max()
-        self._ks = ks
-        self.k = ks.min()
-        self.maxk = ks.median()
-        self.nvecs = ks.shape[0]
-        self.ind_ptr = get_lookup_ranges(knn_df.src_vertex, self.nvecs)
+def factor_neighbors(knng, idx, k_intra):
+    """factor_neighbors (knn_graph.py:213-242): split a patch-level graph into edges BETWEEN images — per source the
+    nearest patch of every other image, re-ranked 0.. by distance — and edges WITHIN the source's own image (rank
+    1..k_intra by distance; the rank-0 self edge has distance 0 and is rank 1 there, as in the reference).  ``idx`` is
+    an index whose ``vector_meta.dbidx`` maps vertices to images.  Array code over the (src, rank)-sorted edge table."""
+    dbidx = idx.vector_meta["dbidx"].to_numpy().astype(np.int32)
+    df = knng.knn_df
+    src, dst = df["src_vertex"].to_numpy(), df["dst_vertex"].to_numpy()
+    dist, pos = df["distance"].to_numpy(), np.arange(len(df))
+    sdb, ddb = dbidx[src], dbidx[dst]
+    same = sdb == ddb
 
-    def _check_rep(self):
-        """knn_graph.py:258-262: with one self edge per vertex the sources and destinations coincide."""
-        srcs, dsts = np.unique(self.knn_df.src_vertex.values), np.unique(self.knn_df.dst_vertex.values)
-        assert np.array_equal(srcs, dsts), "self edges should guarantee this"
-        assert self._ks.index.max() + 1 == len(srcs), "self edges guarantee this"
+    def first_rank(keys, sel):
+        """1-based rank of every selected edge within its key group by (distance, table order)."""
+        order = np.lexsort((pos[sel], dist[sel]) + tuple(k[sel] for k in reversed(keys)))
+        ks = [k[sel][order] for k in keys]
+        new = np.ones(len(order), bool)
+        if len(order) > 1:
+            new[1:] = np.logical_or.reduce([k[1:] != k[:-1] for k in ks])
+        start = np.maximum.accumulate(np.where(new, np.arange(len(order)), 0))
+        rank = np.empty(len(order), np.int64)
+        rank[order] = np.arange(len(order)) - start + 1
+        return rank
 
-    @staticmethod
-    def from_vectors(vectors, *, n_neighbors, device=0, **_ignored):
-        """Entry point of scripts/make_knn_graph.py:49 — returns (graph, auxiliary index or None)."""
-        return KNNGraph(compute_exact_knn(vectors, n_neighbors, device=device)), None
+    inter_sel = np.flatnonzero(~same)
+    edge_rank = first_rank([src, ddb], inter_sel)
+    keep = inter_sel[edge_rank <= 1]                                   # nearest patch per (source, other image)
+    inter = df.iloc[keep].assign(src_dbidx=sdb[keep], dst_dbidx=ddb[keep])
+    inter = inter.assign(dst_rank=(first_rank([src], keep) - 1).astype("int"))
+    intra_sel = np.flatnonzero(same)
+    r = first_rank([src], intra_sel)
+    keep2 = intra_sel[r <= k_intra]
+    intra = df.iloc[keep2].assign(src_dbidx=sdb[keep2], dst_dbidx=ddb[keep2], dst_rank=r[r <= k_intra].astype("int"))
+    return pd.concat([inter, intra], ignore_index=True)
 
-    def save(self, path, overwrite=False):
-        os.makedirs(path, exist_ok=overwrite)
-        self.knn_df.to_parquet(f"{path}/forward.parquet")
 
-    @staticmethod
-    def from_file(path):
-        return KNNGraph(pd.read_parquet(f"{path}/forward.parquet"))
+def _graph_base():
+    """Inside the reference's environment KNNGraph IS the reference's class (plus the entry points its CLI expects);
+    standalone, a minimal container with the same attributes."""
+    try:
+        from seesaw.knn_graph import KNNGraph as ref      # type: ignore
+        return ref
+    except Exception:      # noqa: BLE001
+        return None
 
-    def restrict_k(self, *, k):
-        if k < self.maxk:
-            return KNNGraph(self.knn_df[self.knn_df.dst_rank < k].reset_index(drop=True))
-        if k > self.maxk:
-            raise AssertionError(f"can only do up to k={self.k} neighbors based on input df")
-        return self
 
-    def rev_lookup(self, dst_vertex) -> pd.DataFrame:
-        return self.knn_df.iloc[self.ind_ptr[dst_vertex]:self.ind_ptr[dst_vertex + 1]]
+_RefKNNGraph = _graph_base()
+
+if _RefKNNGraph is not None:
+    class KNNGraph(_RefKNNGraph):
+        """seesaw.knn_graph.KNNGraph plus ``from_vectors`` / ``save``, which scripts/make_knn_graph.py:49-50 calls and the
+        reference class lacks."""
+
+        @staticmethod
+        def from_vectors(vectors, *, n_neighbors, device=0, **_ignored):
+            return KNNGraph(compute_exact_knn(vectors, n_neighbors, device=device)), None
+
+        def save(self, path, overwrite=False):
+            os.makedirs(path, exist_ok=overwrite)
+            self.knn_df.to_parquet(f"{path}/forward.parquet")
+
+        @staticmethod
+        def from_file(path):
+            return KNNGraph(pd.read_parquet(f"{path}/forward.parquet"))
+else:
+    class KNNGraph:
+        """Container over the edge table with the attributes the reference's consumers read (knn_graph.py:246-286):
+        ``knn_df``, ``k`` / ``maxk`` (min / median over vertices of the largest rank), ``nvecs``, ``ind_ptr`` (CSR over
+        src_vertex), ``restrict_k``, ``rev_lookup``; ``from_vectors`` / ``save`` are the entry points of
+        scripts/make_knn_graph.py:49-50, ``from_file`` reads ``{path}/forward.parquet`` (:272-283)."""
+
+        def __init__(self, knn_df, nvecs=None):
+            self.knn_df = knn_df
+            src = knn_df["src_vertex"].to_numpy().astype(np.int64)
+            n = int(src.max()) + 1 if len(src) else 0
+            top = np.zeros(n, np.int64)
+            np.maximum.at(top, src, knn_df["dst_rank"].to_numpy().astype(np.int64))
+            present = np.bincount(src, minlength=n) > 0
+            self._top_rank = pd.Series(top[present], index=np.flatnonzero(present))
+            self.k = self._top_rank.min()
+            self.maxk = self._top_rank.median()
+            self.nvecs = int(present.sum())
+            self.ind_ptr = get_lookup_ranges(src, self.nvecs)
+
+        def _check_rep(self):
+            """Invariants the self edges guarantee (knn_graph.py:258-262): every destination is also a source, and the
+            sources are exactly 0 .. nvecs-1."""
+            seen_src = np.zeros(self.nvecs, bool)
+            seen_src[self.knn_df["src_vertex"].to_numpy()] = True
+            dst = self.knn_df["dst_vertex"].to_numpy()
+            assert dst.max(initial=-1) < self.nvecs and seen_src.all() and seen_src[dst].all(), "self edges should guarantee this"
+
+        @staticmethod
+        def from_vectors(vectors, *, n_neighbors, device=0, **_ignored):
+            """Returns (graph, auxiliary index or None) as the CLI unpacks it."""
+            return KNNGraph(compute_exact_knn(vectors, n_neighbors, device=device)), None
+
+        def save(self, path, overwrite=False):
+            os.makedirs(path, exist_ok=overwrite)
+            self.knn_df.to_parquet(f"{path}/forward.parquet")
+
+        @staticmethod
+        def from_file(path):
+            return KNNGraph(pd.read_parquet(f"{path}/forward.parquet"))
+
+        def restrict_k(self, *, k):
+            if k > self.maxk:
+                raise AssertionError(f"can only do up to k={self.k} neighbors based on input df")
+            if k == self.maxk:
+                return self
+            return KNNGraph(self.knn_df[self.knn_df["dst_rank"] < k].reset_index(drop=True))
+
+        def rev_lookup(self, dst_vertex) -> pd.DataFrame:
+            lo, hi = self.ind_ptr[dst_vertex], self.ind_ptr[dst_vertex + 1]
+            return self.knn_df.iloc[lo:hi]

@@ -149,49 +149,67 @@ class OracleLP:
 
 
 @pytest.mark.parametrize("sigmoid_first,normalize", [(True, False), (False, True)])
-def test_label_propagation_ranker_vs_live_reference(reference, sigmoid_first, normalize):
-    """B200LabelPropagationRanker (host logic; propagation injected) == the reference's LabelPropagationRanker2 over a
-    feedback session: prior scores, positives only (no propagation yet), first negative, more labels, top_k."""
+def test_reference_ranker_runs_on_the_swapped_propagation_class(reference, sigmoid_first, normalize, monkeypatch):
+    """The rankers are the reference's own (research/knn_methods.py, out of scope); the drop-in is the ONE class they
+    instantiate.  With ``knn_methods.LabelPropagation`` rebound (what seesaw_b200.label_propagation.use_in_reference
+    does, here with the oracle standing in for the GPU loop) LabelPropagationRanker2 gives the same scores as with the
+    reference's own loop over a feedback session."""
     import importlib
     from seesaw_b200 import knn_graph as kg
-    from seesaw_b200.label_propagation import B200LabelPropagationRanker
-    ref_mod = importlib.import_module("seesaw.research.knn_methods")
+    km = importlib.import_module("seesaw.research.knn_methods")
     c = cases.LP["lp_reg"]
     df = orc.compute_exact_knn(cases.lp_vectors(c), c["k"])
     W = kg.get_weight_matrix(df, kfun=kg.rbf_kernel(c["edist"]), self_edges=False, normalized=False, symmetric=True)
     kw = dict(weight_matrix=W, normalize_scores=normalize, sigmoid_before_propagate=sigmoid_first, calib_a=2.0, calib_b=-0.1,
               prior_weight=1.0, normalize_epsilon=0.1 if normalize else None)
-    mine = B200LabelPropagationRanker(lp_factory=OracleLP, **kw)
-    ref = ref_mod.LabelPropagationRanker2(**kw)
-    rng = np.random.default_rng(9)
-    base = rng.standard_normal(c["n"])
+    ref = km.LabelPropagationRanker2(**kw)
+    monkeypatch.setattr(km, "LabelPropagation", OracleLP)
+    mine = km.LabelPropagationRanker2(**kw)
+    assert isinstance(mine.lp, OracleLP) and not isinstance(ref.lp, OracleLP)
+    base = np.random.default_rng(9).standard_normal(c["n"])
     mine.set_base_scores(base.copy())
     ref.set_base_scores(base.copy())
-    steps = [([3, 17], [1, 1]), ([40], [0]), ([5, 77, 120], [1, 0, 0])]
-    for idxs, labels in steps:
+    for idxs, labels in cases.RANKER_STEPS:
         mine.update(idxs, labels)
         ref.update(idxs, labels)
         assert np.array_equal(mine.current_scores(), ref.current_scores())
-        assert np.array_equal(mine.is_labeled, ref.is_labeled) and np.array_equal(mine.labels, ref.labels)
-        mi, ms = mine.top_k(15)
-        ri, rs = ref.top_k(15)
-        assert np.array_equal(ms, rs) and set(mi.tolist()) >= set(ri[rs > rs[-1]].tolist())
-    mine.set_base_scores(base * 0.5)           # with labels present the new prior is propagated at once
-    ref.set_base_scores(base * 0.5)
-    assert np.array_equal(mine.current_scores(), ref.current_scores())
 
 
-def test_label_propagation_ranker_vs_reference_golden(golden):
+def test_use_in_reference_rebinds_the_class(reference):
+    import importlib
+    from seesaw_b200 import label_propagation as lp
+    km = importlib.import_module("seesaw.research.knn_methods")
+    before = km.LabelPropagation
+    try:
+        assert lp.use_in_reference() is before and km.LabelPropagation is lp.B200LabelPropagation
+    finally:
+        km.LabelPropagation = before
+
+
+def test_graph_host_helpers_vs_live_reference(reference):
+    """post_process_graph_df on an arbitrary edge table, factor_neighbors, the KNNGraph container and the NN-descent
+    shim's signature against the reference's own functions."""
+    import inspect
     from seesaw_b200 import knn_graph as kg
-    from seesaw_b200.label_propagation import B200LabelPropagationRanker
-    c = cases.LP["lp_reg"]
-    W = kg.get_weight_matrix(orc.compute_exact_knn(cases.lp_vectors(c), c["k"]), kfun=kg.rbf_kernel(c["edist"]),
-                             self_edges=False, normalized=False, symmetric=True)
-    rk = B200LabelPropagationRanker(weight_matrix=W, normalize_scores=False, sigmoid_before_propagate=True, calib_a=2.0,
-                                    calib_b=-0.1, prior_weight=1.0, lp_factory=OracleLP)
-    rk.set_base_scores(np.random.default_rng(9).standard_normal(c["n"]))
-    for step, (idxs, labels) in enumerate(cases.RANKER_STEPS):
-        rk.update(idxs, labels)
-        assert np.array_equal(rk.current_scores(), golden[f"ranker/scores/{step}"]), step
-    idx, sc = rk.top_k(10)
-    assert not set(idx.tolist()) & {3, 17, 40, 5, 77, 120} and (np.diff(sc) <= 0).all()
+    rk = reference.knn_graph
+    v = cases.knn_inputs(cases.KNN["knn_600"])
+    idx, dist = orc.exact_knn_candidates(v, 10)
+    n, k1 = idx.shape
+    rng = np.random.default_rng(3)
+    shuffle = rng.permutation(n * k1)                 # an arbitrary (unsorted) edge table, as an approximate method returns
+    raw = pd.DataFrame({"src_vertex": np.repeat(np.arange(n), k1)[shuffle], "dst_vertex": idx.reshape(-1)[shuffle],
+                        "distance": dist.reshape(-1)[shuffle]})
+    pd.testing.assert_frame_equal(kg.post_process_graph_df(raw, n), rk.post_process_graph_df(raw, n))
+    df = orc.compute_exact_knn(v, 10)
+    mine, ref = kg.KNNGraph(df), rk.KNNGraph(df)
+    assert (mine.k, mine.maxk, mine.nvecs) == (ref.k, ref.maxk, ref.nvecs) and np.array_equal(mine.ind_ptr, ref.ind_ptr)
+    pd.testing.assert_frame_equal(mine.restrict_k(k=4).knn_df, ref.restrict_k(k=4).knn_df)
+    pd.testing.assert_frame_equal(mine.rev_lookup(17), ref.rev_lookup(17))
+
+    class Idx:
+        vector_meta = pd.DataFrame({"dbidx": np.arange(n) // 4})
+    a, b = rk.factor_neighbors(ref, Idx, 2), kg.factor_neighbors(mine, Idx, 2)
+    pd.testing.assert_frame_equal(a.reset_index(drop=True), b.reset_index(drop=True), check_dtype=False)
+    want = inspect.signature(rk.compute_knn_from_nndescent).parameters
+    got = inspect.signature(kg.compute_knn_from_nndescent).parameters
+    assert list(want)[:4] == list(got)[:4] == ["vectors", "n_neighbors", "n_jobs", "low_memory"]

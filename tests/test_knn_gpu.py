@@ -110,3 +110,63 @@ def test_knn_variants_and_limits(kg, n, dim, k):
     assert (dist == od).all() and (idx == oi).all()
     with pytest.raises(Exception):
         kg.knn_candidates(synth.synth_rows(0, 100, dim, 1, "lattice", np.float32), 64)     # k1 = 65 > SSW_MAX_KNN_K1
+
+
+def test_float32_vectors_give_the_float32_graph():
+    """Vectors that are NOT fp16-representable: the tensor cores only propose candidates, distances and
+    ranks come from the float32 rows — the neighbour lists equal the float32 oracle's (a swap admissible only between
+    neighbours whose float64 distances differ by < 1e-5 relative), the distances agree to 1e-6; the plain fp16 build of
+    the same vectors differs visibly, which is what the refinement is for."""
+    import ctypes as C
+    from seesaw_b200 import knn_graph as kg, synth
+    from seesaw_b200._lib import SSW_F16, check, lib, ptr
+    n, k = 6000, 10
+    v = synth.unit_rows(n, 512, 71)
+    assert not (v.astype(np.float16).astype(np.float32) == v).all()
+    idx, dist = kg.knn_candidates(v, k)
+    stats = kg.knn_exact_stats()
+    assert stats["rows_refined"] == n and stats["rho"] > 0
+    oi, od = orc.exact_knn_candidates(v, k)
+    np.testing.assert_allclose(dist, od, rtol=0, atol=2e-6)
+    d64 = 1.0 - v.astype(np.float64) @ v.astype(np.float64).T
+    bad_rows = np.flatnonzero((idx != oi).any(axis=1))
+    for r in bad_rows:
+        for a, b in zip(idx[r], oi[r]):
+            if a != b:
+                assert abs(d64[r, a] - d64[r, b]) <= 1e-5 * max(abs(d64[r, a]), 1e-3), (r, a, b)
+    print(f"float32 kNN: {len(bad_rows)} of {n} rows differ from the float32 oracle (near-ties), "
+          f"{stats['rows_rescanned']} rows needed the full float32 re-scan")
+    # the edge table through the reference-facing call
+    df = kg.compute_exact_knn(v, k)
+    want = orc.compute_exact_knn(v, k)
+    assert len(df) == len(want) and (df.src_vertex.values == want.src_vertex.values).all()
+    assert (df.dst_vertex.values != want.dst_vertex.values).sum() <= (k + 1) * len(bad_rows)
+    # fp16 rounding alone: neighbour lists change
+    i16 = np.empty((n, k + 1), np.int32)
+    d16 = np.empty((n, k + 1), np.float32)
+    v16 = v.astype(np.float16)
+    check(lib.ssw_knn_build(0, ptr(v16), SSW_F16, n, 512, k + 1, 0, n, ptr(i16), ptr(d16)))
+    assert (i16 != oi).any(axis=1).sum() > len(bad_rows)
+    print(f"plain fp16 build of the same vectors: {(i16 != oi).any(axis=1).sum()} rows differ")
+
+
+def test_float32_near_duplicates_fall_back_to_the_full_rescan():
+    """Clusters tighter than the fp16 rounding error cannot be certified from fp16 candidates: those rows are re-scanned
+    against all columns in float32 and still equal the float64 ranking up to near-ties."""
+    from seesaw_b200 import knn_graph as kg, synth
+    rng = np.random.default_rng(5)
+    centres = synth.unit_rows(20, 512, 72)
+    n = 1500
+    v = (centres[rng.integers(0, 20, size=n)] + rng.standard_normal((n, 512)).astype(np.float32) * np.float32(3e-6)).astype(np.float32)
+    v[7] = v[3]                                       # and one exact duplicate pair
+    idx, dist = kg.knn_candidates(v, 10)
+    stats = kg.knn_exact_stats()
+    assert stats["rows_rescanned"] > 0
+    oi, od = orc.exact_knn_candidates(v, 10)
+    np.testing.assert_allclose(dist, od, rtol=0, atol=2e-6)
+    d64 = 1.0 - v.astype(np.float64) @ v.astype(np.float64).T
+    for r in np.flatnonzero((idx != oi).any(axis=1)):
+        for a, b in zip(idx[r], oi[r]):
+            if a != b:
+                assert abs(d64[r, a] - d64[r, b]) <= 1e-6, (r, a, b)       # fp32 resolution of a 512-term dot near 1
+    assert dist[3, 0] == dist[3, 1] and {3, 7} <= set(idx[3].tolist()) and {3, 7} <= set(idx[7].tolist())

@@ -1,7 +1,9 @@
 """CPU test of the batching front end with the oracle standing in for the GPU scanner."""
+import os
 import threading
 
 import numpy as np
+import pytest
 
 import seesaw_oracle as orc
 from seesaw_b200 import synth
@@ -62,3 +64,71 @@ def test_scanner_failure_reaches_every_waiter():
         except ValueError:
             pass
     b.close()
+
+
+# ---- the process boundary: one server process, many session processes (CPU: the oracle stands in for the GPU database)
+def _stub_database():
+    import sys as _sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (os.path.dirname(here), os.path.join(os.path.dirname(here), "oracle"), here):
+        if p not in _sys.path:
+            _sys.path.insert(0, p)
+    from fake_db import FakeDB
+    counts = synth.patches_per_image(300, 1, 9, 3)
+    dbidx = synth.dbidx_of_rows(counts)
+    vecs = synth.synth_rows(0, int(counts.sum()), 256, 5, "lattice", np.float32)
+    return FakeDB(vecs, dbidx), vecs, dbidx
+
+
+def _server_process(address):
+    from seesaw_b200.service import ScanServer
+    db, _, _ = _stub_database()
+    ScanServer(db, address, max_batch=16, max_wait_s=0.1).serve_forever()
+
+
+def _session_process(address, i, out):
+    from seesaw_b200.service import ScanClient
+    c = ScanClient(address)
+    qs = synth.lattice_queries(24, 256, 6)
+    ex = None if i % 3 else [np.arange(i, 300, 7)]
+    r = c.scan_topk(qs[i:i + 1], 3 + i % 5, exclude=ex)
+    s = c.score_all(qs[i])
+    out.put((i, r["dbidx"][0], r["row"][0], int(r["count"][0]), float(s.sum()), c.n_rows))
+    c.close()
+
+
+def test_session_processes_share_one_server_process(tmp_path):
+    """24 session PROCESSES (the reference runs one Ray actor process per session, web_session_actor.py:13-16) send
+    their single queries to one database-owning process; it batches them across connections and every session gets
+    exactly what a call of its own would have returned."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    address = str(tmp_path / "ssw.sock")
+    server = ctx.Process(target=_server_process, args=(address,), daemon=True)
+    server.start()
+    out = ctx.Queue()
+    sessions = [ctx.Process(target=_session_process, args=(address, i, out)) for i in range(24)]
+    [p.start() for p in sessions]
+    got = {}
+    for _ in sessions:
+        rec = out.get(timeout=120)
+        got[rec[0]] = rec[1:]
+    [p.join(60) for p in sessions]
+    from seesaw_b200.service import ScanClient
+    c = ScanClient(address)
+    stats = c.stats()
+    _, vecs, dbidx = _stub_database()
+    qs = synth.lattice_queries(24, 256, 6)
+    for i in range(24):
+        k = 3 + i % 5
+        o = orc.query_prelim(vecs, dbidx, qs[i], k, exclude=None if i % 3 else np.arange(i, 300, 7))
+        d, row, cnt, ssum, n_rows = got[i]
+        assert cnt == len(o["dbidx"]) and (d[:cnt] == o["dbidx"]).all() and (row[:cnt] == o["best_row"]).all(), i
+        assert ssum == float((vecs @ qs[i]).sum()) and n_rows == len(vecs)
+    assert stats["queries_served"] == 24 and stats["batches_issued"] < 24       # batched across processes
+    with pytest.raises(RuntimeError):
+        c._call("scan", (np.zeros((2, 255), np.float32), 3, None))      # wrong width -> server-side error, server survives
+    assert c.stats()["queries_served"] == 24
+    c.shutdown_server()
+    server.join(30)
+    assert not server.is_alive()

@@ -1,0 +1,92 @@
+"""GPU test of the cross-process batching front end: ONE process owns the B200 and the database, 64 session
+PROCESSES (the reference's one-actor-process-per-session model, web_session_actor.py:13-16) run the reference-facing
+``B200MultiscaleIndex.query`` over a ``ScanClient`` — results equal the oracle's, and the stage-1 scans of different
+processes were answered by shared tensor-core passes."""
+import multiprocessing as mp
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+N_SESSIONS = 64
+
+
+def _paths():
+    for p in (ROOT, os.path.join(ROOT, "oracle"), HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+
+
+def _inputs():
+    _paths()
+    from seesaw_b200 import synth
+    counts = synth.patches_per_image(3000, 5, 30, 3)
+    meta = synth.synth_vector_meta(counts, 7, dbidx_start=10, dbidx_stride=2)
+    vecs = synth.synth_rows(0, int(counts.sum()), 512, 9, "lattice", np.float32)     # exact arithmetic: bit-equal to the oracle
+    qs = synth.lattice_queries(N_SESSIONS, 512, 10)
+    return vecs, meta, qs
+
+
+def _server(address, ready):
+    _paths()
+    from seesaw_b200.engine import PatchDatabase
+    from seesaw_b200.service import ScanServer
+    vecs, meta, _ = _inputs()
+    db = PatchDatabase.from_arrays(vecs, meta.dbidx.to_numpy().astype(np.int32), store="f16", device=0)
+    db.set_boxes(*[meta[c].to_numpy() for c in ("x1", "y1", "x2", "y2", "zoom_level")])
+    srv = ScanServer(db, address, max_batch=64, max_wait_s=0.02)
+    ready.set()
+    srv.serve_forever()
+    db.close()
+
+
+def _session(address, i, out):
+    _paths()
+    from seesaw_b200.indices import B200MultiscaleIndex, BitMap
+    from seesaw_b200.service import ScanClient
+    _, meta, qs = _inputs()
+    client = ScanClient(address)
+    idx = B200MultiscaleIndex.from_database(client, meta)        # no CUDA in this process: every call crosses the socket
+    seen = BitMap(np.unique(meta.dbidx.values)[i::17])
+    agg = "avg_score" if i % 2 else "plain_score"
+    r = idx.query(vector=qs[i], topk=3, shortlist_size=20, exclude=seen, agg_method=agg)
+    out.put((i, np.asarray(r["dbidxs"]), [float(a.score.values[0]) for a in r["activations"]]))
+    client.close()
+
+
+def test_64_session_processes_one_gpu_process(tmp_path):
+    _paths()
+    import seesaw_oracle as orc
+    from seesaw_b200.service import ScanClient
+    ctx = mp.get_context("spawn")
+    address = str(tmp_path / "ssw.sock")
+    ready = ctx.Event()
+    server = ctx.Process(target=_server, args=(address, ready), daemon=True)
+    server.start()
+    assert ready.wait(300), "the GPU-owning process did not come up"
+    out = ctx.Queue()
+    sessions = [ctx.Process(target=_session, args=(address, i, out)) for i in range(N_SESSIONS)]
+    [p.start() for p in sessions]
+    got = {}
+    for _ in sessions:
+        i, ids, scores = out.get(timeout=600)
+        got[i] = (ids, scores)
+    [p.join(60) for p in sessions]
+    vecs, meta, qs = _inputs()
+    for i in range(N_SESSIONS):
+        seen = np.unique(meta.dbidx.values)[i::17]
+        agg = "avg_score" if i % 2 else "plain_score"
+        want = orc.multiscale_query(vecs, meta, qs[i], 3, 20, exclude=seen, agg_method=agg)
+        assert (got[i][0] == want["dbidxs"]).all(), i
+        assert got[i][1] == [float(a.score.values[0]) for a in want["activations"]], i
+    c = ScanClient(address)
+    stats = c.stats()
+    print(f"{stats['queries_served']} stage-1 scans of {N_SESSIONS} session processes in {stats['batches_issued']} GPU passes")
+    assert stats["queries_served"] == N_SESSIONS and stats["batches_issued"] < N_SESSIONS
+    c.shutdown_server()
+    server.join(60)
