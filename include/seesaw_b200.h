@@ -194,6 +194,15 @@ int ssw_topk_from_scores(ssw_db* db, const float* scores, const uint8_t* row_mas
                          const int32_t* exclude_dbidx, int64_t n_exclude, int32_t* out_dbidx,
                          float* out_score, int64_t* out_row, int32_t* out_count);
 
+/* The same when the caller already holds the rows in ranked order — exactly _get_top_dbidxs' own input
+ * (multiscale_index.py:189-199 takes vec_idxs, the rows best first): row_order[n_order] ORIGINAL row numbers best
+ * first (rows not listed take no part).  An image is represented by its earliest-listed row and images are ranked
+ * by that position, so the result follows the caller's order whatever the dtype of the scores behind it (label
+ * propagation scores are float64; ties keep the caller's order).  out_pos[k] = position in row_order of each image's
+ * best row (the caller reads its score there), out_row[k] = that row. */
+int ssw_topk_from_order(ssw_db* db, const int64_t* row_order, int64_t n_order, int k, const int32_t* exclude_dbidx,
+                        int64_t n_exclude, int32_t* out_dbidx, int64_t* out_pos, int64_t* out_row, int32_t* out_count);
+
 /* ---- exact kNN graph -------------------------------------------------------------------
  * Replaces the matmul + row argsort of compute_exact_knn (knn_graph.py:170-182):
  * for rows [row_begin,row_end) of vectors [n, dim]: the k1 = min(n_neighbors+1, n) columns j
@@ -227,6 +236,19 @@ int ssw_knn_edges_workspace_bytes(int64_t rows, int64_t* bytes);
 int ssw_knn_edges_device(int device, const int32_t* d_idx, const float* d_dist, int64_t rows, int k1,
                          int64_t src_offset, int32_t* d_src, int32_t* d_dst, float* d_distance, int32_t* d_rank,
                          int64_t* d_total, void* d_workspace, void* stream);
+
+/* ---- weight matrix of the kNN graph --------------------------------------------------------
+ * Replaces get_weight_matrix(df, kfun=, self_edges=False, normalized=False, symmetric=True) (knn_graph.py:31-104), the
+ * matrix KnnProp2 propagates over (loops/graph_based.py:36-43).  src/dst/weight[n_edges]: the edge table sorted by
+ * src_vertex (vertices 0 .. n-1, one self edge each, at most one edge per ordered pair) with weight = kfun(distance)
+ * evaluated by the caller (the reference's own numpy function: values stay bit-identical).  Output: CSR with sorted
+ * indices — both directions of every listed edge, value = (sum of the listed positive weights) / (number of
+ * listings), explicit zeros on the diagonal — exactly the arrays the reference builds; capacity >= 2 * n_edges
+ * entries, *out_nnz valid.  out_weight_sum[n] (may be NULL) = W.sum(0) as LabelPropagation computes it
+ * (label_propagation.py:24).  Fails with SSW_ERR_INVALID when a vertex ends with zero degree (:77). */
+int ssw_weight_matrix(int device, const int32_t* src, const int32_t* dst, const double* weight, int64_t n_edges,
+                      int64_t n, int64_t* out_indptr, int32_t* out_indices, double* out_data, int64_t capacity,
+                      int64_t* out_nnz, double* out_weight_sum);
 
 /* ---- label propagation over the kNN graph ----------------------------------------------
  * Replaces the iteration of LabelPropagation.fit_transform / _step (label_propagation.py:30-83):

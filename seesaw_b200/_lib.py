@@ -68,6 +68,7 @@ SIGNATURES = {
     "ssw_db_exact_info": (C.c_int, [_p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), _i64p, _i64p]),
     "ssw_rescore": (C.c_int, [_p, _p, _p, _p, C.c_int, C.c_int, C.c_int, _p, _p]),
     "ssw_topk_from_scores": (C.c_int, [_p, _p, _p, C.c_int, _p, C.c_int64, _p, _p, _p, _p]),
+    "ssw_topk_from_order": (C.c_int, [_p, _p, C.c_int64, C.c_int, _p, C.c_int64, _p, _p, _p, _p]),
     "ssw_score_all": (C.c_int, [_p, _p, _p]),
     "ssw_score_all_device": (C.c_int, [_p, _p, _p, _p]),
     "ssw_knn_build": (C.c_int, [C.c_int, _p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64, _p, _p]),
@@ -76,6 +77,7 @@ SIGNATURES = {
     "ssw_knn_graph": (C.c_int, [C.c_int, _p, C.c_int, C.c_int64, C.c_int, C.c_int, _p, _p, _p, _p, C.c_int64, _i64p]),
     "ssw_knn_edges_workspace_bytes": (C.c_int, [C.c_int64, _i64p]),
     "ssw_knn_edges_device": (C.c_int, [C.c_int, _p, _p, C.c_int64, C.c_int, C.c_int64, _p, _p, _p, _p, _p, _p, _p]),
+    "ssw_weight_matrix": (C.c_int, [C.c_int, _p, _p, _p, C.c_int64, C.c_int64, _p, _p, _p, C.c_int64, _i64p, _p]),
     "ssw_lp_create": (C.c_int, [C.POINTER(_p), C.c_int, C.c_int64, _p, _p, _p, _p, C.c_double]),
     "ssw_lp_destroy": (C.c_int, [_p]),
     "ssw_lp_fit": (C.c_int, [_p, _p, _p, C.c_int64, _p, _p, C.c_int, C.c_double, _p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

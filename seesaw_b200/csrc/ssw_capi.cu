@@ -899,6 +899,68 @@ int ssw_topk_from_scores(ssw_db* db, const float* scores, const uint8_t* row_mas
   return SSW_OK;
 }
 
+int ssw_topk_from_order(ssw_db* db, const int64_t* row_order, int64_t n_order, int k, const int32_t* exclude_dbidx,
+                        int64_t n_exclude, int32_t* out_dbidx, int64_t* out_pos, int64_t* out_row, int32_t* out_count) {
+  SSW_REQUIRE(db != nullptr && (row_order != nullptr || n_order == 0), "null argument");
+  SSW_REQUIRE(n_order >= 0 && n_order < (int64_t)0xFFFFFFFEll, "row list too long");
+  SSW_REQUIRE(k > 0 && k <= SSW_MAX_TOPK, "k must be in [1, SSW_MAX_TOPK]");
+  SSW_REQUIRE(n_exclude >= 0 && (n_exclude == 0 || exclude_dbidx != nullptr), "bad exclude list");
+  std::lock_guard<std::mutex> guard(db->mu);
+  SSW_CUDA(cudaSetDevice(db->device));
+  auto up16 = [](size_t x) { return (x + 15) / 16 * 16; };
+  const int64_t n = db->n_rows;
+  const int64_t n_lists = std::max<int64_t>(1, (db->n_images + k - 1) / k), n_padded = n_lists * k;
+  // device block: order | pos | offsets | ids | bitmap | image keys | image dbidx | outputs (dbidx, key, count)
+  const size_t ord_b = up16((size_t)n_order * 8), pos_b = up16((size_t)std::max<int64_t>(n, 1) * 4), off_b = 16;
+  const size_t ids_b = up16((size_t)n_exclude * 4), bits_b = n_exclude ? up16((size_t)db->excl_words * 4) : 0;
+  const size_t key_b = up16((size_t)n_padded * 8), id_b = up16((size_t)n_padded * 4);
+  const size_t o_db = up16((size_t)k * 4), o_key = up16((size_t)k * 8), o_cnt = 16;
+  const size_t out_b = o_db + o_key + o_cnt;
+  int rc = ensure_stage(db, ord_b + pos_b + off_b + ids_b + bits_b + key_b + id_b + out_b, std::max(off_b + ids_b, out_b));
+  if (rc) return rc;
+  uint8_t* d = static_cast<uint8_t*>(db->d_stage);
+  uint8_t* h = static_cast<uint8_t*>(db->h_stage);
+  cudaStream_t st = db->stream;
+  if (n_order) SSW_CUDA(cudaMemcpyAsync(d, row_order, (size_t)n_order * 8, cudaMemcpyHostToDevice, st));
+  uint32_t* d_pos = reinterpret_cast<uint32_t*>(d + ord_b);
+  if ((rc = launch_order_to_pos(reinterpret_cast<const int64_t*>(d), n_order, n, d_pos, st))) return rc;
+  uint32_t* d_bits = nullptr;
+  uint8_t* p = d + ord_b + pos_b;
+  if (n_exclude) {
+    int64_t* off = reinterpret_cast<int64_t*>(h);
+    off[0] = 0;
+    off[1] = n_exclude;
+    memcpy(h + off_b, exclude_dbidx, (size_t)n_exclude * 4);
+    SSW_CUDA(cudaMemcpyAsync(p, h, off_b + ids_b, cudaMemcpyHostToDevice, st));
+    d_bits = reinterpret_cast<uint32_t*>(p + off_b + ids_b);
+    rc = launch_exclude_build(db, reinterpret_cast<const int32_t*>(p + off_b), reinterpret_cast<const int64_t*>(p), 1, d_bits, st);
+    if (rc) return rc;
+  }
+  p += off_b + ids_b + bits_b;
+  uint64_t* d_keys = reinterpret_cast<uint64_t*>(p);
+  int32_t* d_ids = reinterpret_cast<int32_t*>(p + key_b);
+  rc = launch_image_max(db, nullptr, nullptr, d_bits, n_padded, d_keys, d_ids, st, d_pos);
+  if (rc) return rc;
+  uint8_t* d_out = p + key_b + id_b;
+  rc = launch_merge(d_keys, d_ids, (int)n_lists, k, n_padded, 1, k, nullptr, reinterpret_cast<uint64_t*>(d_out + o_db),
+                    reinterpret_cast<int32_t*>(d_out), nullptr, nullptr, reinterpret_cast<int32_t*>(d_out + o_db + o_key), st);
+  if (rc) return rc;
+  SSW_CUDA(cudaStreamSynchronize(st));      // the uploads above read pageable host memory: finish before h is reused
+  SSW_CUDA(cudaMemcpyAsync(h, d_out, out_b, cudaMemcpyDeviceToHost, st));
+  SSW_CUDA(cudaStreamSynchronize(st));
+  int cnt = 0;
+  memcpy(&cnt, h + o_db + o_key, 4);
+  const uint64_t* keys = reinterpret_cast<const uint64_t*>(h + o_db);
+  for (int i = 0; i < k; ++i) {
+    const bool ok = i < cnt;
+    if (out_dbidx) out_dbidx[i] = ok ? reinterpret_cast<const int32_t*>(h)[i] : -1;
+    if (out_pos) out_pos[i] = ok ? (int64_t)(0xFFFFFFFFull - (keys[i] >> 32)) : -1;
+    if (out_row) out_row[i] = ok ? (int64_t)key_row(keys[i]) : -1;
+  }
+  if (out_count) *out_count = cnt;
+  return SSW_OK;
+}
+
 int ssw_scan_topk(ssw_db* db, const float* queries, int nq, int k, const int32_t* exclude_dbidx,
                   const int64_t* exclude_offsets, int32_t* out_dbidx, float* out_score, int64_t* out_row,
                   int32_t* out_count) {

@@ -109,7 +109,8 @@ int launch_exchange_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_
                           int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row, int32_t* d_out_count,
                           cudaStream_t st, bool pdl = false, const int32_t* d_counts = nullptr);
 int launch_image_max(ssw_db* db, const float* d_scores, const uint8_t* d_row_mask, const uint32_t* d_excl,
-                     int64_t n_padded, uint64_t* d_keys, int32_t* d_dbidx, cudaStream_t st);
+                     int64_t n_padded, uint64_t* d_keys, int32_t* d_dbidx, cudaStream_t st, const uint32_t* d_pos = nullptr);
+int launch_order_to_pos(const int64_t* d_order, int64_t n_order, int64_t n_rows, uint32_t* d_pos, cudaStream_t st);
 int launch_exclude_build(ssw_db* db, const int32_t* d_ids, const int64_t* d_offsets, int nq, uint32_t* d_bits,
                          cudaStream_t st);
 int launch_synth(void* d_out, int dtype, int64_t n_rows, int dim, int64_t global_row0, uint64_t seed, int kind,

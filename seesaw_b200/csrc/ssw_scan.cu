@@ -869,12 +869,15 @@ __global__ void __launch_bounds__(kMergeThreads, 1) exchange_merge_kernel(const 
       pd[i] = i < m ? M.od[i] : -1;
     }
   }
-  __threadfence_system();
+  // Publication: the block's stores are ordered before the barrier (CTA scope); the few threads that raise the flags
+  // then fence at system scope — fences are cumulative, so the whole block's stores are visible to a peer that
+  // acquires the flag.  (A system-scope fence in all 1024 threads cost a third of this kernel: ncu, ERRBAR stalls.)
   __syncthreads();
   if (tid < x.world) {
     uint8_t* base = static_cast<uint8_t*>(x.peers[tid]);
     uint32_t* flag = reinterpret_cast<uint32_t*>(base + xchg_keys_bytes(x.world, x.nq_cap, x.k_cap) +
                                                  xchg_dbidx_bytes(x.world, x.nq_cap, x.k_cap)) + slot;
+    __threadfence_system();
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(x.epoch) : "memory");
   }
   // ---- 3. wait until every rank's slot of THIS rank's buffer carries this epoch
@@ -964,7 +967,10 @@ int launch_exclude_build(ssw_db* db, const int32_t* d_ids, const int64_t* d_offs
 // label propagation, KnnProp2.next_batch -> _get_top_dbidxs, seesaw/loops/graph_based.py:97-99).
 // One thread per image walks the image's rows; the top-k over the image keys is K4's job.
 // ------------------------------------------------------------------------------------------
-__global__ void image_max_kernel(const float* __restrict__ scores, const uint8_t* __restrict__ row_mask,
+// `pos` non-null: rank by the caller's ORDER instead of a score — pos[o] = position of original row o in the caller's
+// best-first row list (0xFFFFFFFF = not listed); an image's best row is its earliest-listed one.
+__global__ void image_max_kernel(const float* __restrict__ scores, const uint32_t* __restrict__ pos,
+                                 const uint8_t* __restrict__ row_mask,
                                  const int64_t* __restrict__ row_ptr, const int64_t* __restrict__ orig_row,
                                  const int32_t* __restrict__ img_dbidx, const uint32_t* __restrict__ excl,
                                  int64_t row_base, int64_t n_images, int64_t n_padded, uint64_t* __restrict__ keys_out,
@@ -977,9 +983,16 @@ __global__ void image_max_kernel(const float* __restrict__ scores, const uint8_t
       for (int64_t r = row_ptr[i]; r < row_ptr[i + 1]; ++r) {
         const int64_t o = orig_row ? orig_row[r] : r;
         if (row_mask && !row_mask[o]) continue;
-        const float sc = scores[o];
-        if (sc != sc) continue;                       // NaN never ranks
-        const uint64_t key = make_key(sc, (uint32_t)(row_base + o));
+        uint64_t key;
+        if (pos) {
+          const uint32_t p = pos[o];
+          if (p == 0xFFFFFFFFu) continue;
+          key = ((uint64_t)(0xFFFFFFFEu - p) + 1ull) << 32 | (uint64_t)(0xFFFFFFFFu - (uint32_t)(row_base + o));
+        } else {
+          const float sc = scores[o];
+          if (sc != sc) continue;                       // NaN never ranks
+          key = make_key(sc, (uint32_t)(row_base + o));
+        }
         best = key > best ? key : best;
       }
     }
@@ -988,11 +1001,27 @@ __global__ void image_max_kernel(const float* __restrict__ scores, const uint8_t
   }
 }
 
+__global__ void order_to_pos_kernel(const int64_t* __restrict__ order, int64_t n_order, int64_t n_rows, uint32_t* __restrict__ pos) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_order; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o = order[p];
+    if (o >= 0 && o < n_rows) atomicMin(pos + o, (uint32_t)p);      // a row listed twice counts at its first position
+  }
+}
+
+int launch_order_to_pos(const int64_t* d_order, int64_t n_order, int64_t n_rows, uint32_t* d_pos, cudaStream_t st) {
+  SSW_CUDA(cudaMemsetAsync(d_pos, 0xFF, (size_t)std::max<int64_t>(n_rows, 1) * 4, st));
+  if (n_order == 0) return SSW_OK;
+  const int grid = (int)std::min<int64_t>((n_order + 255) / 256, 148 * 16);
+  order_to_pos_kernel<<<grid, 256, 0, st>>>(d_order, n_order, n_rows, d_pos);
+  SSW_LAUNCHED();
+  return SSW_OK;
+}
+
 int launch_image_max(ssw_db* db, const float* d_scores, const uint8_t* d_row_mask, const uint32_t* d_excl,
-                     int64_t n_padded, uint64_t* d_keys, int32_t* d_dbidx, cudaStream_t st) {
+                     int64_t n_padded, uint64_t* d_keys, int32_t* d_dbidx, cudaStream_t st, const uint32_t* d_pos) {
   if (n_padded == 0) return SSW_OK;
   const int grid = (int)std::min<int64_t>((n_padded + 255) / 256, 148 * 16);
-  image_max_kernel<<<grid, 256, 0, st>>>(d_scores, d_row_mask, db->d_row_ptr, db->d_orig_row, db->d_img_dbidx, d_excl,
+  image_max_kernel<<<grid, 256, 0, st>>>(d_scores, d_pos, d_row_mask, db->d_row_ptr, db->d_orig_row, db->d_img_dbidx, d_excl,
                                          db->row_base, db->n_images, n_padded, d_keys, d_dbidx);
   SSW_LAUNCHED();
   return SSW_OK;

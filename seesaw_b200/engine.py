@@ -210,6 +210,18 @@ class PatchDatabase:
         n = int(cnt[0])
         return dict(dbidx=out_dbidx[:n], score=out_score[:n], row=out_row[:n])
 
+    def topk_from_order(self, row_order, k, exclude=None):
+        """Top-k images from rows ALREADY ranked by the caller (best first): the input ``_get_top_dbidxs`` itself
+        takes.  Returns dict(dbidx, pos, row) trimmed to the count; ``pos`` indexes ``row_order``."""
+        order = np.ascontiguousarray(np.asarray(row_order, dtype=np.int64).reshape(-1))
+        ids = np.zeros(0, np.int32) if exclude is None else _ids(exclude)
+        out_dbidx, out_pos = np.empty(k, np.int32), np.empty(k, np.int64)
+        out_row, cnt = np.empty(k, np.int64), np.zeros(1, np.int32)
+        check(lib.ssw_topk_from_order(self._h, ptr(order), len(order), int(k), ptr(ids), len(ids), ptr(out_dbidx), ptr(out_pos),
+                                      ptr(out_row), ptr(cnt)))
+        n = int(cnt[0])
+        return dict(dbidx=out_dbidx[:n], pos=out_pos[:n], row=out_row[:n])
+
     def score_all(self, query):
         q = np.ascontiguousarray(np.asarray(query, dtype=np.float32).reshape(-1))
         assert q.shape[0] == self.dim

@@ -155,17 +155,19 @@ class _GpuIndexMixin:
     def top_dbidxs(self, *, vec_idxs, scores, exclude=None, topk):
         """``_get_top_dbidxs(vec_idxs=, scores=, vector_meta=, exclude=, topk=)`` (multiscale_index.py:189-199)
         for scores that did not come from this index's scan — KnnProp2.next_batch passes the rows sorted by
-        label-propagation score (loops/graph_based.py:97-99).  Only the rows in ``vec_idxs`` take part;
-        their order does not matter (the reference's is score-sorted).  Returns DataFrame(dbidx, max_score)."""
+        label-propagation score (loops/graph_based.py:97-99).  Like the reference it walks the rows IN THE GIVEN
+        ORDER (``vec_idxs`` best first, ``scores`` aligned with it): per image the earliest-listed row, images ranked
+        by that position, excluded images dropped, the first ``topk`` — on the device, independent of the scores'
+        dtype (float64 propagation scores are not squeezed into float32).  Returns DataFrame(dbidx, max_score, best_row)."""
         vec_idxs = np.asarray(vec_idxs, dtype=np.int64).reshape(-1)
-        dense = np.zeros(len(self._dbidx_of_row), np.float32)
-        dense[vec_idxs] = np.asarray(scores, dtype=np.float32).reshape(-1)
-        mask = None
-        if len(vec_idxs) != len(dense):
-            mask = np.zeros(len(dense), np.uint8)
-            mask[vec_idxs] = 1
-        r = self.db.topk_from_scores(dense, int(topk), exclude=as_id_array(exclude), row_mask=mask)
-        return pd.DataFrame({"dbidx": r["dbidx"].astype(np.int64), "max_score": r["score"], "best_row": r["row"]})
+        scores = np.asarray(scores).reshape(-1)
+        r = self.db.topk_from_order(self._unmap_rows(vec_idxs), int(topk), exclude=as_id_array(exclude))
+        return pd.DataFrame({"dbidx": r["dbidx"].astype(np.int64), "max_score": scores[r["pos"]],
+                             "best_row": self._map_rows(r["row"])})
+
+    def _unmap_rows(self, rows):
+        """positions in this index's vectors -> ORIGINAL rows of the database (identity, except for a shared subset)."""
+        return rows
 
     def string2vec(self, string: str) -> np.ndarray:
         init_vec = self.embedding.from_string(string=string)
@@ -354,11 +356,12 @@ class _SharedSubset(B200MultiscaleIndex):
     def score(self, vec):
         return self._parent.score(vec)[self._parent_rows]
 
+    def _unmap_rows(self, rows):
+        return self._parent_rows[np.asarray(rows, dtype=np.int64)]
+
     def top_dbidxs(self, *, vec_idxs, scores, exclude=None, topk):
         ex = np.concatenate([as_id_array(exclude), self._complement])
-        r = self._parent.top_dbidxs(vec_idxs=self._parent_rows[np.asarray(vec_idxs, dtype=np.int64)], scores=scores,
-                                    exclude=ex, topk=topk)
-        return r.assign(best_row=self._map_rows(r["best_row"].to_numpy()))
+        return super().top_dbidxs(vec_idxs=vec_idxs, scores=scores, exclude=ex, topk=topk)
 
     def subset(self, indices, share_device=True):
         keep_rows = np.isin(self._parent._dbidx_of_row, np.intersect1d(as_id_array(indices), self._img_ids))

@@ -168,10 +168,32 @@ def compute_knn_from_nndescent(vectors, *, n_neighbors, n_jobs=-1, low_memory=Fa
     return compute_exact_knn(vectors, n_neighbors, device=device)
 
 
+def get_weight_matrix_device(df, *, kfun, device=0, return_weight_sum=False):
+    """The matrix label propagation runs over — get_weight_matrix(df, kfun=, self_edges=False, normalized=False,
+    symmetric=True) (knn_graph.py:31-104, as loops/graph_based.py:36-43 calls it) — built on the GPU (C ABI
+    ``ssw_weight_matrix``): mirror look-ups, row sizes, scan, scatter and per-row ordering for the ~2 k N entries run as
+    six small kernels; ``kfun`` is evaluated here with numpy, so the weights are the reference's own values and the CSR
+    arrays come out bit-identical to scipy's.  Returns a scipy ``csr_array`` (and W.sum(0) when asked)."""
+    import scipy.sparse as sp
+    src = np.ascontiguousarray(df["src_vertex"].to_numpy(), dtype=np.int32)
+    dst = np.ascontiguousarray(df["dst_vertex"].to_numpy(), dtype=np.int32)
+    w = np.ascontiguousarray(np.asarray(kfun(df["distance"].to_numpy()), dtype=np.float64))
+    assert (w >= 0).all(), "edge weights must be non-negative"
+    n_edges = len(src)
+    n = int(src[-1]) + 1 if n_edges else 0
+    indptr = np.empty(n + 1, np.int64)
+    indices, data = np.empty(2 * n_edges, np.int32), np.empty(2 * n_edges, np.float64)
+    wsum = np.empty(n, np.float64)
+    nnz = C.c_int64()
+    check(lib.ssw_weight_matrix(int(device), ptr(src), ptr(dst), ptr(w), n_edges, n, ptr(indptr), ptr(indices), ptr(data),
+                                2 * n_edges, C.byref(nnz), ptr(wsum)))
+    W = sp.csr_array((data[:nnz.value].copy(), indices[:nnz.value].copy(), indptr), shape=(n, n))
+    return (W, wsum) if return_weight_sum else W
+
+
 def get_weight_matrix(df, *, kfun, self_edges=False, normalized, laplacian=False, symmetric=True):
-    """Weight matrix / graph Laplacian of a kNN edge table — get_weight_matrix (knn_graph.py:31-104), the input of
-    label propagation.  One-off host step (scipy); stated here so the graph chain compute_exact_knn ->
-    get_weight_matrix -> B200LabelPropagation lives in one package.  Same semantics: weights kfun(distance), an
+    """Weight matrix / graph Laplacian of a kNN edge table — get_weight_matrix (knn_graph.py:31-104), all variants,
+    on the host (scipy); the variant label propagation uses has a device form, :func:`get_weight_matrix_device`.  Same semantics: weights kfun(distance), an
     edge listed from both ends gets the mean of its two weights, one listed from one end keeps its weight, the
     diagonal is stored as explicit zeros (the reference's setdiag(0.) keeps them), CSR with sorted indices;
     ``laplacian`` gives D - W (optionally D^-1/2 (D - W) D^-1/2)."""

@@ -145,6 +145,9 @@ class ScanServer:
                     elif op == "topk_from_scores":
                         sc, k, kw = args
                         out = self.db.topk_from_scores(sc, k, **kw)
+                    elif op == "topk_from_order":
+                        order, k, ex = args
+                        out = self.db.topk_from_order(order, k, exclude=ex)
                     elif op == "info":
                         out = self.info()
                     elif op == "stats":
@@ -246,6 +249,9 @@ class ScanClient:
     def topk_from_scores(self, scores, k, exclude=None, row_mask=None):
         return self._call("topk_from_scores", (np.asarray(scores, np.float32), int(k),
                                                dict(exclude=None if exclude is None else np.asarray(exclude), row_mask=row_mask)))
+
+    def topk_from_order(self, row_order, k, exclude=None):
+        return self._call("topk_from_order", (np.asarray(row_order, np.int64), int(k), None if exclude is None else np.asarray(exclude)))
 
     def set_boxes(self, *a, **k):
         """The server's database already holds the boxes (set once by the GPU-owning process)."""

@@ -53,5 +53,10 @@ class FakeDB:
         d, s, r = orc.get_top_dbidxs(order, np.asarray(scores)[order], self.dbidx, exclude, k)
         return dict(dbidx=d.astype(np.int32), score=s.astype(np.float32), row=r.astype(np.int64))
 
+    def topk_from_order(self, row_order, k, exclude=None):
+        order = np.asarray(row_order, dtype=np.int64)
+        d, pos, r = orc.get_top_dbidxs(order, np.arange(len(order)), self.dbidx, exclude, k)
+        return dict(dbidx=d.astype(np.int32), pos=pos.astype(np.int64), row=r.astype(np.int64))
+
     def close(self):
         self.closed = True

@@ -342,6 +342,20 @@ def test_topk_from_scores_matches_get_top_dbidxs(eng, grouped):
         d, s, r = orc.get_top_dbidxs(order, scores[order], dbidx, ex, k)
         assert len(got) == len(d)
         assert (got.dbidx.values == d).all() and (got.max_score.values == s).all() and (got.best_row.values == r).all()
+        # the score-keyed entry point (ssw_topk_from_scores): float32 scores per row, ties to the lower row
+        dense, mask = np.zeros(n, np.float32), np.zeros(n, np.uint8)
+        dense[rows], mask[rows] = scores[rows], 1
+        g2 = idx.db.topk_from_scores(dense, k, exclude=ex, row_mask=None if frac == 1 else mask)
+        assert (g2["dbidx"] == d).all() and (g2["score"] == s).all() and (g2["row"] == r).all()
+    # float64 propagation scores that differ only beyond float32 precision, handed over in the CALLER'S order (ties in
+    # arbitrary order, as an unstable argsort leaves them): the result follows that order exactly
+    s64 = 0.5 + rng.integers(0, 40, size=n) * 1e-13
+    order = rng.permutation(n)
+    order = order[np.argsort(-s64[order], kind="stable")]
+    got = idx.top_dbidxs(vec_idxs=order, scores=s64[order], exclude=ids[::5], topk=60)
+    d, s, r = orc.get_top_dbidxs(order, s64[order], dbidx, ids[::5], 60)
+    assert got.max_score.dtype == np.float64 and len(np.unique(s64.astype(np.float32))) == 1
+    assert (got.dbidx.values == d).all() and (got.max_score.values == s).all() and (got.best_row.values == r).all()
     idx.close()
 
 
