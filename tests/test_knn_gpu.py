@@ -169,4 +169,5 @@ def test_float32_near_duplicates_fall_back_to_the_full_rescan():
         for a, b in zip(idx[r], oi[r]):
             if a != b:
                 assert abs(d64[r, a] - d64[r, b]) <= 1e-6, (r, a, b)       # fp32 resolution of a 512-term dot near 1
-    assert dist[3, 0] == dist[3, 1] and {3, 7} <= set(idx[3].tolist()) and {3, 7} <= set(idx[7].tolist())
+    # rows 3 and 7 hold the same vector: identical distance rows, and column tie-breaking does not depend on the row
+    assert (idx[3] == idx[7]).all() and (dist[3] == dist[7]).all()
