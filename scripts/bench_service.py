@@ -75,7 +75,7 @@ def run(n_sessions, n_req, max_wait_s):
 if __name__ == "__main__":
     res = {"workload": f"{N_IMAGES * PATCHES} x {DIM} fp16, top-{K}, 50 excluded ids per session; one request in flight per session process",
            "runs": []}
-    for n_sessions, wait in ((1, 0.0005), (64, 0.0), (64, 0.0005), (64, 0.002)):
+    for n_sessions, wait in ((1, 0.002), (8, 0.002), (64, 0.0), (64, 0.0005), (64, 0.002)):
         res["runs"].append(run(n_sessions, 200 if n_sessions > 1 else 100, wait))
         print(json.dumps(res["runs"][-1]), file=sys.stderr, flush=True)
     print(json.dumps(res))

@@ -127,7 +127,7 @@ def test_session_processes_share_one_server_process(tmp_path):
         assert ssum == float((vecs @ qs[i]).sum()) and n_rows == len(vecs)
     assert stats["queries_served"] == 24 and stats["batches_issued"] < 24       # batched across processes
     with pytest.raises(RuntimeError):
-        c._call("scan", (np.zeros((2, 255), np.float32), 3, None))      # wrong width -> server-side error, server survives
+        c._call("scan_topk", np.zeros((2, 255), np.float32), 3)         # wrong width -> server-side error, server survives
     assert c.stats()["queries_served"] == 24
     c.shutdown_server()
     server.join(30)
