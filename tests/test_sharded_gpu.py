@@ -35,6 +35,40 @@ def _check(res, counts, dbidx, n, qs, excl, k):
         assert (got["score"][i, :m] == o["max_score"]).all(), i
 
 
+def _exact_sharded_check(rank, world):
+    """Exact mode across shards: float32 unit vectors (not fp16-representable) in fp16 storage + float32 copy; every
+    shard certifies its own float32 top-k, the fused exchange merges them — the float32 oracle's ids, 1e-5 scores."""
+    from seesaw_b200.engine import PatchDatabase
+    from seesaw_b200.sharded import ShardedPatchDatabase, shard_image_ranges
+    counts = synth.patches_per_image(3000, 2, 20, 31)
+    dbidx = synth.dbidx_of_rows(counts, dbidx_start=4, dbidx_stride=3)
+    n = int(counts.sum())
+    vecs = synth.unit_rows(n, 512, 32)
+    qs = synth.unit_queries(9, 512, 33)
+    ids = np.unique(dbidx)
+    excl = [ids[i::13] for i in range(len(qs))]
+    bounds = shard_image_ranges(counts, world)
+    cum = np.concatenate([[0], np.cumsum(counts)])
+    r0, r1 = int(cum[bounds[rank]]), int(cum[bounds[rank + 1]])
+    local = PatchDatabase.from_arrays(vecs[r0:r1], dbidx[r0:r1], store="f16", device=rank, global_row_base=r0, exact=True)
+    sdb = ShardedPatchDatabase(local, rank=rank, world_size=world)
+    sdb.enable_fused_exchange(nq_cap=32, k_cap=64)
+    for batch in (slice(0, 9), slice(0, 1)):
+        res = sdb.scan_topk(qs[batch], 50, exclude=excl[batch])
+        for j, i in enumerate(range(*batch.indices(len(qs)))):
+            o = orc.query_prelim(vecs, dbidx, qs[i], 50, exclude=excl[i])
+            np.testing.assert_allclose(res["score"][j], o["max_score"], rtol=1e-5, atol=1e-7)
+            if not (res["dbidx"][j] == o["dbidx"]).all():          # only float32 near-ties may swap
+                s64 = orc.scores_f64(vecs, qs[i])
+                d, s, _ = orc.per_image_best(s64, dbidx, excl[i])
+                best = dict(zip(d.tolist(), s.tolist()))
+                for a, b in zip(res["dbidx"][j].tolist(), o["dbidx"].tolist()):
+                    assert a == b or abs(best[a] - best[b]) <= 1e-5 * abs(best[b]), (i, a, b)
+            assert (dbidx[res["row"][j]] == res["dbidx"][j]).all()          # rows are GLOBAL original rows
+    assert local.exact_info()["queries"] == 10
+    sdb.close()
+
+
 def test_sharded_world1():
     import torch
     from seesaw_b200.sharded import ShardedPatchDatabase
@@ -48,6 +82,7 @@ def test_sharded_world1():
             torch.cuda.synchronize()
             _check(res, counts, dbidx, n, qs, excl, k)
     sdb.close()
+    _exact_sharded_check(0, 1)
 
 
 def _worker(rank, world, port, out_dir):
@@ -73,6 +108,8 @@ def _worker(rank, world, port, out_dir):
         _check({n: torch.from_numpy(v) for n, v in res.items()}, counts, dbidx, n, qs, excl, k)
     dist.barrier()
     sdb.close()
+    _exact_sharded_check(rank, world)
+    dist.barrier()
     dist.destroy_process_group()
     open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
 
