@@ -522,7 +522,8 @@ static int scan_topk_impl(ssw_db* db, const float* d_queries, int nq, int k, con
                           uint64_t* d_out_key, int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row,
                           int32_t* d_out_count, cudaStream_t st, const XchgCtx* xc = nullptr, bool exact_rows = false) {
   const int lists = db->scan_grid;
-  int rc = ensure_lists(db, nq, lists, k);
+  const int kl = k + kScanTcSlack;           // slots per (query, CTA): the batched scan publishes up to k + slack entries
+  int rc = ensure_lists(db, nq, lists, kl);
   if (rc) return rc;
   const bool tc_ok = scan_tc_supported(db, k) && !exact_rows;
   if (db->scan_mode == 2 && !tc_ok && !exact_rows) {
@@ -536,7 +537,7 @@ static int scan_topk_impl(ssw_db* db, const float* d_queries, int nq, int k, con
       const int nb = std::min(SSW_MAX_BATCH, nq - q0);
       rc = launch_scan_tc(db, d_queries + (size_t)q0 * db->dim, nb, k,
                           d_exclude_bits ? d_exclude_bits + (size_t)q0 * db->excl_words : nullptr,
-                          db->d_list_keys + (size_t)q0 * lists * k, db->d_list_dbidx + (size_t)q0 * lists * k,
+                          db->d_list_keys + (size_t)q0 * lists * kl, db->d_list_dbidx + (size_t)q0 * lists * kl,
                           db->d_cand_cnt + q0, db->d_gthr + q0, db->d_tc_ws, st);
       if (rc) return rc;
     }
@@ -557,13 +558,13 @@ static int scan_topk_impl(ssw_db* db, const float* d_queries, int nq, int k, con
       SSW_CUDA(cudaHostAlloc((void**)&db->d_xchg_timed_out, 4, cudaHostAllocMapped));
       *db->d_xchg_timed_out = 0;
     }
-    return launch_exchange_merge(db->d_list_keys, db->d_list_dbidx, lists, k, (int64_t)lists * k, nq, k, db->d_gthr,
+    return launch_exchange_merge(db->d_list_keys, db->d_list_dbidx, lists, k, (int64_t)lists * (use_tc ? kl : k), nq, k, db->d_gthr,
                                  xc->peers, xc->world, xc->rank, xc->nq_cap, xc->k_cap, xc->epoch, db->d_xchg_timed_out,
                                  d_out_key, d_out_dbidx, d_out_score, d_out_row, d_out_count, st, use_tc && !db->prof_sampled,
                                  use_tc ? db->d_cand_cnt : nullptr);
   }
   // after the batched scan the merge is a programmatic dependent launch (the scan triggers it early)
-  return launch_merge(db->d_list_keys, db->d_list_dbidx, lists, k, (int64_t)lists * k, nq, k, db->d_gthr,
+  return launch_merge(db->d_list_keys, db->d_list_dbidx, lists, k, (int64_t)lists * (use_tc ? kl : k), nq, k, db->d_gthr,
                       d_out_key, d_out_dbidx, d_out_score, d_out_row, d_out_count, st, use_tc && !db->prof_sampled,
                       use_tc ? db->d_cand_cnt : nullptr);
 }

@@ -93,7 +93,8 @@ int launch_row_error_stats(const float* d_rows_f32, int64_t n_rows, int dim, flo
 // tcgen05 batched scan (K2): one pass for up to 64 queries; fp16 storage, dim 256/512/768, k <= 64
 bool scan_tc_supported(const ssw_db* db, int k);
 size_t scan_tc_workspace_bytes(int dim, int grid);
-// d_cand_keys / d_cand_dbidx: [nq][grid * k] compacted candidates, d_cand_cnt [nq] their number per query
+// d_cand_keys / d_cand_dbidx: [nq][grid * (k + kScanTcSlack)] compacted candidates, d_cand_cnt [nq] their number per query
+constexpr int kScanTcSlack = 8;
 int launch_scan_tc(ssw_db* db, const float* d_queries, int nq, int k, const uint32_t* d_excl, uint64_t* d_cand_keys,
                    int32_t* d_cand_dbidx, int32_t* d_cand_cnt, uint64_t* d_gthr, void* workspace, cudaStream_t st);
 // merge kernel (K4)

@@ -944,10 +944,16 @@ __global__ void exclude_build_kernel(const int32_t* ids, const int64_t* offsets,
   const int64_t b = offsets[q], e = offsets[q + 1];
   for (int64_t i = b + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < e; i += (int64_t)gridDim.x * blockDim.x) {
     const int32_t id = ids[i];
-    int64_t lo = 0, hi = n_images;      // first position with img_dbidx >= id
-    while (lo < hi) {
-      const int64_t mid = (lo + hi) >> 1;
-      if (img_dbidx[mid] < id) lo = mid + 1; else hi = mid;
+    // image ids are usually consecutive (dbidx = position in the dataset): try that slot first — one load instead
+    // of log2(n_images) dependent ones (the search was 8 of the ~55 us the host-buffer path adds to a step)
+    int64_t lo = (int64_t)id - (int64_t)img_dbidx[0];
+    if (lo < 0 || lo >= n_images || img_dbidx[lo] != id) {
+      lo = 0;
+      int64_t hi = n_images;            // first position with img_dbidx >= id
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (img_dbidx[mid] < id) lo = mid + 1; else hi = mid;
+      }
     }
     if (lo < n_images && img_dbidx[lo] == id) atomicOr(bits + (int64_t)q * words + (lo >> 5), 1u << (lo & 31));
   }
@@ -956,6 +962,7 @@ __global__ void exclude_build_kernel(const int32_t* ids, const int64_t* offsets,
 int launch_exclude_build(ssw_db* db, const int32_t* d_ids, const int64_t* d_offsets, int nq, uint32_t* d_bits,
                          cudaStream_t st) {
   SSW_CUDA(cudaMemsetAsync(d_bits, 0, (size_t)nq * db->excl_words * 4, st));
+  if (db->n_images == 0) return SSW_OK;
   dim3 grid(8, nq);
   exclude_build_kernel<<<grid, 256, 0, st>>>(d_ids, d_offsets, db->d_img_dbidx, db->n_images, db->excl_words, d_bits);
   SSW_LAUNCHED();

@@ -68,6 +68,7 @@ struct ScanTcArgs {
 #endif
 
 constexpr int kTcMaxK = 64;   // per-query list length the batched epilogue keeps in shared memory
+constexpr int kTcSlack = 8;   // extra list slots: entries are appended and the list is cut back to k when it overflows
 
 // ------------------------------------------------------------------------------------------
 // query preparation: fp32 [nq, DIM] -> hi/lo fp16 image of the A operand, scales, zeroed thresholds
@@ -124,24 +125,24 @@ __global__ void scan_tc_prep_kernel(const float* __restrict__ q, int nq, int dim
 
 // Per-query epilogue state in SHARED memory (structure of arrays over the 64 query slots).
 struct QShared {
-  uint64_t* keys;       // [k][64]   candidate keys, slot s of query q at keys[s*64 + q]
-  int32_t* img;         // [k][64]   local image index of the candidate
-  uint64_t* thr;        // [64] reject keys <= thr: max(own k-th best once full, shared lower bound)
-  int32_t* cnt;         // [64]
-  int32_t* minpos;      // [64]
+  uint64_t* keys;       // [k + kTcSlack][64]   candidate keys, slot s of query q at keys[s*64 + q]
+  int32_t* img;         // [k + kTcSlack][64]   local image index of the candidate
+  uint64_t* thr;        // [64] reject keys <= thr: max(own k-th best after a compaction, shared lower bound)
+  int32_t* cnt;         // [64] entries held (<= k + kTcSlack)
+  int32_t* minpos;      // [64] (unused)
   uint32_t* best;       // [64] order-preserving score bits of the best candidate held (published to the other CTAs)
   int* done;            // epilogue warps that have finished (the threshold warp leaves at 8)
   uint32_t* upd;        // [64] list updates of this CTA (appends + replacements), [64] images offered (past the vote)
   uint32_t* excl;       // [64][slice_words] this CTA's slice of the exclusion bitmaps (optional)
 };
-__host__ __device__ constexpr size_t qshared_bytes(int k) { return (size_t)k * 64 * 12 + 64 * (8 + 4 + 4 + 4 + 8) + 16; }
+__host__ __device__ constexpr size_t qshared_bytes(int k) { return (size_t)(k + kTcSlack) * 64 * 12 + 64 * (8 + 4 + 4 + 4 + 8) + 16; }
 
 __device__ __forceinline__ QShared qshared_carve(uint8_t* base, int k) {
   QShared q;
   q.keys = reinterpret_cast<uint64_t*>(base);
-  q.thr = q.keys + (size_t)k * 64;
+  q.thr = q.keys + (size_t)(k + kTcSlack) * 64;
   q.img = reinterpret_cast<int32_t*>(q.thr + 64);
-  q.cnt = q.img + (size_t)k * 64;
+  q.cnt = q.img + (size_t)(k + kTcSlack) * 64;
   q.minpos = q.cnt + 64;
   q.best = reinterpret_cast<uint32_t*>(q.minpos + 64);
   q.done = reinterpret_cast<int*>(q.best + 64);
@@ -156,13 +157,14 @@ __device__ __forceinline__ float thr_to_acc(uint64_t thr, float scale) {
 }
 
 // Owner thread of query q: the finished image `img` peaked at accumulator value `best` in device row
-// `drow`.  Applies the threshold, the exclusion bitmap and the list update; returns the (possibly
-// raised) threshold key of the query.
-__device__ __forceinline__ uint64_t scan_tc_offer(const QShared& Q, const ScanTcArgs& a, int q, float best,
-                                                  float inv_scale, int64_t drow, int img, int slice_base) {
-  const int k = a.k;
-  // every shared-memory word the common (append) path needs is loaded up front: one LDS latency instead of
-  // a chain of five dependent ones — this path runs for every image until the first pooled threshold arrives
+// `drow`.  Applies the threshold and the exclusion bitmap and APPENDS the candidate to the query's list; sets
+// `full` when the list has reached its k + kTcSlack slots (the warp then cuts it back to k: scan_tc_compact).
+// A list is never searched for its minimum on insertion: on data whose scores rise along a CTA's range every
+// image replaces the weakest entry, and a k-entry rescan per image by one thread made that CTA the straggler of
+// the whole launch (10M rows sorted by one query's score: 3.3 ms instead of 1.55 ms).
+__device__ __forceinline__ void scan_tc_offer(const QShared& Q, const ScanTcArgs& a, int q, float best,
+                                              float inv_scale, int64_t drow, int img, int slice_base, bool& full) {
+  // every shared-memory word the path needs is loaded up front: one LDS latency instead of a chain of dependent ones
   const uint64_t thr = Q.thr[q];
   const int cnt = Q.cnt[q];
   const uint32_t best_seen = Q.best[q];
@@ -170,13 +172,13 @@ __device__ __forceinline__ uint64_t scan_tc_offer(const QShared& Q, const ScanTc
   if (a.excl && a.excl_slice_words > 0) xw = Q.excl[q * a.excl_slice_words + (img >> 5) - slice_base];
   uint64_t key = make_key(best * inv_scale, (uint32_t)drow);
   ++Q.upd[64 + q];
-  if ((key >> 32) < (thr >> 32)) return thr;
+  if ((key >> 32) < (thr >> 32)) return;
   const int64_t orow = a.orig_row ? a.orig_row[drow] : drow;
   key = (key & 0xFFFFFFFF00000000ull) | (uint64_t)(0xFFFFFFFFu - (uint32_t)(a.row_base + orow));
-  if (key <= thr) return thr;
+  if (key <= thr) return;
   if (a.excl) {
     if (a.excl_slice_words == 0) xw = __ldg(a.excl + (size_t)q * a.excl_words + (img >> 5));
-    if ((xw >> (img & 31)) & 1u) return thr;
+    if ((xw >> (img & 31)) & 1u) return;
   }
   if ((uint32_t)(key >> 32) > best_seen) {      // a new best of this CTA: let the other CTAs see it
     Q.best[q] = (uint32_t)(key >> 32);
@@ -184,36 +186,50 @@ __device__ __forceinline__ uint64_t scan_tc_offer(const QShared& Q, const ScanTc
                  "r"((uint32_t)(key >> 32)) : "memory");
   }
   ++Q.upd[q];
-  if (cnt < k) {
-    Q.keys[cnt * 64 + q] = key;
-    Q.img[cnt * 64 + q] = img;
-    Q.cnt[q] = cnt + 1;
-    if (cnt + 1 < k) return thr;
-  } else {
-    const int mp = Q.minpos[q];
-    Q.keys[mp * 64 + q] = key;
-    Q.img[mp * 64 + q] = img;
-  }
-  // new minimum of the full list: eight independent loads in flight, then a compare chain
-  uint64_t mk = ~0ull;
-  int mp = 0;
-#pragma unroll 1
-  for (int s0 = 0; s0 < k; s0 += 8) {
-    uint64_t x[8];
+  Q.keys[cnt * 64 + q] = key;
+  Q.img[cnt * 64 + q] = img;
+  Q.cnt[q] = cnt + 1;
+  full = cnt + 1 >= a.k + kTcSlack;
+}
+
+// All 32 lanes: cut query q's full list (k + kTcSlack entries) back to its k best.  Every lane ranks up to three
+// entries by counting the larger ones (keys are unique, the rank is the slot: the list comes out sorted best
+// first); the k-th key becomes the query's own threshold and is folded into the shared bound.  Returns that key.
+__device__ __forceinline__ uint64_t scan_tc_compact(const QShared& Q, const ScanTcArgs& a, int q, int lane) {
+  const int k = a.k, C = a.k + kTcSlack;        // C <= 72: three slots per lane
+  uint64_t mine[3];
+  int mimg[3], rank[3] = {0, 0, 0};
 #pragma unroll
-    for (int u = 0; u < 8; ++u) x[u] = s0 + u < k ? Q.keys[(s0 + u) * 64 + q] : ~0ull;
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-      if (x[u] < mk) {
-        mk = x[u];
-        mp = s0 + u;
-      }
+  for (int u = 0; u < 3; ++u) {
+    const int e = lane + 32 * u;
+    mine[u] = e < C ? Q.keys[e * 64 + q] : 0ull;
+    mimg[u] = e < C ? Q.img[e * 64 + q] : 0;
   }
-  Q.minpos[q] = mp;
-  // the threshold warp raises Q.thr concurrently: merge with an atomic max
-  const uint64_t old = atomicMax(reinterpret_cast<unsigned long long*>(Q.thr + q), (unsigned long long)mk);
-  atomicMax(reinterpret_cast<unsigned long long*>(a.g_thr + q), (unsigned long long)mk);
-  return mk > old ? mk : old;
+#pragma unroll 4
+  for (int j = 0; j < C; ++j) {
+    const uint64_t x = Q.keys[j * 64 + q];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) rank[u] += x > mine[u];
+  }
+  __syncwarp();
+  uint64_t kth = 0;
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    if (lane + 32 * u < C && rank[u] < k) {
+      Q.keys[rank[u] * 64 + q] = mine[u];
+      Q.img[rank[u] * 64 + q] = mimg[u];
+      if (rank[u] == k - 1) kth = mine[u];
+    }
+  }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) kth |= shfl_xor_u64(kth, m);      // exactly one lane holds it
+  if (lane == 0) {
+    Q.cnt[q] = k;
+    atomicMax(reinterpret_cast<unsigned long long*>(Q.thr + q), (unsigned long long)kth);    // the threshold warp writes too
+    atomicMax(reinterpret_cast<unsigned long long*>(a.g_thr + q), (unsigned long long)kth);
+  }
+  __syncwarp();
+  return kth;
 }
 
 // Threshold warp.  Every CTA publishes the best score it holds per query (a.pub).  Split the G CTAs into
@@ -313,12 +329,23 @@ __device__ __forceinline__ void scan_tc8_boundary(Epi1State& st, const Epi1Ctx& 
     k0 = o0 > k0 ? o0 : k0;
     o0 = shfl_xor_u64(k0, 2);
     k0 = o0 > k0 ? o0 : k0;
+    bool full = false;
     if (cx.owner) {
       const float best = f32_from_ordered((uint32_t)(k0 >> 32));
       if (best >= st.thr) {
         const int col = 0x7FFFFFFF - (int)(uint32_t)(k0 & 0xFFFFFFFFu);
-        const uint64_t nthr = scan_tc_offer(Q, a, cx.own_q, best, cx.inv, cx.r_begin + col, st.cur_img, cx.slice_base);
-        st.thr = thr_to_acc(nthr, cx.scale);
+        scan_tc_offer(Q, a, cx.own_q, best, cx.inv, cx.r_begin + col, st.cur_img, cx.slice_base, full);
+      }
+    }
+    uint32_t need = __ballot_sync(0xffffffffu, full);
+    while (need) {        // rare: a list ran over its slack — the whole warp cuts it back to k
+      const int src = __ffs(need) - 1;
+      need &= need - 1;
+      const int q = __shfl_sync(0xffffffffu, cx.own_q, src);
+      const uint64_t kth = scan_tc_compact(Q, a, q, threadIdx.x & 31);
+      if ((int)(threadIdx.x & 31) == src) {
+        const float t = thr_to_acc(kth, cx.scale);
+        st.thr = t > st.thr ? t : st.thr;
       }
     }
     __syncwarp();
@@ -633,9 +660,9 @@ __global__ void __launch_bounds__(kScanTc8Threads, 1) scan_tc8_kernel(const __gr
     //      round trip, not eight).
     {
       const int nqw = min(8, a.nq - (q4 * 16 + h * 8));
-      const int64_t cap = (int64_t)gridDim.x * k;
-      uint64_t key[8][2];
-      uint32_t mask[8][2];
+      const int64_t cap = (int64_t)gridDim.x * (k + kTcSlack);
+      uint64_t key[8][3];
+      uint32_t mask[8][3];
       int n_pass = 0;                                   // lane qq: entries of query qq that pass
 #pragma unroll
       for (int qq = 0; qq < 8; ++qq) {
@@ -644,7 +671,7 @@ __global__ void __launch_bounds__(kScanTc8Threads, 1) scan_tc8_kernel(const __gr
         const uint64_t thr = qq < nqw ? ld_relaxed_u64(a.g_thr + qi) : ~0ull;
         int tot = 0;
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {                   // k <= 64: two slots per lane
+        for (int u = 0; u < 3; ++u) {                   // k + kTcSlack <= 72: three slots per lane
           const int sl = lane + 32 * u;
           key[qq][u] = sl < cntq ? Q.keys[sl * 64 + qi] : 0ull;
           mask[qq][u] = __ballot_sync(0xffffffffu, key[qq][u] != 0ull && key[qq][u] >= thr);
@@ -659,7 +686,7 @@ __global__ void __launch_bounds__(kScanTc8Threads, 1) scan_tc8_kernel(const __gr
         const int qi = q4 * 16 + h * 8 + qq;
         int o = __shfl_sync(0xffffffffu, base, qq);
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < 3; ++u) {
           if ((mask[qq][u] >> lane) & 1u) {
             const int64_t at = (int64_t)qi * cap + o + __popc(mask[qq][u] & ((1u << lane) - 1u));
             a.cand_keys[at] = key[qq][u];
