@@ -293,6 +293,7 @@ def main():
     ap.add_argument("--no-data-sweep", action="store_true", help="skip roofline_by_data (N=1)")
     ap.add_argument("--no-config5", action="store_true", help="skip the 100M x 768 leg (N=8)")
     ap.add_argument("--nccl-exchange", action="store_true", help="N>1: use NCCL all-gather instead of the fused exchange kernel")
+    ap.add_argument("--no-pipeline", action="store_true", help="N>1: do not overlap a step's exchange with the next step's scan")
     ap.add_argument("--cpu-sample-images", type=int, default=0, help="CPU arm on the first N images only (tests; default: the full database)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -338,17 +339,24 @@ def main():
     sdb = ShardedPatchDatabase.synthetic(rows_per_image, DIM, seed=DB_SEED, rank=rank, world_size=world,
                                          device=local_rank)
     db = sdb.local
-    exchange = "fused peer-memory exchange + merge kernel (ssw_scan_topk_sharded_device)"
+    exchange = ("fused peer-memory exchange + merge kernel, pipelined: the exchange of step i runs under the scan of step i+1 "
+                "(ssw_scan_topk_sharded_pipelined_device)")
     if world > 1 and not args.nccl_exchange:
         sdb.enable_fused_exchange(nq_cap=NQ, k_cap=64)
     elif world > 1:
         exchange = "NCCL all-gather + merge kernel"
+    if world > 1 and args.no_pipeline and not args.nccl_exchange:
+        exchange = "fused peer-memory exchange + merge kernel (ssw_scan_topk_sharded_device)"
     q_host, ex_host = make_queries_and_excludes()
     d_q = torch.from_numpy(q_host).to(dev)
     d_bits = db.build_exclude_bits(ex_host, NQ)
 
+    pipelined = world > 1 and not args.nccl_exchange and not args.no_pipeline
+
     def step_resident():
-        return sdb.scan_topk_device(d_q, TOPK, d_exclude_bits=d_bits)
+        # N > 1: pipelined steps — the exchange of step i (peer stores, flag wait, world merge) runs on a second stream
+        # under the scan of step i+1; drained inside the timed region
+        return sdb.scan_topk_device(d_q, TOPK, d_exclude_bits=d_bits, pipelined=pipelined)
 
     # ---- e2e leg: host buffers in, host results out, every step (exclude lists in the C ABI's CSR form)
     q_pinned = torch.from_numpy(q_host).pin_memory()
@@ -366,12 +374,14 @@ def main():
         out = sdb.scan_topk_device(dq, TOPK, d_exclude_bits=bits)
         return {k: v.cpu() for k, v in out.items() if k in ("dbidx", "score", "row", "count")}
 
-    def timed(fn, steps, profile=0, before=None, target=None):
+    def timed(fn, steps, profile=0, before=None, target=None, drain=None):
         target = target or db
         if before is not None:
             before()
         for _ in range(warmup):
             fn()
+        if drain is not None:
+            drain()
         barrier()
         if profile:
             target.profile(True, every=profile)
@@ -382,6 +392,8 @@ def main():
         ev0.record()
         for _ in range(steps):
             fn()
+        if drain is not None:
+            drain()                  # the last step's exchange completes inside the timed region
         ev1.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -401,7 +413,8 @@ def main():
     # production
     PROF_EVERY = 8 if args.steps >= 16 else 1
     dev_ms, wall_ms, launches, (kern_ms, kern_n) = timed(step_resident, args.steps, profile=PROF_EVERY,
-                                                        before=sampler.window_begin if rank == 0 else None)
+                                                        before=sampler.window_begin if rank == 0 else None,
+                                                        drain=sdb.drain if pipelined else None)
     e2e_steps = max(3, min(args.steps, 50))
     _, e2e_wall_ms, _, _ = timed(step_e2e, e2e_steps)
     if rank == 0:
@@ -409,6 +422,8 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     res = step_resident()
+    if pipelined:
+        sdb.drain()
     torch.cuda.synchronize()         # the two legs share the handle's workspace: one stream at a time
     res_e2e = step_e2e()
     torch.cuda.synchronize()

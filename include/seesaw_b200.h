@@ -144,6 +144,20 @@ int ssw_scan_topk_sharded_device(ssw_db* db, const float* d_queries, int nq, int
                                  int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row,
                                  int32_t* d_out_count, void* stream);
 
+/* Pipelined form of the same step for a stream of batches (a serving loop): the scan of this call runs on `stream`,
+ * its exchange + merge on an internal stream UNDER THE SCAN OF THE NEXT CALL (a slim exchange kernel that shares the
+ * SMs with the scan kernel; two sets of scan workspaces alternate).  The outputs of a call are complete on `stream`
+ * once the NEXT pipelined call on this handle has been enqueued, or after ssw_scan_pipeline_drain(db, stream) —
+ * pass distinct output buffers to consecutive calls.  Same arguments and collective contract as above; nq <= 64,
+ * k <= 64, fp16 storage without an exact copy (the batched kernel).  Throughput at 8 GPUs no longer pays the
+ * exchange latency and the skew between ranks per step. */
+int ssw_scan_topk_sharded_pipelined_device(ssw_db* db, const float* d_queries, int nq, int k,
+                                           const uint32_t* d_exclude_bits, void* const* peer_bufs, int world, int rank,
+                                           int nq_cap, int k_cap, uint32_t epoch, uint64_t* d_out_key,
+                                           int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row,
+                                           int32_t* d_out_count, void* stream);
+int ssw_scan_pipeline_drain(ssw_db* db, void* stream);
+
 /* Host-buffer form of the sharded step (arguments as ssw_scan_topk + the exchange arguments above):
  * one H2D of queries and id lists, bitmap build, scan, fused exchange + merge, one D2H of the results. */
 int ssw_scan_topk_sharded(ssw_db* db, const float* queries, int nq, int k, const int32_t* exclude_dbidx,

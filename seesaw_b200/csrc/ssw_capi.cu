@@ -113,6 +113,18 @@ static int ensure_lists(ssw_db* db, int nq, int lists, int k) {
   return SSW_OK;
 }
 
+// the pipelined sharded step alternates between two sets of scan workspaces: the exchange of step i still reads
+// one set while the scan of step i+1 fills the other
+static void swap_scan_ws(ssw_db* db) {
+  std::swap(db->d_list_keys, db->ws_alt.keys);
+  std::swap(db->d_list_dbidx, db->ws_alt.dbidx);
+  std::swap(db->d_gthr, db->ws_alt.gthr);
+  std::swap(db->d_pub1, db->ws_alt.pub1);
+  std::swap(db->d_cand_cnt, db->ws_alt.cand_cnt);
+  std::swap(db->list_capacity, db->ws_alt.list_capacity);
+  std::swap(db->gthr_capacity, db->ws_alt.gthr_capacity);
+}
+
 int ensure_stage(ssw_db* db, size_t dev_bytes, size_t host_bytes) {
   if (dev_bytes > db->d_stage_bytes) {
     if (db->d_stage) cudaFree(db->d_stage);
@@ -306,6 +318,15 @@ int ssw_db_destroy(ssw_db* db) {
   cudaFree(db->d_list_keys);
   cudaFree(db->d_list_dbidx);
   cudaFree(db->d_gthr);
+  cudaFree(db->ws_alt.keys);
+  cudaFree(db->ws_alt.dbidx);
+  cudaFree(db->ws_alt.gthr);
+  if (db->xstream) {
+    cudaStreamSynchronize(db->xstream);
+    cudaStreamDestroy(db->xstream);
+  }
+  if (db->ev_scan) cudaEventDestroy(db->ev_scan);
+  if (db->ev_xdone) cudaEventDestroy(db->ev_xdone);
   cudaFree(db->d_stage);
   if (db->h_stage) cudaFreeHost(db->h_stage);
   for (auto* v : {&db->prof_pending, &db->prof_free})
@@ -583,6 +604,60 @@ int ssw_scan_topk_sharded_device(ssw_db* db, const float* d_queries, int nq, int
   XchgCtx xc{peer_bufs, world, rank, nq_cap, k_cap, epoch};
   return scan_topk_impl(db, d_queries, nq, k, d_exclude_bits, d_out_key, d_out_dbidx, d_out_score, d_out_row,
                         d_out_count, (cudaStream_t)stream, &xc);
+}
+
+int ssw_scan_topk_sharded_pipelined_device(ssw_db* db, const float* d_queries, int nq, int k, const uint32_t* d_exclude_bits,
+                                           void* const* peer_bufs, int world, int rank, int nq_cap, int k_cap, uint32_t epoch,
+                                           uint64_t* d_out_key, int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row,
+                                           int32_t* d_out_count, void* stream) {
+  SSW_REQUIRE(db != nullptr && d_queries != nullptr && peer_bufs != nullptr, "null argument");
+  SSW_REQUIRE(world >= 1 && world <= SSW_MAX_WORLD && rank >= 0 && rank < world, "bad world/rank");
+  SSW_REQUIRE(nq >= 1 && nq <= nq_cap && nq <= SSW_MAX_BATCH, "pipelined step: 1 <= nq <= min(nq_cap, 64)");
+  SSW_REQUIRE(k > 0 && k <= k_cap && scan_tc_supported(db, k) && world * k <= 1024,
+              "pipelined step needs the batched kernel (fp16 storage, dim 256/512/768, k <= 64)");
+  SSW_REQUIRE(epoch != 0, "epoch must be non-zero and increase by one per call");
+  SSW_REQUIRE(db->d_exact == nullptr, "the pipelined step serves plain fp16 databases (exact mode certifies on the host path)");
+  for (int i = 0; i < world; ++i) SSW_REQUIRE(peer_bufs[i] != nullptr, "peer buffer is null");
+  SSW_CUDA(cudaSetDevice(db->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!db->xstream) {
+    SSW_CUDA(cudaStreamCreateWithFlags(&db->xstream, cudaStreamNonBlocking));
+    SSW_CUDA(cudaEventCreateWithFlags(&db->ev_scan, cudaEventDisableTiming));
+    SSW_CUDA(cudaEventCreateWithFlags(&db->ev_xdone, cudaEventDisableTiming));
+  }
+  if (!db->d_xchg_timed_out) {
+    SSW_CUDA(cudaHostAlloc((void**)&db->d_xchg_timed_out, 4, cudaHostAllocMapped));
+    *db->d_xchg_timed_out = 0;
+  }
+  swap_scan_ws(db);       // this set was last read by the exchange two steps back, which `stream` already waited for
+  const int lists = db->scan_grid, kl = k + kScanTcSlack;
+  int rc = ensure_lists(db, nq, lists, kl);
+  if (rc) return rc;
+  if (!db->d_tc_ws) SSW_CUDA(cudaMalloc(&db->d_tc_ws, scan_tc_workspace_bytes(db->dim, db->scan_grid)));
+  rc = launch_scan_tc(db, d_queries, nq, k, d_exclude_bits, db->d_list_keys, db->d_list_dbidx, db->d_cand_cnt, db->d_gthr,
+                      db->d_tc_ws, st);
+  if (rc) return rc;
+  // from here on `stream` holds the PREVIOUS call's results (and frees its workspace for the next call)
+  if (db->pipe_pending) SSW_CUDA(cudaStreamWaitEvent(st, db->ev_xdone, 0));
+  SSW_CUDA(cudaEventRecord(db->ev_scan, st));
+  SSW_CUDA(cudaStreamWaitEvent(db->xstream, db->ev_scan, 0));
+  rc = launch_exchange_slim(db->d_list_keys, db->d_list_dbidx, (int64_t)lists * kl, nq, k, db->d_cand_cnt, peer_bufs, world, rank,
+                            nq_cap, k_cap, epoch, db->d_xchg_timed_out, d_out_key, d_out_dbidx, d_out_score, d_out_row,
+                            d_out_count, db->xstream);
+  if (rc) return rc;
+  SSW_CUDA(cudaEventRecord(db->ev_xdone, db->xstream));
+  db->pipe_pending = true;
+  return SSW_OK;
+}
+
+int ssw_scan_pipeline_drain(ssw_db* db, void* stream) {
+  SSW_REQUIRE(db != nullptr, "db is null");
+  SSW_CUDA(cudaSetDevice(db->device));
+  if (db->pipe_pending) {
+    SSW_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, db->ev_xdone, 0));
+    db->pipe_pending = false;
+  }
+  return SSW_OK;
 }
 
 int ssw_xchg_create(int device, int world, int nq_cap, int k_cap, void** d_buf, void* ipc_handle_out, int64_t* bytes) {

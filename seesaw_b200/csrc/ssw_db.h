@@ -49,7 +49,20 @@ struct ssw_db {
   uint64_t* d_gthr = nullptr;      // [nq] shared lower bound on the k-th best key, followed by
   uint32_t* d_pub1 = nullptr;      // [nq][grid] best score per CTA of the streaming scan (same allocation)
   int32_t* d_cand_cnt = nullptr;   // [nq] compacted candidates per query of the batched scan (same allocation)
-  size_t list_capacity = 0;        // entries
+  size_t list_capacity = 0;        // entries (per pipeline parity: two such blocks are allocated)
+  // pipelined sharded step: the exchange of step i runs on `xstream` under the scan of step i+1
+  cudaStream_t xstream = nullptr;
+  cudaEvent_t ev_scan = nullptr, ev_xdone = nullptr;
+  bool pipe_pending = false;
+  struct ScanWs {                  // the second set of scan workspaces (swapped with the fields above per pipelined call)
+    uint64_t* keys = nullptr;
+    int32_t* dbidx = nullptr;
+    uint64_t* gthr = nullptr;
+    uint32_t* pub1 = nullptr;
+    int32_t* cand_cnt = nullptr;
+    size_t list_capacity = 0;
+    int gthr_capacity = 0;
+  } ws_alt;
   int gthr_capacity = 0;
   // staging for the host-pointer API
   void* d_stage = nullptr;
@@ -109,6 +122,11 @@ int launch_exchange_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_
                           int rank, int nq_cap, int k_cap, uint32_t epoch, int* d_timed_out, uint64_t* d_out_key,
                           int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row, int32_t* d_out_count,
                           cudaStream_t st, bool pdl = false, const int32_t* d_counts = nullptr);
+// slim exchange for the pipelined sharded step (co-resides with the next step's scan kernel)
+int launch_exchange_slim(const uint64_t* d_keys, const int32_t* d_dbidx, int64_t query_stride, int nq, int k,
+                         const int32_t* d_counts, void* const* peers, int world, int rank, int nq_cap, int k_cap, uint32_t epoch,
+                         int* d_timed_out, uint64_t* d_out_key, int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row,
+                         int32_t* d_out_count, cudaStream_t st);
 int launch_image_max(ssw_db* db, const float* d_scores, const uint8_t* d_row_mask, const uint32_t* d_excl,
                      int64_t n_padded, uint64_t* d_keys, int32_t* d_dbidx, cudaStream_t st, const uint32_t* d_pos = nullptr);
 int launch_order_to_pos(const int64_t* d_order, int64_t n_order, int64_t n_rows, uint32_t* d_pos, cudaStream_t st);

@@ -935,6 +935,186 @@ int launch_exchange_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_
 }
 
 // ------------------------------------------------------------------------------------------
+// K4x, slim form for the PIPELINED sharded step: the same shard merge + peer exchange + world merge, written to
+// co-reside with the next step's scan kernel on the same SMs (128 threads, <= 48 registers, 14 KB of static shared
+// memory: the scan CTA leaves 6.4k registers and ~20 KB per SM free), so that the exchange of step i — including the
+// wait for the slowest peer — runs UNDER the scan of step i+1 instead of after its own.  Input is the batched scan's
+// compacted candidate array; k <= 64, world * k <= 1024.
+// ------------------------------------------------------------------------------------------
+constexpr int kSlimThreads = 128;
+constexpr int kSlimCap = 1024;
+
+// rank the n <= kSlimCap keys in s_k by counting (keys unique; 0 = empty) and write the best k, sorted, to ok / od
+// (slots past the number of valid keys stay 0 / -1).  Ends with a barrier.
+__device__ __forceinline__ void slim_rank(const uint64_t* s_k, const int32_t* s_d, int n, int k, uint64_t* ok, int32_t* od) {
+  for (int i = threadIdx.x; i < k; i += kSlimThreads) {
+    ok[i] = 0ull;
+    od[i] = -1;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += kSlimThreads) {
+    const uint64_t mine = s_k[i];
+    if (mine == 0ull) continue;
+    int rank = 0;
+#pragma unroll 4
+    for (int j = 0; j < n; ++j) rank += s_k[j] > mine;
+    if (rank < k) {
+      ok[rank] = mine;
+      od[rank] = s_d[i];
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSlimThreads, 10) exchange_slim_kernel(const XchgArgs x) {
+  __shared__ uint64_t s_k[kSlimCap];
+  __shared__ int32_t s_d[kSlimCap];
+  __shared__ uint64_t s_ok[64];
+  __shared__ int32_t s_od[64];
+  __shared__ int s_hist[256], s_cnt, s_remaining;
+  __shared__ uint64_t s_prefix;
+  const MergeArgs& a = x.m;
+  const int q = blockIdx.x, tid = threadIdx.x, k = a.k;
+  const int par = (int)(x.epoch & 1u);
+  // ---- 1. this shard's top-k from its compacted candidates
+  const uint64_t* kq = a.keys + (int64_t)q * a.query_stride;
+  const int32_t* dq = a.dbidx + (int64_t)q * a.query_stride;
+  int n = a.counts[q];
+  if (n > kSlimCap) {
+    // rare (thresholds could not prune, e.g. all scores equal): find the k-th largest key by an 8-pass radix select
+    // over the candidates in global memory, then keep exactly the keys >= it (keys are unique)
+    if (tid == 0) {
+      s_prefix = 0;
+      s_remaining = k;
+    }
+    for (int d = 7; d >= 0; --d) {
+      for (int i = tid; i < 256; i += kSlimThreads) s_hist[i] = 0;
+      __syncthreads();
+      const uint64_t prefix = s_prefix;
+      for (int e = tid; e < n; e += kSlimThreads) {
+        const uint64_t key = kq[e];
+        const bool match = (d == 7) || ((key >> (8 * (d + 1))) == (prefix >> (8 * (d + 1))));
+        if (match && key != 0ull) atomicAdd(&s_hist[(int)((key >> (8 * d)) & 255)], 1);
+      }
+      __syncthreads();
+      merge_pick_bin(s_hist, d, &s_prefix, &s_remaining);
+      __syncthreads();
+    }
+    const uint64_t T = s_prefix;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    for (int e = tid; e < n; e += kSlimThreads) {
+      const uint64_t key = kq[e];
+      if (key != 0ull && key >= T) {
+        const int p = atomicAdd(&s_cnt, 1);
+        if (p < kSlimCap) {
+          s_k[p] = key;
+          s_d[p] = dq[e];
+        }
+      }
+    }
+    __syncthreads();
+    n = min(s_cnt, kSlimCap);
+  } else {
+    for (int e = tid; e < n; e += kSlimThreads) {
+      s_k[e] = kq[e];
+      s_d[e] = dq[e];
+    }
+  }
+  __syncthreads();
+  slim_rank(s_k, s_d, n, k, s_ok, s_od);
+  // ---- 2. store it into slot `rank` of every rank's buffer (own included), then raise the flags
+  const size_t slot = (((size_t)par * x.world + x.rank) * x.nq_cap + q);
+  for (int p = 0; p < x.world; ++p) {
+    uint8_t* base = static_cast<uint8_t*>(x.peers[p]);
+    uint64_t* pk = reinterpret_cast<uint64_t*>(base) + slot * x.k_cap;
+    int32_t* pd = reinterpret_cast<int32_t*>(base + xchg_keys_bytes(x.world, x.nq_cap, x.k_cap)) + slot * x.k_cap;
+    for (int i = tid; i < k; i += kSlimThreads) {
+      pk[i] = s_ok[i];
+      pd[i] = s_od[i];
+    }
+  }
+  __syncthreads();
+  if (tid < x.world) {
+    uint8_t* base = static_cast<uint8_t*>(x.peers[tid]);
+    uint32_t* flag = reinterpret_cast<uint32_t*>(base + xchg_keys_bytes(x.world, x.nq_cap, x.k_cap) +
+                                                 xchg_dbidx_bytes(x.world, x.nq_cap, x.k_cap)) + slot;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(x.epoch) : "memory");
+  }
+  // ---- 3. wait until every rank's slot of THIS rank's buffer carries this epoch
+  uint8_t* mine = static_cast<uint8_t*>(x.peers[x.rank]);
+  if (tid < x.world) {
+    const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine + xchg_keys_bytes(x.world, x.nq_cap, x.k_cap) +
+                                                             xchg_dbidx_bytes(x.world, x.nq_cap, x.k_cap)) +
+                           (((size_t)par * x.world + tid) * x.nq_cap + q);
+    uint32_t v;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+      if (v != x.epoch) {
+        __nanosleep(200);       // the next step's scan shares this SM: do not burn its issue slots
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > kXchgTimeoutNs) {
+          if (x.timed_out) *x.timed_out = 1;
+          break;
+        }
+      }
+    } while (v != x.epoch);
+  }
+  __syncthreads();
+  // ---- 4. merge the world's lists (read through L2: they were written by other GPUs)
+  const size_t q0 = ((size_t)par * x.world) * x.nq_cap + q;
+  const uint64_t* wk = reinterpret_cast<const uint64_t*>(mine) + q0 * x.k_cap;
+  const int32_t* wd = reinterpret_cast<const int32_t*>(mine + xchg_keys_bytes(x.world, x.nq_cap, x.k_cap)) + q0 * x.k_cap;
+  const int total = x.world * k;
+  for (int e = tid; e < total; e += kSlimThreads) {
+    const int64_t off = (int64_t)(e / k) * ((int64_t)x.nq_cap * x.k_cap) + (e % k);
+    s_k[e] = __ldcg(wk + off);
+    s_d[e] = __ldcg(wd + off);
+  }
+  __syncthreads();
+  slim_rank(s_k, s_d, total, k, s_ok, s_od);
+  int cnt = 0;
+  for (int i = tid; i < k; i += kSlimThreads) {
+    const uint64_t key = s_ok[i];
+    const bool valid = key != 0ull;
+    cnt += valid;
+    const int64_t o = (int64_t)q * k + i;
+    if (a.out_key) a.out_key[o] = key;
+    if (a.out_dbidx) a.out_dbidx[o] = valid ? s_od[i] : -1;
+    if (a.out_score) a.out_score[o] = valid ? key_score(key) : -INFINITY;
+    if (a.out_row) a.out_row[o] = valid ? (int64_t)key_row(key) : -1;
+  }
+  // count of valid slots: block-wide sum of the per-thread partials
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  if (cnt) atomicAdd(&s_cnt, cnt);
+  __syncthreads();
+  if (tid == 0 && a.out_count) a.out_count[q] = s_cnt;
+}
+
+int launch_exchange_slim(const uint64_t* d_keys, const int32_t* d_dbidx, int64_t query_stride, int nq, int k,
+                         const int32_t* d_counts, void* const* peers, int world, int rank, int nq_cap, int k_cap, uint32_t epoch,
+                         int* d_timed_out, uint64_t* d_out_key, int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row,
+                         int32_t* d_out_count, cudaStream_t st) {
+  XchgArgs x{};
+  x.timed_out = d_timed_out;
+  x.m = MergeArgs{d_keys, d_dbidx, 1, query_stride, query_stride, k, d_counts, nullptr,
+                  d_out_key, d_out_dbidx, d_out_score, d_out_row, d_out_count};
+  for (int i = 0; i < world; ++i) x.peers[i] = peers[i];
+  x.world = world;
+  x.rank = rank;
+  x.nq_cap = nq_cap;
+  x.k_cap = k_cap;
+  x.epoch = epoch;
+  exchange_slim_kernel<<<nq, kSlimThreads, 0, st>>>(x);
+  SSW_LAUNCHED();
+  return SSW_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // exclusion bitmaps: per query, bit i set <=> local image i is excluded
 // (replaces pr.BitMap difference / DataFrame.isin, multiscale_index.py:192-193, 295)
 // ------------------------------------------------------------------------------------------

@@ -134,7 +134,17 @@ class ShardedPatchDatabase:
                                         ptr(out["dbidx"]), ptr(out["score"]), ptr(out["row"]), ptr(out["count"])))
         return out
 
-    def _scan_fused(self, d_queries, k, d_exclude_bits, stream=None):
+    def drain(self, stream=None):
+        """After pipelined steps: make ``stream`` wait for the last exchange (its outputs are complete from there)."""
+        import ctypes as C
+
+        import torch
+
+        from ._lib import check, lib
+        s = torch.cuda.current_stream(self.local.device) if stream is None else stream
+        check(lib.ssw_scan_pipeline_drain(self.local._h, C.c_void_p(s.cuda_stream)))
+
+    def _scan_fused(self, d_queries, k, d_exclude_bits, stream=None, pipelined=False):
         import ctypes as C
 
         import torch
@@ -151,7 +161,8 @@ class ShardedPatchDatabase:
         x["epoch"] += 1
         s = torch.cuda.current_stream(dev) if stream is None else stream
         bits = None if d_exclude_bits is None else C.c_void_p(d_exclude_bits.data_ptr())
-        check(lib.ssw_scan_topk_sharded_device(
+        fn = lib.ssw_scan_topk_sharded_pipelined_device if pipelined else lib.ssw_scan_topk_sharded_device
+        check(fn(
             self.local._h, C.c_void_p(d_queries.data_ptr()), nq, int(k), bits, x["peers"], self.world_size, self.rank,
             x["nq_cap"], x["k_cap"], x["epoch"], C.c_void_p(out["key"].data_ptr()), C.c_void_p(out["dbidx"].data_ptr()),
             C.c_void_p(out["score"].data_ptr()), C.c_void_p(out["row"].data_ptr()), C.c_void_p(out["count"].data_ptr()),
@@ -172,15 +183,17 @@ class ShardedPatchDatabase:
                                         global_row_base=row_base)
         return cls(local, rank=rank, world_size=world_size, group=group)
 
-    def scan_topk_device(self, d_queries, k, exclude=None, d_exclude_bits=None):
-        """Same result on every rank: dict(key, dbidx [nq,k], and on GPUs score/row/count)."""
+    def scan_topk_device(self, d_queries, k, exclude=None, d_exclude_bits=None, pipelined=False):
+        """Same result on every rank: dict(key, dbidx [nq,k], and on GPUs score/row/count).  ``pipelined=True`` (fused
+        exchange only): this step's exchange runs under the NEXT step's scan; its outputs are complete on the current
+        stream once the next pipelined step has been enqueued or after :meth:`drain`."""
         import torch
         import torch.distributed as dist
         nq = d_queries.shape[0]
         if d_exclude_bits is None and exclude is not None:
             d_exclude_bits = self.local.build_exclude_bits(exclude, nq)
         if self._xchg is not None and nq <= self._xchg["nq_cap"] and k <= self._xchg["k_cap"]:
-            return self._scan_fused(d_queries, k, d_exclude_bits)
+            return self._scan_fused(d_queries, k, d_exclude_bits, pipelined=pipelined)
         if self.world_size == 1 and self._merge is None:
             return self.local.scan_topk_device(d_queries, k, d_exclude_bits, decoded=True)
         keys, dbidx = self.local.scan_topk_device(d_queries, k, d_exclude_bits)

@@ -69,6 +69,23 @@ def _exact_sharded_check(rank, world):
     sdb.close()
 
 
+def _pipelined_check(sdb, counts, dbidx, n, qs, excl):
+    """Pipelined steps: the exchange of step i runs under the scan of step i+1 on alternating workspaces.  Different
+    queries / k every step; every step's outputs must equal the oracle once the pipeline is drained."""
+    import torch
+    outs = []
+    for step in range(7):
+        sel = np.roll(np.arange(len(qs)), step)[: 3 + 2 * step]
+        k = (50, 3, 17)[step % 3]
+        bits = sdb.local.build_exclude_bits([excl[i] for i in sel], len(sel))
+        res = sdb.scan_topk_device(torch.from_numpy(qs[sel]).cuda(), k, d_exclude_bits=bits, pipelined=True)
+        outs.append((sel, k, res, bits))
+    sdb.drain()
+    torch.cuda.synchronize()
+    for sel, k, res, _ in outs:
+        _check(res, counts, dbidx, n, qs[sel], [excl[i] for i in sel], k)
+
+
 def test_sharded_world1():
     import torch
     from seesaw_b200.sharded import ShardedPatchDatabase
@@ -81,6 +98,7 @@ def test_sharded_world1():
             res = sdb.scan_topk_device(torch.from_numpy(qs).cuda(), k, exclude=excl)
             torch.cuda.synchronize()
             _check(res, counts, dbidx, n, qs, excl, k)
+    _pipelined_check(sdb, counts, dbidx, n, qs, excl)
     sdb.close()
     _exact_sharded_check(0, 1)
 
@@ -106,6 +124,7 @@ def _worker(rank, world, port, out_dir):
     for k in (50, 3):
         res = sdb.scan_topk(qs, k, exclude=excl)
         _check({n: torch.from_numpy(v) for n, v in res.items()}, counts, dbidx, n, qs, excl, k)
+    _pipelined_check(sdb, counts, dbidx, n, qs, excl)
     dist.barrier()
     sdb.close()
     _exact_sharded_check(rank, world)
