@@ -542,6 +542,10 @@ struct XchgCtx {
 static int scan_topk_impl(ssw_db* db, const float* d_queries, int nq, int k, const uint32_t* d_exclude_bits,
                           uint64_t* d_out_key, int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row,
                           int32_t* d_out_count, cudaStream_t st, const XchgCtx* xc = nullptr, bool exact_rows = false) {
+  if (db->pipe_pending) {      // a pipelined step's exchange may still read the scan workspace: order this call behind it
+    SSW_CUDA(cudaStreamWaitEvent(st, db->ev_xdone, 0));
+    db->pipe_pending = false;
+  }
   const int lists = db->scan_grid;
   const int kl = k + kScanTcSlack;           // slots per (query, CTA): the batched scan publishes up to k + slack entries
   int rc = ensure_lists(db, nq, lists, kl);

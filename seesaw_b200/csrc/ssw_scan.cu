@@ -936,28 +936,75 @@ int launch_exchange_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_
 
 // ------------------------------------------------------------------------------------------
 // K4x, slim form for the PIPELINED sharded step: the same shard merge + peer exchange + world merge, written to
-// co-reside with the next step's scan kernel on the same SMs (128 threads, <= 48 registers, 14 KB of static shared
+// co-reside with the next step's scan kernel on the same SMs (128 threads, <= 48 registers, 3 KB of static shared
 // memory: the scan CTA leaves 6.4k registers and ~20 KB per SM free), so that the exchange of step i — including the
 // wait for the slowest peer — runs UNDER the scan of step i+1 instead of after its own.  Input is the batched scan's
 // compacted candidate array; k <= 64, world * k <= 1024.
 // ------------------------------------------------------------------------------------------
 constexpr int kSlimThreads = 128;
-constexpr int kSlimCap = 1024;
 
-// rank the n <= kSlimCap keys in s_k by counting (keys unique; 0 = empty) and write the best k, sorted, to ok / od
-// (slots past the number of valid keys stay 0 / -1).  Ends with a barrier.
-__device__ __forceinline__ void slim_rank(const uint64_t* s_k, const int32_t* s_d, int n, int k, uint64_t* ok, int32_t* od) {
-  for (int i = threadIdx.x; i < k; i += kSlimThreads) {
+// The slim kernel shares its SMs with a running scan CTA whose epilogue is issue-latency bound, so it must execute
+// few instructions: the k best of n keys are found by an 8-pass MSB radix select (n / 128 keys per thread and pass)
+// and only those <= k survivors are ranked by counting (k^2 compares), instead of ranking all n (n^2).
+// `at(e)` maps entry e to its offset in keys / dbs.  Leaves the best min(n_valid, k) entries, sorted best first, in
+// ok / od (other slots 0 / -1).  Ends with a barrier.
+template <bool CG, typename At>
+__device__ __forceinline__ void slim_topk(const uint64_t* keys, const int32_t* dbs, int n, At at, int k, uint64_t* s_k,
+                                          int32_t* s_d, int* s_hist, uint64_t* s_prefix, int* s_remaining, int* s_cnt,
+                                          uint64_t* ok, int32_t* od) {
+  const int tid = threadIdx.x;
+  auto ldk = [&](int e) { return CG ? __ldcg(keys + at(e)) : keys[at(e)]; };
+  if (tid == 0) {
+    *s_prefix = 0;
+    *s_remaining = k;
+    *s_cnt = 0;
+  }
+  for (int i = tid; i < k; i += kSlimThreads) {
     ok[i] = 0ull;
     od[i] = -1;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += kSlimThreads) {
+  uint64_t T = 1;                        // fewer than k valid keys: keep them all
+  int valid = 0;
+  for (int e = tid; e < n; e += kSlimThreads) valid += ldk(e) != 0ull;
+  if (valid) atomicAdd(s_cnt, valid);
+  __syncthreads();
+  const int n_valid = *s_cnt;
+  __syncthreads();
+  if (tid == 0) *s_cnt = 0;
+  if (n_valid > k) {
+    for (int d = 7; d >= 0; --d) {
+      for (int i = tid; i < 256; i += kSlimThreads) s_hist[i] = 0;
+      __syncthreads();
+      const uint64_t prefix = *s_prefix;
+      for (int e = tid; e < n; e += kSlimThreads) {
+        const uint64_t key = ldk(e);
+        const bool match = (d == 7) || ((key >> (8 * (d + 1))) == (prefix >> (8 * (d + 1))));
+        if (match && key != 0ull) atomicAdd(&s_hist[(int)((key >> (8 * d)) & 255)], 1);
+      }
+      __syncthreads();
+      merge_pick_bin(s_hist, d, s_prefix, s_remaining);
+      __syncthreads();
+    }
+    T = *s_prefix;                       // the k-th largest key (keys are unique)
+  }
+  __syncthreads();
+  for (int e = tid; e < n; e += kSlimThreads) {
+    const uint64_t key = ldk(e);
+    if (key != 0ull && key >= T) {
+      const int p = atomicAdd(s_cnt, 1);
+      if (p < 64) {
+        s_k[p] = key;
+        s_d[p] = CG ? __ldcg(dbs + at(e)) : dbs[at(e)];
+      }
+    }
+  }
+  __syncthreads();
+  const int m = min(*s_cnt, 64);
+  for (int i = tid; i < m; i += kSlimThreads) {
     const uint64_t mine = s_k[i];
-    if (mine == 0ull) continue;
     int rank = 0;
-#pragma unroll 4
-    for (int j = 0; j < n; ++j) rank += s_k[j] > mine;
+    for (int j = 0; j < m; ++j) rank += s_k[j] > mine;
     if (rank < k) {
       ok[rank] = mine;
       od[rank] = s_d[i];
@@ -967,8 +1014,8 @@ __device__ __forceinline__ void slim_rank(const uint64_t* s_k, const int32_t* s_
 }
 
 __global__ void __launch_bounds__(kSlimThreads, 10) exchange_slim_kernel(const XchgArgs x) {
-  __shared__ uint64_t s_k[kSlimCap];
-  __shared__ int32_t s_d[kSlimCap];
+  __shared__ uint64_t s_k[64];
+  __shared__ int32_t s_d[64];
   __shared__ uint64_t s_ok[64];
   __shared__ int32_t s_od[64];
   __shared__ int s_hist[256], s_cnt, s_remaining;
@@ -979,50 +1026,8 @@ __global__ void __launch_bounds__(kSlimThreads, 10) exchange_slim_kernel(const X
   // ---- 1. this shard's top-k from its compacted candidates
   const uint64_t* kq = a.keys + (int64_t)q * a.query_stride;
   const int32_t* dq = a.dbidx + (int64_t)q * a.query_stride;
-  int n = a.counts[q];
-  if (n > kSlimCap) {
-    // rare (thresholds could not prune, e.g. all scores equal): find the k-th largest key by an 8-pass radix select
-    // over the candidates in global memory, then keep exactly the keys >= it (keys are unique)
-    if (tid == 0) {
-      s_prefix = 0;
-      s_remaining = k;
-    }
-    for (int d = 7; d >= 0; --d) {
-      for (int i = tid; i < 256; i += kSlimThreads) s_hist[i] = 0;
-      __syncthreads();
-      const uint64_t prefix = s_prefix;
-      for (int e = tid; e < n; e += kSlimThreads) {
-        const uint64_t key = kq[e];
-        const bool match = (d == 7) || ((key >> (8 * (d + 1))) == (prefix >> (8 * (d + 1))));
-        if (match && key != 0ull) atomicAdd(&s_hist[(int)((key >> (8 * d)) & 255)], 1);
-      }
-      __syncthreads();
-      merge_pick_bin(s_hist, d, &s_prefix, &s_remaining);
-      __syncthreads();
-    }
-    const uint64_t T = s_prefix;
-    if (tid == 0) s_cnt = 0;
-    __syncthreads();
-    for (int e = tid; e < n; e += kSlimThreads) {
-      const uint64_t key = kq[e];
-      if (key != 0ull && key >= T) {
-        const int p = atomicAdd(&s_cnt, 1);
-        if (p < kSlimCap) {
-          s_k[p] = key;
-          s_d[p] = dq[e];
-        }
-      }
-    }
-    __syncthreads();
-    n = min(s_cnt, kSlimCap);
-  } else {
-    for (int e = tid; e < n; e += kSlimThreads) {
-      s_k[e] = kq[e];
-      s_d[e] = dq[e];
-    }
-  }
-  __syncthreads();
-  slim_rank(s_k, s_d, n, k, s_ok, s_od);
+  slim_topk<false>(kq, dq, a.counts[q], [](int e) { return (int64_t)e; }, k, s_k, s_d, s_hist, &s_prefix, &s_remaining, &s_cnt,
+                   s_ok, s_od);
   // ---- 2. store it into slot `rank` of every rank's buffer (own included), then raise the flags
   const size_t slot = (((size_t)par * x.world + x.rank) * x.nq_cap + q);
   for (int p = 0; p < x.world; ++p) {
@@ -1054,7 +1059,7 @@ __global__ void __launch_bounds__(kSlimThreads, 10) exchange_slim_kernel(const X
     do {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
       if (v != x.epoch) {
-        __nanosleep(200);       // the next step's scan shares this SM: do not burn its issue slots
+        __nanosleep(500);       // the next step's scan shares this SM: do not burn its issue slots
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         if (t1 - t0 > kXchgTimeoutNs) {
           if (x.timed_out) *x.timed_out = 1;
@@ -1068,14 +1073,9 @@ __global__ void __launch_bounds__(kSlimThreads, 10) exchange_slim_kernel(const X
   const size_t q0 = ((size_t)par * x.world) * x.nq_cap + q;
   const uint64_t* wk = reinterpret_cast<const uint64_t*>(mine) + q0 * x.k_cap;
   const int32_t* wd = reinterpret_cast<const int32_t*>(mine + xchg_keys_bytes(x.world, x.nq_cap, x.k_cap)) + q0 * x.k_cap;
-  const int total = x.world * k;
-  for (int e = tid; e < total; e += kSlimThreads) {
-    const int64_t off = (int64_t)(e / k) * ((int64_t)x.nq_cap * x.k_cap) + (e % k);
-    s_k[e] = __ldcg(wk + off);
-    s_d[e] = __ldcg(wd + off);
-  }
-  __syncthreads();
-  slim_rank(s_k, s_d, total, k, s_ok, s_od);
+  const int64_t lstride = (int64_t)x.nq_cap * x.k_cap;
+  slim_topk<true>(wk, wd, x.world * k, [=](int e) { return (int64_t)(e / k) * lstride + (e % k); }, k, s_k, s_d, s_hist,
+                  &s_prefix, &s_remaining, &s_cnt, s_ok, s_od);
   int cnt = 0;
   for (int i = tid; i < k; i += kSlimThreads) {
     const uint64_t key = s_ok[i];
