@@ -83,14 +83,18 @@ def _stub_database():
 def _server_process(address):
     from seesaw_b200.service import ScanServer
     db, _, _ = _stub_database()
-    ScanServer(db, address, max_batch=16, max_wait_s=0.1).serve_forever()
+    ScanServer(db, address, max_batch=16, max_wait_s=0.5).serve_forever()
 
 
-def _session_process(address, i, out):
+def _session_process(address, i, out, gate):
     from seesaw_b200.service import ScanClient
     c = ScanClient(address)
     qs = synth.lattice_queries(24, 256, 6)
     ex = None if i % 3 else [np.arange(i, 300, 7)]
+    try:
+        gate.wait(90)        # all sessions connected: their requests now meet inside the server's waiting window
+    except Exception:        # a broken barrier only costs the batching assertion, never a hang
+        pass
     r = c.scan_topk(qs[i:i + 1], 3 + i % 5, exclude=ex)
     s = c.score_all(qs[i])
     out.put((i, r["dbidx"][0], r["row"][0], int(r["count"][0]), float(s.sum()), c.n_rows))
@@ -107,7 +111,8 @@ def test_session_processes_share_one_server_process(tmp_path):
     server = ctx.Process(target=_server_process, args=(address,), daemon=True)
     server.start()
     out = ctx.Queue()
-    sessions = [ctx.Process(target=_session_process, args=(address, i, out)) for i in range(12)]
+    gate = ctx.Barrier(12)
+    sessions = [ctx.Process(target=_session_process, args=(address, i, out, gate)) for i in range(12)]
     [p.start() for p in sessions]
     got = {}
     for _ in sessions:

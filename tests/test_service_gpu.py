@@ -45,7 +45,7 @@ def _server(address, ready):
     db.close()
 
 
-def _session(address, i, out):
+def _session(address, i, out, gate):
     _paths()
     from seesaw_b200.indices import B200MultiscaleIndex, BitMap
     from seesaw_b200.service import ScanClient
@@ -54,6 +54,10 @@ def _session(address, i, out):
     idx = B200MultiscaleIndex.from_database(client, meta)        # no CUDA in this process: every call crosses the socket
     seen = BitMap(np.unique(meta.dbidx.values)[i::17])
     agg = "avg_score" if i % 2 else "plain_score"
+    try:
+        gate.wait(240)       # sessions start together, so their stage-1 scans meet in the server's waiting window
+    except Exception:        # a broken barrier only costs the batching assertion, never a hang
+        pass
     r = idx.query(vector=qs[i], topk=3, shortlist_size=20, exclude=seen, agg_method=agg)
     out.put((i, np.asarray(r["dbidxs"]), [float(a.score.values[0]) for a in r["activations"]]))
     client.close()
@@ -70,7 +74,8 @@ def test_64_session_processes_one_gpu_process(tmp_path):
     server.start()
     assert ready.wait(300), "the GPU-owning process did not come up"
     out = ctx.Queue()
-    sessions = [ctx.Process(target=_session, args=(address, i, out)) for i in range(N_SESSIONS)]
+    gate = ctx.Barrier(N_SESSIONS)
+    sessions = [ctx.Process(target=_session, args=(address, i, out, gate)) for i in range(N_SESSIONS)]
     [p.start() for p in sessions]
     got = {}
     for _ in sessions:
