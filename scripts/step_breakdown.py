@@ -17,6 +17,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--images", type=int, nargs="+", default=[31250, 62500, 250000])
 ap.add_argument("--dim", type=int, default=512)
 ap.add_argument("--iters", type=int, default=200)
+ap.add_argument("--pipeline", type=int, nargs="*", default=None,
+                help="only the device API and the PIPELINED sharded step (world = 1) with these numbers of side SMs")
 args = ap.parse_args()
 NQ, K, PATCHES = 64, 50, 40
 peak = 6516.7
@@ -69,6 +71,15 @@ for n_img in args.images:
     print(f"rows={db.n_rows:>9} per query and CTA and launch: {upd / 10 / NQ / 148:.1f} list updates, {off / 10 / NQ / 148:.1f} images offered", flush=True)
     sdb.enable_fused_exchange(nq_cap=NQ, k_cap=64)
     run(lambda: sdb.scan_topk_device(d_q, K, d_exclude_bits=bits), "fused exchange, world=1")
+    if args.pipeline is not None:
+        for side in args.pipeline:
+            sdb.set_side_sms(side)
+            run(lambda: sdb.scan_topk_device(d_q, K, d_exclude_bits=bits, pipelined=True), f"pipelined, side SMs = {side}")
+            sdb.drain()
+            torch.cuda.synchronize()
+        sdb.close()
+        torch.cuda.empty_cache()
+        continue
     run(lambda: sdb.scan_topk(q_host, K, exclude=ex), "host API (sharded, world=1)")
     run(lambda: db.scan_topk(q_host, K, exclude=ex), "host API ssw_scan_topk")
     from seesaw_b200.engine import exclude_lists_to_csr

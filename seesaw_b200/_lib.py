@@ -62,6 +62,7 @@ SIGNATURES = {
     "ssw_scan_topk_sharded_pipelined_device": (C.c_int, [_p, _p, C.c_int, C.c_int, _p, C.POINTER(_p), C.c_int, C.c_int, C.c_int,
                                                          C.c_int, C.c_uint32, _p, _p, _p, _p, _p, _p]),
     "ssw_scan_pipeline_drain": (C.c_int, [_p, _p]),
+    "ssw_scan_pipeline_side_sms": (C.c_int, [_p, C.c_int]),
     "ssw_scan_topk_sharded": (C.c_int, [_p, _p, C.c_int, C.c_int, _p, _p, C.POINTER(_p), C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_uint32, _p, _p, _p, _p]),
     "ssw_set_scan_mode": (C.c_int, [_p, C.c_int]),

@@ -308,6 +308,7 @@ int ssw_db_destroy(ssw_db* db) {
   cudaFree(db->d_img_dbidx);
   cudaFree(db->d_orig_row);
   cudaFree(db->d_part);
+  cudaFree(db->d_part_side);
   cudaFree(db->d_last_bits);
   cudaFree(db->d_boxes);
   cudaFree(db->d_zoom);
@@ -492,9 +493,15 @@ int ssw_scan_stats(ssw_db* db, int enable, int64_t* list_updates, int64_t* image
 #endif
     SSW_CUDA(cudaMalloc((void**)&db->d_scan_stats, stats_bytes));
     SSW_CUDA(cudaMemset(db->d_scan_stats, 0, stats_bytes));
+#ifdef SSW_TRACE
+    g_trace_block = db->d_scan_stats;
+#endif
   } else if (!enable && db->d_scan_stats) {
     cudaFree(db->d_scan_stats);
     db->d_scan_stats = nullptr;
+#ifdef SSW_TRACE
+    g_trace_block = nullptr;
+#endif
   }
   if (list_updates) *list_updates = (int64_t)v[0];
   if (images_offered) *images_offered = (int64_t)v[1];
@@ -633,13 +640,40 @@ int ssw_scan_topk_sharded_pipelined_device(ssw_db* db, const float* d_queries, i
     SSW_CUDA(cudaHostAlloc((void**)&db->d_xchg_timed_out, 4, cudaHostAllocMapped));
     *db->d_xchg_timed_out = 0;
   }
+  // the scan of a pipelined step leaves `side_sms` SMs to the exchange blocks: its own grid and image partition
+  const int side = (db->side_sms > 0 && db->sm_count - db->side_sms >= 64) ? db->side_sms : 0;
+  const int grid = db->sm_count - side;
+  ScanTcGrid sg{grid, db->d_part, db->max_cta_images};
+  if (side > 0) {
+    if (db->side_grid != grid) {
+      int32_t* part = nullptr;
+      SSW_CUDA(cudaMalloc((void**)&part, ((size_t)grid * kScanWarps + 1) * 4 + 4));
+      int* d_max = reinterpret_cast<int*>(part + (size_t)grid * kScanWarps + 1);
+      int rc0 = launch_part_build(db, grid, part, d_max, st);
+      int h_max = 0;
+      cudaError_t e = rc0 ? cudaSuccess : cudaMemcpyAsync(&h_max, d_max, 4, cudaMemcpyDeviceToHost, st);
+      if (!rc0 && e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (rc0 || e != cudaSuccess) {
+        cudaFree(part);
+        if (rc0) return rc0;
+        set_error(std::string("side partition: ") + cudaGetErrorString(e));
+        return SSW_ERR_CUDA;
+      }
+      if (db->d_part_side) cudaFree(db->d_part_side);
+      db->d_part_side = part;
+      db->side_grid = grid;
+      db->side_max_cta_images = h_max;
+    }
+    sg.part = db->d_part_side;
+    sg.max_cta_images = db->side_max_cta_images;
+  }
   swap_scan_ws(db);       // this set was last read by the exchange two steps back, which `stream` already waited for
-  const int lists = db->scan_grid, kl = k + kScanTcSlack;
-  int rc = ensure_lists(db, nq, lists, kl);
+  const int lists = grid, kl = k + kScanTcSlack;
+  int rc = ensure_lists(db, nq, db->scan_grid, kl);
   if (rc) return rc;
   if (!db->d_tc_ws) SSW_CUDA(cudaMalloc(&db->d_tc_ws, scan_tc_workspace_bytes(db->dim, db->scan_grid)));
   rc = launch_scan_tc(db, d_queries, nq, k, d_exclude_bits, db->d_list_keys, db->d_list_dbidx, db->d_cand_cnt, db->d_gthr,
-                      db->d_tc_ws, st);
+                      db->d_tc_ws, st, &sg);
   if (rc) return rc;
   // from here on `stream` holds the PREVIOUS call's results (and frees its workspace for the next call)
   if (db->pipe_pending) SSW_CUDA(cudaStreamWaitEvent(st, db->ev_xdone, 0));
@@ -647,10 +681,17 @@ int ssw_scan_topk_sharded_pipelined_device(ssw_db* db, const float* d_queries, i
   SSW_CUDA(cudaStreamWaitEvent(db->xstream, db->ev_scan, 0));
   rc = launch_exchange_slim(db->d_list_keys, db->d_list_dbidx, (int64_t)lists * kl, nq, k, db->d_cand_cnt, peer_bufs, world, rank,
                             nq_cap, k_cap, epoch, db->d_xchg_timed_out, d_out_key, d_out_dbidx, d_out_score, d_out_row,
-                            d_out_count, db->xstream);
+                            d_out_count, db->xstream, side);
   if (rc) return rc;
   SSW_CUDA(cudaEventRecord(db->ev_xdone, db->xstream));
   db->pipe_pending = true;
+  return SSW_OK;
+}
+
+int ssw_scan_pipeline_side_sms(ssw_db* db, int side_sms) {
+  SSW_REQUIRE(db != nullptr, "db is null");
+  SSW_REQUIRE(side_sms >= 0 && side_sms <= 16, "side_sms must be in [0, 16]");
+  db->side_sms = side_sms;
   return SSW_OK;
 }
 

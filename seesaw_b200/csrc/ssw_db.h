@@ -54,6 +54,11 @@ struct ssw_db {
   cudaStream_t xstream = nullptr;
   cudaEvent_t ev_scan = nullptr, ev_xdone = nullptr;
   bool pipe_pending = false;
+  // ... on `side_sms` SMs of its own: the pipelined scan runs on a grid of sm_count - side_sms CTAs (its own partition)
+  int side_sms = 4;                // 0 = the exchange blocks co-reside with the scan CTAs instead
+  int side_grid = 0;               // grid d_part_side was built for (0 = not built)
+  int32_t* d_part_side = nullptr;  // [side_grid * kScanWarps + 1]
+  int64_t side_max_cta_images = 0;
   struct ScanWs {                  // the second set of scan workspaces (swapped with the fields above per pipelined call)
     uint64_t* keys = nullptr;
     int32_t* dbidx = nullptr;
@@ -79,6 +84,10 @@ struct ssw_db {
 };
 
 namespace ssw {
+
+#ifdef SSW_TRACE
+extern unsigned long long* g_trace_block;   // development timeline block of the handle that enabled ssw_scan_stats
+#endif
 
 constexpr int kScanWarps = 8;             // warps per CTA of the streaming scan
 constexpr int kMergeCap = 8192;           // candidates the merge kernel sorts in shared memory
@@ -108,8 +117,17 @@ bool scan_tc_supported(const ssw_db* db, int k);
 size_t scan_tc_workspace_bytes(int dim, int grid);
 // d_cand_keys / d_cand_dbidx: [nq][grid * (k + kScanTcSlack)] compacted candidates, d_cand_cnt [nq] their number per query
 constexpr int kScanTcSlack = 8;
+// `grid`: CTAs of this launch with their partition (null = the database's own: one CTA per SM)
+struct ScanTcGrid {
+  int grid;
+  const int32_t* part;             // [grid * kScanWarps + 1]
+  int64_t max_cta_images;
+};
 int launch_scan_tc(ssw_db* db, const float* d_queries, int nq, int k, const uint32_t* d_excl, uint64_t* d_cand_keys,
-                   int32_t* d_cand_dbidx, int32_t* d_cand_cnt, uint64_t* d_gthr, void* workspace, cudaStream_t st);
+                   int32_t* d_cand_dbidx, int32_t* d_cand_cnt, uint64_t* d_gthr, void* workspace, cudaStream_t st,
+                   const ScanTcGrid* grid = nullptr);
+// image partition for `grid` CTAs computed on the device (same rule as the database's own); d_max_cta: most images per CTA
+int launch_part_build(ssw_db* db, int grid, int32_t* d_part, int* d_max_cta, cudaStream_t st);
 // merge kernel (K4)
 int launch_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_lists, int64_t list_stride,
                  int64_t query_stride, int nq, int k, const uint64_t* d_thr, uint64_t* d_out_key,
@@ -122,11 +140,12 @@ int launch_exchange_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_
                           int rank, int nq_cap, int k_cap, uint32_t epoch, int* d_timed_out, uint64_t* d_out_key,
                           int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row, int32_t* d_out_count,
                           cudaStream_t st, bool pdl = false, const int32_t* d_counts = nullptr);
-// slim exchange for the pipelined sharded step (co-resides with the next step's scan kernel)
+// slim exchange for the pipelined sharded step: side_blocks > 0 = that many 1024-thread blocks on SMs of their own,
+// 0 = one 128-thread block per query next to the scan CTAs
 int launch_exchange_slim(const uint64_t* d_keys, const int32_t* d_dbidx, int64_t query_stride, int nq, int k,
                          const int32_t* d_counts, void* const* peers, int world, int rank, int nq_cap, int k_cap, uint32_t epoch,
                          int* d_timed_out, uint64_t* d_out_key, int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row,
-                         int32_t* d_out_count, cudaStream_t st);
+                         int32_t* d_out_count, cudaStream_t st, int side_blocks);
 int launch_image_max(ssw_db* db, const float* d_scores, const uint8_t* d_row_mask, const uint32_t* d_excl,
                      int64_t n_padded, uint64_t* d_keys, int32_t* d_dbidx, cudaStream_t st, const uint32_t* d_pos = nullptr);
 int launch_order_to_pos(const int64_t* d_order, int64_t n_order, int64_t n_rows, uint32_t* d_pos, cudaStream_t st);

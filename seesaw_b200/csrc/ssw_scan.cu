@@ -21,6 +21,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "ssw_db.h"
 
@@ -533,9 +534,10 @@ struct MergeArgs {
 
 // One MSB-first radix-select step over 8 bits: given the histogram of byte d of the keys that match
 // the prefix above it, warp 0 finds the bin holding the `remaining`-th largest key.
-__device__ __forceinline__ void merge_pick_bin(const int* hist, int d, uint64_t* s_prefix, int* s_remaining) {
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
+// `tid`: thread index within the block (or within the 128-thread group of the slim exchange kernel).
+__device__ __forceinline__ void merge_pick_bin(const int* hist, int d, uint64_t* s_prefix, int* s_remaining, int tid) {
+  if (tid < 32) {
+    const int lane = tid;
     // lane l owns bins 255-8l .. 248-8l (descending order of key value)
     int c[8], tot = 0;
 #pragma unroll
@@ -641,7 +643,7 @@ __device__ __forceinline__ int merge_gather(const MergeSmem& M, const uint64_t* 
         if (match) atomicAdd(&M.hist[(int)((key >> (8 * d)) & 255)], 1);
       }
       __syncthreads();
-      merge_pick_bin(M.hist, d, M.prefix, M.remaining);
+      merge_pick_bin(M.hist, d, M.prefix, M.remaining, threadIdx.x);
       __syncthreads();
     }
     n = gather(*M.prefix);
@@ -714,7 +716,7 @@ __device__ __forceinline__ int merge_select_sort(const MergeSmem& M, int n, int 
         if (match) atomicAdd(&M.hist[(int)((key >> (8 * d)) & 255)], 1);
       }
       __syncthreads();
-      merge_pick_bin(M.hist, d, M.prefix, M.remaining);
+      merge_pick_bin(M.hist, d, M.prefix, M.remaining, threadIdx.x);
       __syncthreads();
     }
     const uint64_t T = *M.prefix;     // the k-th largest key
@@ -832,6 +834,10 @@ struct XchgArgs {
   void* peers[8];              // exchange buffer of every rank, as mapped on this device
   int world, rank, nq_cap, k_cap;
   uint32_t epoch;              // strictly increasing per call, same on all ranks
+  int nq;                      // queries of the step (the slim kernel's groups loop over them)
+#ifdef SSW_TRACE
+  unsigned long long* trace;   // development timeline (ssw_scan_stats block): %globaltimer at entry / exit of the first 8 blocks
+#endif
   int* timed_out;              // set to 1 when a peer's flag did not arrive within kXchgTimeoutNs
 };
 
@@ -935,170 +941,202 @@ int launch_exchange_merge(const uint64_t* d_keys, const int32_t* d_dbidx, int n_
 }
 
 // ------------------------------------------------------------------------------------------
-// K4x, slim form for the PIPELINED sharded step: the same shard merge + peer exchange + world merge, written to
-// co-reside with the next step's scan kernel on the same SMs (128 threads, <= 48 registers, 3 KB of static shared
-// memory: the scan CTA leaves 6.4k registers and ~20 KB per SM free), so that the exchange of step i — including the
-// wait for the slowest peer — runs UNDER the scan of step i+1 instead of after its own.  Input is the batched scan's
-// compacted candidate array; k <= 64, world * k <= 1024.
+// K4x, slim form for the PIPELINED sharded step: the same shard merge + peer exchange + world merge, run on a second
+// stream so that the exchange of step i — including the wait for the slowest peer — lies UNDER the scan of step i+1
+// instead of after its own.  A query is served by a GROUP of 128 threads (its own named barrier and 2.6 KB of shared
+// memory); input is the batched scan's compacted candidate array; k <= 64, world * k <= 1024.  Two launch shapes:
+//  * side blocks <S blocks x 8 groups> (default): the pipelined scan runs on (SM count - S) CTAs and these S blocks of
+//    1024 threads cannot share an SM with a scan CTA (it leaves 6.4k registers), so whichever kernel is placed first
+//    the two end up on DISJOINT SMs: the exchange costs the scan nothing but the S SMs it gave up.
+//  * co-resident blocks <nq blocks x 1 group> (side SMs = 0): 128 threads, <= 48 registers, next to a scan CTA on the
+//    same SM.  Measured at 8 GPUs: the scan kernel slows from 216 to 243 us with these blocks next to it.
 // ------------------------------------------------------------------------------------------
-constexpr int kSlimThreads = 128;
+constexpr int kSlimThreads = 128;    // threads of one group
 
-// The slim kernel shares its SMs with a running scan CTA whose epilogue is issue-latency bound, so it must execute
-// few instructions: the k best of n keys are found by an 8-pass MSB radix select (n / 128 keys per thread and pass)
-// and only those <= k survivors are ranked by counting (k^2 compares), instead of ranking all n (n^2).
-// `at(e)` maps entry e to its offset in keys / dbs.  Leaves the best min(n_valid, k) entries, sorted best first, in
-// ok / od (other slots 0 / -1).  Ends with a barrier.
+struct SlimSmem {                    // scratch of one group
+  uint64_t k[64];                    // survivors of the select
+  uint64_t ok[64];                   // the best k, sorted best first
+  uint64_t prefix;
+  int32_t d[64];
+  int32_t od[64];
+  int hist[256];
+  int cnt, remaining;
+};
+
+// barrier of group g (named barriers 1..8; barrier 0 is left to __syncthreads)
+__device__ __forceinline__ void slim_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(kSlimThreads) : "memory"); }
+
+// The slim kernel must execute few instructions (in its co-resident shape it shares SMs with a scan CTA whose epilogue
+// is issue-latency bound): the k best of n keys are found by an 8-pass MSB radix select (n / 128 keys per thread and
+// pass) and only those <= k survivors are ranked by counting (k^2 compares), instead of ranking all n (n^2).
+// `at(e)` maps entry e to its offset in keys / dbs; tid = thread within the group g.  Leaves the best min(n_valid, k)
+// entries, sorted best first, in S.ok / S.od (other slots 0 / -1).  Ends with a group barrier.
 template <bool CG, typename At>
-__device__ __forceinline__ void slim_topk(const uint64_t* keys, const int32_t* dbs, int n, At at, int k, uint64_t* s_k,
-                                          int32_t* s_d, int* s_hist, uint64_t* s_prefix, int* s_remaining, int* s_cnt,
-                                          uint64_t* ok, int32_t* od) {
-  const int tid = threadIdx.x;
+__device__ __forceinline__ void slim_topk(const uint64_t* keys, const int32_t* dbs, int n, At at, int k, SlimSmem& S, int tid,
+                                          int g) {
   auto ldk = [&](int e) { return CG ? __ldcg(keys + at(e)) : keys[at(e)]; };
   if (tid == 0) {
-    *s_prefix = 0;
-    *s_remaining = k;
-    *s_cnt = 0;
+    S.prefix = 0;
+    S.remaining = k;
+    S.cnt = 0;
   }
   for (int i = tid; i < k; i += kSlimThreads) {
-    ok[i] = 0ull;
-    od[i] = -1;
+    S.ok[i] = 0ull;
+    S.od[i] = -1;
   }
-  __syncthreads();
+  slim_sync(g);
   uint64_t T = 1;                        // fewer than k valid keys: keep them all
   int valid = 0;
   for (int e = tid; e < n; e += kSlimThreads) valid += ldk(e) != 0ull;
-  if (valid) atomicAdd(s_cnt, valid);
-  __syncthreads();
-  const int n_valid = *s_cnt;
-  __syncthreads();
-  if (tid == 0) *s_cnt = 0;
+  if (valid) atomicAdd(&S.cnt, valid);
+  slim_sync(g);
+  const int n_valid = S.cnt;
+  slim_sync(g);
+  if (tid == 0) S.cnt = 0;
   if (n_valid > k) {
     for (int d = 7; d >= 0; --d) {
-      for (int i = tid; i < 256; i += kSlimThreads) s_hist[i] = 0;
-      __syncthreads();
-      const uint64_t prefix = *s_prefix;
+      for (int i = tid; i < 256; i += kSlimThreads) S.hist[i] = 0;
+      slim_sync(g);
+      const uint64_t prefix = S.prefix;
       for (int e = tid; e < n; e += kSlimThreads) {
         const uint64_t key = ldk(e);
         const bool match = (d == 7) || ((key >> (8 * (d + 1))) == (prefix >> (8 * (d + 1))));
-        if (match && key != 0ull) atomicAdd(&s_hist[(int)((key >> (8 * d)) & 255)], 1);
+        if (match && key != 0ull) atomicAdd(&S.hist[(int)((key >> (8 * d)) & 255)], 1);
       }
-      __syncthreads();
-      merge_pick_bin(s_hist, d, s_prefix, s_remaining);
-      __syncthreads();
+      slim_sync(g);
+      merge_pick_bin(S.hist, d, &S.prefix, &S.remaining, tid);
+      slim_sync(g);
     }
-    T = *s_prefix;                       // the k-th largest key (keys are unique)
+    T = S.prefix;                        // the k-th largest key (keys are unique)
   }
-  __syncthreads();
+  slim_sync(g);
   for (int e = tid; e < n; e += kSlimThreads) {
     const uint64_t key = ldk(e);
     if (key != 0ull && key >= T) {
-      const int p = atomicAdd(s_cnt, 1);
+      const int p = atomicAdd(&S.cnt, 1);
       if (p < 64) {
-        s_k[p] = key;
-        s_d[p] = CG ? __ldcg(dbs + at(e)) : dbs[at(e)];
+        S.k[p] = key;
+        S.d[p] = CG ? __ldcg(dbs + at(e)) : dbs[at(e)];
       }
     }
   }
-  __syncthreads();
-  const int m = min(*s_cnt, 64);
+  slim_sync(g);
+  const int m = min(S.cnt, 64);
   for (int i = tid; i < m; i += kSlimThreads) {
-    const uint64_t mine = s_k[i];
+    const uint64_t mine = S.k[i];
     int rank = 0;
-    for (int j = 0; j < m; ++j) rank += s_k[j] > mine;
+    for (int j = 0; j < m; ++j) rank += S.k[j] > mine;
     if (rank < k) {
-      ok[rank] = mine;
-      od[rank] = s_d[i];
+      S.ok[rank] = mine;
+      S.od[rank] = S.d[i];
     }
   }
-  __syncthreads();
+  slim_sync(g);
 }
 
-__global__ void __launch_bounds__(kSlimThreads, 10) exchange_slim_kernel(const XchgArgs x) {
-  __shared__ uint64_t s_k[64];
-  __shared__ int32_t s_d[64];
-  __shared__ uint64_t s_ok[64];
-  __shared__ int32_t s_od[64];
-  __shared__ int s_hist[256], s_cnt, s_remaining;
-  __shared__ uint64_t s_prefix;
+// Group (blockIdx.x, g) serves queries first, first + stride, ...  — the same order on every rank, and a group raises
+// the flags of ALL its queries before it waits for any, so the waits cannot deadlock whatever is resident.
+template <int GROUPS>
+__global__ void __launch_bounds__(kSlimThreads * GROUPS, GROUPS == 1 ? 10 : 1) exchange_slim_kernel(const XchgArgs x) {
+  __shared__ SlimSmem s_all[GROUPS];
+  const int g = threadIdx.x / kSlimThreads, tid = threadIdx.x % kSlimThreads;
+  SlimSmem& S = s_all[g];
   const MergeArgs& a = x.m;
-  const int q = blockIdx.x, tid = threadIdx.x, k = a.k;
+  const int k = a.k, nq = x.nq;
+  const int first = blockIdx.x * GROUPS + g, stride = gridDim.x * GROUPS;
   const int par = (int)(x.epoch & 1u);
-  // ---- 1. this shard's top-k from its compacted candidates
-  const uint64_t* kq = a.keys + (int64_t)q * a.query_stride;
-  const int32_t* dq = a.dbidx + (int64_t)q * a.query_stride;
-  slim_topk<false>(kq, dq, a.counts[q], [](int e) { return (int64_t)e; }, k, s_k, s_d, s_hist, &s_prefix, &s_remaining, &s_cnt,
-                   s_ok, s_od);
-  // ---- 2. store it into slot `rank` of every rank's buffer (own included), then raise the flags
-  const size_t slot = (((size_t)par * x.world + x.rank) * x.nq_cap + q);
-  for (int p = 0; p < x.world; ++p) {
-    uint8_t* base = static_cast<uint8_t*>(x.peers[p]);
-    uint64_t* pk = reinterpret_cast<uint64_t*>(base) + slot * x.k_cap;
-    int32_t* pd = reinterpret_cast<int32_t*>(base + xchg_keys_bytes(x.world, x.nq_cap, x.k_cap)) + slot * x.k_cap;
-    for (int i = tid; i < k; i += kSlimThreads) {
-      pk[i] = s_ok[i];
-      pd[i] = s_od[i];
+  const size_t keys_bytes = xchg_keys_bytes(x.world, x.nq_cap, x.k_cap);
+  const size_t flags_off = keys_bytes + xchg_dbidx_bytes(x.world, x.nq_cap, x.k_cap);
+#ifdef SSW_TRACE
+  unsigned long long* tr = (x.trace && threadIdx.x == 0 && blockIdx.x < 8) ? x.trace + 16 + (160 + par) * 16 + 2 * blockIdx.x : nullptr;
+  if (tr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[0]));
+#endif
+  for (int q = first; q < nq; q += stride) {
+    // ---- 1. this shard's top-k from its compacted candidates
+    const uint64_t* kq = a.keys + (int64_t)q * a.query_stride;
+    const int32_t* dq = a.dbidx + (int64_t)q * a.query_stride;
+    slim_topk<false>(kq, dq, a.counts[q], [](int e) { return (int64_t)e; }, k, S, tid, g);
+    // ---- 2. store it into slot `rank` of every rank's buffer (own included), then raise the flags
+    const size_t slot = (((size_t)par * x.world + x.rank) * x.nq_cap + q);
+    for (int p = 0; p < x.world; ++p) {
+      uint8_t* base = static_cast<uint8_t*>(x.peers[p]);
+      uint64_t* pk = reinterpret_cast<uint64_t*>(base) + slot * x.k_cap;
+      int32_t* pd = reinterpret_cast<int32_t*>(base + keys_bytes) + slot * x.k_cap;
+      for (int i = tid; i < k; i += kSlimThreads) {
+        pk[i] = S.ok[i];
+        pd[i] = S.od[i];
+      }
+    }
+    slim_sync(g);       // the group's stores are ordered before the flag threads' system fence (fences are cumulative)
+    if (tid < x.world) {
+      uint32_t* flag = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(x.peers[tid]) + flags_off) + slot;
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(x.epoch) : "memory");
     }
   }
-  __syncthreads();
-  if (tid < x.world) {
-    uint8_t* base = static_cast<uint8_t*>(x.peers[tid]);
-    uint32_t* flag = reinterpret_cast<uint32_t*>(base + xchg_keys_bytes(x.world, x.nq_cap, x.k_cap) +
-                                                 xchg_dbidx_bytes(x.world, x.nq_cap, x.k_cap)) + slot;
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(x.epoch) : "memory");
-  }
-  // ---- 3. wait until every rank's slot of THIS rank's buffer carries this epoch
   uint8_t* mine = static_cast<uint8_t*>(x.peers[x.rank]);
-  if (tid < x.world) {
-    const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine + xchg_keys_bytes(x.world, x.nq_cap, x.k_cap) +
-                                                             xchg_dbidx_bytes(x.world, x.nq_cap, x.k_cap)) +
-                           (((size_t)par * x.world + tid) * x.nq_cap + q);
-    uint32_t v;
-    unsigned long long t0, t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    do {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-      if (v != x.epoch) {
-        __nanosleep(500);       // the next step's scan shares this SM: do not burn its issue slots
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > kXchgTimeoutNs) {
-          if (x.timed_out) *x.timed_out = 1;
-          break;
+  for (int q = first; q < nq; q += stride) {
+    // ---- 3. wait until every rank's slot of THIS rank's buffer carries this epoch
+    if (tid < x.world) {
+      const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine + flags_off) + (((size_t)par * x.world + tid) * x.nq_cap + q);
+      uint32_t v;
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v != x.epoch) {
+          __nanosleep(500);       // co-resident shape: the next step's scan shares this SM, do not burn its issue slots
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          if (t1 - t0 > kXchgTimeoutNs) {
+            if (x.timed_out) *x.timed_out = 1;
+            break;
+          }
         }
-      }
-    } while (v != x.epoch);
+      } while (v != x.epoch);
+    }
+    slim_sync(g);
+    // ---- 4. merge the world's lists (read through L2: they were written by other GPUs)
+    const size_t q0 = ((size_t)par * x.world) * x.nq_cap + q;
+    const uint64_t* wk = reinterpret_cast<const uint64_t*>(mine) + q0 * x.k_cap;
+    const int32_t* wd = reinterpret_cast<const int32_t*>(mine + keys_bytes) + q0 * x.k_cap;
+    const int64_t lstride = (int64_t)x.nq_cap * x.k_cap;
+    slim_topk<true>(wk, wd, x.world * k, [=](int e) { return (int64_t)(e / k) * lstride + (e % k); }, k, S, tid, g);
+    int cnt = 0;
+    for (int i = tid; i < k; i += kSlimThreads) {
+      const uint64_t key = S.ok[i];
+      const bool valid = key != 0ull;
+      cnt += valid;
+      const int64_t o = (int64_t)q * k + i;
+      if (a.out_key) a.out_key[o] = key;
+      if (a.out_dbidx) a.out_dbidx[o] = valid ? S.od[i] : -1;
+      if (a.out_score) a.out_score[o] = valid ? key_score(key) : -INFINITY;
+      if (a.out_row) a.out_row[o] = valid ? (int64_t)key_row(key) : -1;
+    }
+    // count of valid slots: group-wide sum of the per-thread partials
+    if (tid == 0) S.cnt = 0;
+    slim_sync(g);
+    if (cnt) atomicAdd(&S.cnt, cnt);
+    slim_sync(g);
+    if (tid == 0 && a.out_count) a.out_count[q] = S.cnt;
+    slim_sync(g);       // S is reused by the group's next query
   }
-  __syncthreads();
-  // ---- 4. merge the world's lists (read through L2: they were written by other GPUs)
-  const size_t q0 = ((size_t)par * x.world) * x.nq_cap + q;
-  const uint64_t* wk = reinterpret_cast<const uint64_t*>(mine) + q0 * x.k_cap;
-  const int32_t* wd = reinterpret_cast<const int32_t*>(mine + xchg_keys_bytes(x.world, x.nq_cap, x.k_cap)) + q0 * x.k_cap;
-  const int64_t lstride = (int64_t)x.nq_cap * x.k_cap;
-  slim_topk<true>(wk, wd, x.world * k, [=](int e) { return (int64_t)(e / k) * lstride + (e % k); }, k, s_k, s_d, s_hist,
-                  &s_prefix, &s_remaining, &s_cnt, s_ok, s_od);
-  int cnt = 0;
-  for (int i = tid; i < k; i += kSlimThreads) {
-    const uint64_t key = s_ok[i];
-    const bool valid = key != 0ull;
-    cnt += valid;
-    const int64_t o = (int64_t)q * k + i;
-    if (a.out_key) a.out_key[o] = key;
-    if (a.out_dbidx) a.out_dbidx[o] = valid ? s_od[i] : -1;
-    if (a.out_score) a.out_score[o] = valid ? key_score(key) : -INFINITY;
-    if (a.out_row) a.out_row[o] = valid ? (int64_t)key_row(key) : -1;
-  }
-  // count of valid slots: block-wide sum of the per-thread partials
-  if (tid == 0) s_cnt = 0;
-  __syncthreads();
-  if (cnt) atomicAdd(&s_cnt, cnt);
-  __syncthreads();
-  if (tid == 0 && a.out_count) a.out_count[q] = s_cnt;
+#ifdef SSW_TRACE
+  if (tr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[1]));
+#endif
 }
 
+#ifdef SSW_TRACE
+unsigned long long* g_trace_block = nullptr;      // set by ssw_scan_stats
+#endif
+
+constexpr int kSideGroups = 8;       // groups per side block: 1024 threads, too many to fit next to a scan CTA
+
+// side_blocks > 0: that many blocks of kSideGroups groups (disjoint SMs from the pipelined scan); 0: one co-resident
+// 128-thread block per query.
 int launch_exchange_slim(const uint64_t* d_keys, const int32_t* d_dbidx, int64_t query_stride, int nq, int k,
                          const int32_t* d_counts, void* const* peers, int world, int rank, int nq_cap, int k_cap, uint32_t epoch,
                          int* d_timed_out, uint64_t* d_out_key, int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row,
-                         int32_t* d_out_count, cudaStream_t st) {
+                         int32_t* d_out_count, cudaStream_t st, int side_blocks) {
   XchgArgs x{};
   x.timed_out = d_timed_out;
   x.m = MergeArgs{d_keys, d_dbidx, 1, query_stride, query_stride, k, d_counts, nullptr,
@@ -1109,7 +1147,52 @@ int launch_exchange_slim(const uint64_t* d_keys, const int32_t* d_dbidx, int64_t
   x.nq_cap = nq_cap;
   x.k_cap = k_cap;
   x.epoch = epoch;
-  exchange_slim_kernel<<<nq, kSlimThreads, 0, st>>>(x);
+  x.nq = nq;
+#ifdef SSW_TRACE
+  x.trace = g_trace_block;
+  if (getenv("SSW_SIDE_CARVEOUT")) {     // experiment: same shared-memory configuration as the scan kernel
+    cudaFuncSetAttribute(exchange_slim_kernel<kSideGroups>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("SSW_SIDE_CARVEOUT")));
+    cudaFuncSetAttribute(exchange_slim_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("SSW_SIDE_CARVEOUT")));
+  }
+#endif
+  if (side_blocks > 0)
+    exchange_slim_kernel<kSideGroups><<<side_blocks, kSlimThreads * kSideGroups, 0, st>>>(x);
+  else
+    exchange_slim_kernel<1><<<nq, kSlimThreads, 0, st>>>(x);
+  SSW_LAUNCHED();
+  return SSW_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// scan partition for a grid other than the database's own (the pipelined sharded step scans on SM count - S CTAs):
+// the same rule as build_layout — range g of `ranges` starts at the first image whose first row is >= n_rows * g / ranges —
+// evaluated on the device from the CSR.  out_max_cta: most images any CTA (kScanWarps consecutive ranges) holds.
+// ------------------------------------------------------------------------------------------
+__global__ void part_build_kernel(const int64_t* __restrict__ row_ptr, int64_t n_images, int64_t n_rows, int ranges,
+                                  int32_t* __restrict__ part, int* __restrict__ out_max_cta) {
+  __shared__ int s_max;
+  if (threadIdx.x == 0) s_max = 0;
+  for (int g = threadIdx.x; g <= ranges; g += blockDim.x) {
+    const int64_t target = n_rows * g / ranges;          // n_rows < 2^32, ranges < 2^12
+    int64_t lo = 0, hi = n_images + 1;                   // first position of row_ptr[0 .. n_images] with value >= target
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (row_ptr[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    if (lo > n_images) lo = n_images;
+    if (g == 0) lo = 0;
+    if (g == ranges) lo = n_images;
+    part[g] = (int32_t)lo;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < ranges / kScanWarps; c += blockDim.x)
+    atomicMax(&s_max, part[(c + 1) * kScanWarps] - part[c * kScanWarps]);
+  __syncthreads();
+  if (threadIdx.x == 0) *out_max_cta = s_max;
+}
+
+int launch_part_build(ssw_db* db, int grid, int32_t* d_part, int* d_max_cta, cudaStream_t st) {
+  part_build_kernel<<<1, 1024, 0, st>>>(db->d_row_ptr, db->n_images, db->n_rows, grid * kScanWarps, d_part, d_max_cta);
   SSW_LAUNCHED();
   return SSW_OK;
 }

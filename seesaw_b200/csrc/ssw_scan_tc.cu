@@ -57,11 +57,21 @@ struct ScanTcArgs {
   unsigned long long* stats; // [2] list updates / images offered to a list, summed over the grid (null = not counted)
 };
 
-// Development-only timeline (make EXTRA=-DSSW_TRACE): clock64 stamps of one CTA's phases into a.stats[16 + ...]
+// Development-only timeline (make EXTRA=-DSSW_TRACE): clock64 stamps of one CTA's phases into a.stats[16 + ...];
+// EXTRA=-DSSW_TRACE=2 stamps %globaltimer instead (ns, comparable across SMs and kernels: scripts/trace_pipe.py)
 #ifdef SSW_TRACE
-#define SSW_TR(slot, cond)                                                                                  \
-  do {                                                                                                      \
-    if (a.stats && (cond)) reinterpret_cast<long long*>(a.stats)[16 + blockIdx.x * 16 + (slot)] = clock64(); \
+__device__ __forceinline__ long long ssw_trace_now() {
+#if SSW_TRACE == 2
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return (long long)t;
+#else
+  return clock64();
+#endif
+}
+#define SSW_TR(slot, cond)                                                                                        \
+  do {                                                                                                            \
+    if (a.stats && (cond)) reinterpret_cast<long long*>(a.stats)[16 + blockIdx.x * 16 + (slot)] = ssw_trace_now(); \
   } while (0)
 #else
 #define SSW_TR(slot, cond) do { } while (0)
@@ -705,7 +715,7 @@ __global__ void __launch_bounds__(kScanTc8Threads, 1) scan_tc8_kernel(const __gr
 }
 
 template <int DIM, int NT, int NS, int NACC>
-static int launch_scan_tc_t(ssw_db* db, const ScanTcArgs& a, cudaStream_t st) {
+static int launch_scan_tc_t(ssw_db* db, const ScanTcArgs& a, cudaStream_t st, int grid, int64_t max_cta_images) {
   using Cfg = TcCfg<DIM, NT, NACC>;
   CUtensorMap tmap;
   int rc = make_tmap_f16_rows(&tmap, db->d_vecs, db->n_rows, DIM, NT);
@@ -714,7 +724,7 @@ static int launch_scan_tc_t(ssw_db* db, const ScanTcArgs& a, cudaStream_t st) {
   ScanTcArgs a2 = a;
   a2.excl_slice_words = 0;
   if (a.excl) {   // keep the CTA's slice of the bitmaps in shared memory when it fits (227 KB per CTA)
-    const int words = (int)(db->max_cta_images / 32) + 2;
+    const int words = (int)(max_cta_images / 32) + 2;
     if (smem + (size_t)64 * words * 4 <= 232448) {
       a2.excl_slice_words = words;
       smem += (size_t)64 * words * 4;
@@ -725,7 +735,7 @@ static int launch_scan_tc_t(ssw_db* db, const ScanTcArgs& a, cudaStream_t st) {
   prof_begin(db, st);      // times the scan kernel alone (not the query preparation)
   // programmatic dependent launch: the kernel's set-up runs under the tail of the preparation kernel (an event
   // record between the two would serialise them, so not while profiling)
-  SSW_CUDA(launch_kernel(kern, dim3(db->scan_grid), dim3(kScanTc8Threads), smem, st, !db->prof_sampled, tmap, a2));
+  SSW_CUDA(launch_kernel(kern, dim3(grid), dim3(kScanTc8Threads), smem, st, !db->prof_sampled, tmap, a2));
   prof_end(db, st);
   SSW_LAUNCHED();
   return SSW_OK;
@@ -740,12 +750,15 @@ size_t scan_tc_workspace_bytes(int dim, int grid) { return (size_t)128 * (dim / 
 // One pass over the database for queries [0, nq), nq <= 64.  `workspace` holds the prepared A operand
 // (scan_tc_workspace_bytes); the preparation kernel also zeroes the queries' shared thresholds.
 int launch_scan_tc(ssw_db* db, const float* d_queries, int nq, int k, const uint32_t* d_excl, uint64_t* d_cand_keys,
-                   int32_t* d_cand_dbidx, int32_t* d_cand_cnt, uint64_t* d_gthr, void* workspace, cudaStream_t st) {
+                   int32_t* d_cand_dbidx, int32_t* d_cand_cnt, uint64_t* d_gthr, void* workspace, cudaStream_t st,
+                   const ScanTcGrid* sg) {
+  const int grid = sg ? sg->grid : db->scan_grid;
+  const int64_t max_cta_images = sg ? sg->max_cta_images : db->max_cta_images;
   uint32_t* a_img = static_cast<uint32_t*>(workspace);
   float* inv_scale = reinterpret_cast<float*>(a_img + (size_t)128 * (db->dim / 2));
   uint32_t* pub = reinterpret_cast<uint32_t*>(inv_scale + 64);
   scan_tc_prep_kernel<<<128, db->dim / 2, 0, st>>>(d_queries, nq, db->dim, a_img, inv_scale, d_gthr, d_cand_cnt, pub,
-                                                     64 * db->scan_grid);
+                                                     64 * grid);
   SSW_LAUNCHED();
   ScanTcArgs a{};
   a.a_img = a_img;
@@ -758,7 +771,7 @@ int launch_scan_tc(ssw_db* db, const float* d_queries, int nq, int k, const uint
   a.row_ptr = db->d_row_ptr;
   a.img_dbidx = db->d_img_dbidx;
   a.orig_row = db->d_orig_row;
-  a.part = db->d_part;
+  a.part = sg ? sg->part : db->d_part;
   a.cand_keys = d_cand_keys;
   a.cand_dbidx = d_cand_dbidx;
   a.cand_cnt = d_cand_cnt;
@@ -768,11 +781,11 @@ int launch_scan_tc(ssw_db* db, const float* d_queries, int nq, int k, const uint
   a.stats = db->d_scan_stats;
   // shared memory: NS stages of NT*128 B + 64 lists of k (key, image) pairs (k <= 64 -> <= 48 KB)
   switch (db->dim) {
-    case 256: return launch_scan_tc_t<256, 128, 10, 2>(db, a, st);
-    case 512: return launch_scan_tc_t<512, 128, 10, 2>(db, a, st);
+    case 256: return launch_scan_tc_t<256, 128, 10, 2>(db, a, st, grid, max_cta_images);
+    case 512: return launch_scan_tc_t<512, 128, 10, 2>(db, a, st, grid, max_cta_images);
     // 768: A takes 384 of the 512 TMEM columns; one 128-column accumulator (MMA and epilogue alternate,
     // together well under the tile's HBM time) beats two 64-column ones (twice the per-tile overhead)
-    case 768: return launch_scan_tc_t<768, 128, 10, 1>(db, a, st);
+    case 768: return launch_scan_tc_t<768, 128, 10, 1>(db, a, st, grid, max_cta_images);
   }
   set_error("batched scan supports dim 256, 512 or 768");
   return SSW_ERR_INVALID;

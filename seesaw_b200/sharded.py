@@ -144,6 +144,12 @@ class ShardedPatchDatabase:
         s = torch.cuda.current_stream(self.local.device) if stream is None else stream
         check(lib.ssw_scan_pipeline_drain(self.local._h, C.c_void_p(s.cuda_stream)))
 
+    def set_side_sms(self, side_sms):
+        """SMs the pipelined step leaves to its exchange blocks (default 4; 0 = small exchange blocks next to the scan
+        CTAs).  Call between steps, after :meth:`drain`."""
+        from ._lib import check, lib
+        check(lib.ssw_scan_pipeline_side_sms(self.local._h, int(side_sms)))
+
     def _scan_fused(self, d_queries, k, d_exclude_bits, stream=None, pipelined=False):
         import ctypes as C
 
