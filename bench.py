@@ -294,8 +294,9 @@ def main():
     ap.add_argument("--no-config5", action="store_true", help="skip the 100M x 768 leg (N=8)")
     ap.add_argument("--nccl-exchange", action="store_true", help="N>1: use NCCL all-gather instead of the fused exchange kernel")
     ap.add_argument("--no-pipeline", action="store_true", help="N>1: do not overlap a step's exchange with the next step's scan")
-    ap.add_argument("--side-sms", type=int, default=4,
-                    help="N>1, pipelined: SMs left to the exchange blocks (the scan runs on the others); 0 = exchange blocks next to the scan CTAs")
+    ap.add_argument("--side-sms", type=int, default=-1,
+                    help="N>1, pipelined: SMs left to the exchange blocks (the scan runs on the others); 0 = exchange blocks next to "
+                         "the scan CTAs, -1 = the library's choice by shard size")
     ap.add_argument("--cpu-sample-images", type=int, default=0, help="CPU arm on the first N images only (tests; default: the full database)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -341,14 +342,13 @@ def main():
     sdb = ShardedPatchDatabase.synthetic(rows_per_image, DIM, seed=DB_SEED, rank=rank, world_size=world,
                                          device=local_rank)
     db = sdb.local
-    exchange = ("fused peer-memory exchange + merge kernel, pipelined: the exchange of step i runs under the scan of step i+1 "
-                f"(ssw_scan_topk_sharded_pipelined_device), {args.side_sms} SMs left to the exchange blocks"
-                if args.side_sms > 0 else
-                "fused peer-memory exchange + merge kernel, pipelined: the exchange of step i runs under the scan of step i+1 "
-                "(ssw_scan_topk_sharded_pipelined_device), exchange blocks next to the scan CTAs")
+    exchange = ""
     if world > 1 and not args.nccl_exchange:
         sdb.enable_fused_exchange(nq_cap=NQ, k_cap=64)
-        sdb.set_side_sms(args.side_sms)
+        side = sdb.set_side_sms(args.side_sms)
+        exchange = ("fused peer-memory exchange + merge kernel, pipelined: the exchange of step i runs under the scan of step i+1 "
+                    "(ssw_scan_topk_sharded_pipelined_device), " +
+                    (f"on {side} SMs of its own (the scan on the other {148 - side})" if side > 0 else "exchange blocks next to the scan CTAs"))
     elif world > 1:
         exchange = "NCCL all-gather + merge kernel"
     if world > 1 and args.no_pipeline and not args.nccl_exchange:

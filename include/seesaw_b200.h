@@ -146,10 +146,11 @@ int ssw_scan_topk_sharded_device(ssw_db* db, const float* d_queries, int nq, int
 
 /* Pipelined form of the same step for a stream of batches (a serving loop): the scan of this call runs on `stream`,
  * its exchange + merge on an internal stream UNDER THE SCAN OF THE NEXT CALL (two sets of scan workspaces alternate).
- * By default the pipelined scan runs on (SM count - 4) CTAs and the exchange on 4 blocks too large to share an SM
- * with a scan CTA, so the two never compete for an SM; ssw_scan_pipeline_side_sms(db, s) changes the number of SMs
- * left to the exchange (0 = one small exchange block per query NEXT TO the scan CTAs; call it between steps, after a
- * drain).  The outputs of a call are complete on `stream`
+ * On small shards (< 2.5 GB) the pipelined scan runs on (SM count - 4) CTAs and the exchange on 4 blocks too large to
+ * share an SM with a scan CTA, so the two never compete for an SM; on larger shards one small exchange block per query
+ * runs NEXT TO the scan CTAs.  ssw_scan_pipeline_side_sms(db, s) fixes the number of SMs left to the exchange (0 = none,
+ * -1 = the automatic choice; call it between steps, after a drain), ..._in_use reports the choice in force.
+ * The outputs of a call are complete on `stream`
  * once the NEXT pipelined call on this handle has been enqueued, or after ssw_scan_pipeline_drain(db, stream) —
  * pass distinct output buffers to consecutive calls.  Same arguments and collective contract as above; nq <= 64,
  * k <= 64, fp16 storage without an exact copy (the batched kernel).  Throughput at 8 GPUs no longer pays the
@@ -161,6 +162,7 @@ int ssw_scan_topk_sharded_pipelined_device(ssw_db* db, const float* d_queries, i
                                            int32_t* d_out_count, void* stream);
 int ssw_scan_pipeline_drain(ssw_db* db, void* stream);
 int ssw_scan_pipeline_side_sms(ssw_db* db, int side_sms);
+int ssw_scan_pipeline_side_sms_in_use(const ssw_db* db, int* side_sms);
 
 /* Host-buffer form of the sharded step (arguments as ssw_scan_topk + the exchange arguments above):
  * one H2D of queries and id lists, bitmap build, scan, fused exchange + merge, one D2H of the results. */

@@ -63,6 +63,7 @@ SIGNATURES = {
                                                          C.c_int, C.c_uint32, _p, _p, _p, _p, _p, _p]),
     "ssw_scan_pipeline_drain": (C.c_int, [_p, _p]),
     "ssw_scan_pipeline_side_sms": (C.c_int, [_p, C.c_int]),
+    "ssw_scan_pipeline_side_sms_in_use": (C.c_int, [_p, C.POINTER(C.c_int)]),
     "ssw_scan_topk_sharded": (C.c_int, [_p, _p, C.c_int, C.c_int, _p, _p, C.POINTER(_p), C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_uint32, _p, _p, _p, _p]),
     "ssw_set_scan_mode": (C.c_int, [_p, C.c_int]),

@@ -617,6 +617,16 @@ int ssw_scan_topk_sharded_device(ssw_db* db, const float* d_queries, int nq, int
                         d_out_count, (cudaStream_t)stream, &xc);
 }
 
+// SMs the pipelined step leaves to its exchange blocks.  Automatic choice (side_sms < 0): giving up 4 of 148 SMs costs
+// the scan up to 2.7 % of its time (it follows the SM count once the boards power-cap their clock), exchange blocks
+// NEXT TO the scan CTAs cost it a roughly constant ~12 us (scan CTAs of the next step find their SM occupied) — so the
+// exchange gets SMs of its own only on small shards (< 2.5 GB: under ~0.4 ms of scan; the 8-GPU shard of 10M x 512).
+static int pipeline_side_sms(const ssw_db* db) {
+  int side = db->side_sms;
+  if (side < 0) side = (double)db->n_rows * db->dim * 2.0 < 2.5e9 ? 4 : 0;
+  return db->sm_count - side >= 64 ? side : 0;
+}
+
 int ssw_scan_topk_sharded_pipelined_device(ssw_db* db, const float* d_queries, int nq, int k, const uint32_t* d_exclude_bits,
                                            void* const* peer_bufs, int world, int rank, int nq_cap, int k_cap, uint32_t epoch,
                                            uint64_t* d_out_key, int32_t* d_out_dbidx, float* d_out_score, int64_t* d_out_row,
@@ -641,7 +651,7 @@ int ssw_scan_topk_sharded_pipelined_device(ssw_db* db, const float* d_queries, i
     *db->d_xchg_timed_out = 0;
   }
   // the scan of a pipelined step leaves `side_sms` SMs to the exchange blocks: its own grid and image partition
-  const int side = (db->side_sms > 0 && db->sm_count - db->side_sms >= 64) ? db->side_sms : 0;
+  const int side = pipeline_side_sms(db);
   const int grid = db->sm_count - side;
   ScanTcGrid sg{grid, db->d_part, db->max_cta_images};
   if (side > 0) {
@@ -690,8 +700,14 @@ int ssw_scan_topk_sharded_pipelined_device(ssw_db* db, const float* d_queries, i
 
 int ssw_scan_pipeline_side_sms(ssw_db* db, int side_sms) {
   SSW_REQUIRE(db != nullptr, "db is null");
-  SSW_REQUIRE(side_sms >= 0 && side_sms <= 16, "side_sms must be in [0, 16]");
+  SSW_REQUIRE(side_sms >= -1 && side_sms <= 16, "side_sms must be in [-1, 16] (-1 = automatic)");
   db->side_sms = side_sms;
+  return SSW_OK;
+}
+
+int ssw_scan_pipeline_side_sms_in_use(const ssw_db* db, int* side_sms) {
+  SSW_REQUIRE(db != nullptr && side_sms != nullptr, "null argument");
+  *side_sms = pipeline_side_sms(db);
   return SSW_OK;
 }
 

@@ -55,7 +55,7 @@ struct ssw_db {
   cudaEvent_t ev_scan = nullptr, ev_xdone = nullptr;
   bool pipe_pending = false;
   // ... on `side_sms` SMs of its own: the pipelined scan runs on a grid of sm_count - side_sms CTAs (its own partition)
-  int side_sms = 4;                // 0 = the exchange blocks co-reside with the scan CTAs instead
+  int side_sms = -1;               // -1 = automatic (by shard size), 0 = the exchange blocks co-reside with the scan CTAs
   int side_grid = 0;               // grid d_part_side was built for (0 = not built)
   int32_t* d_part_side = nullptr;  // [side_grid * kScanWarps + 1]
   int64_t side_max_cta_images = 0;

@@ -145,10 +145,15 @@ class ShardedPatchDatabase:
         check(lib.ssw_scan_pipeline_drain(self.local._h, C.c_void_p(s.cuda_stream)))
 
     def set_side_sms(self, side_sms):
-        """SMs the pipelined step leaves to its exchange blocks (default 4; 0 = small exchange blocks next to the scan
-        CTAs).  Call between steps, after :meth:`drain`."""
+        """SMs the pipelined step leaves to its exchange blocks (-1 = automatic by shard size, the default; 0 = small
+        exchange blocks next to the scan CTAs).  Call between steps, after :meth:`drain`.  Returns the number in force."""
+        import ctypes as C
+
         from ._lib import check, lib
         check(lib.ssw_scan_pipeline_side_sms(self.local._h, int(side_sms)))
+        n = C.c_int(0)
+        check(lib.ssw_scan_pipeline_side_sms_in_use(self.local._h, C.byref(n)))
+        return n.value
 
     def _scan_fused(self, d_queries, k, d_exclude_bits, stream=None, pipelined=False):
         import ctypes as C

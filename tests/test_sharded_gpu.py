@@ -72,7 +72,7 @@ def _exact_sharded_check(rank, world):
 def _pipelined_check(sdb, counts, dbidx, n, qs, excl):
     """Both shapes of the pipelined step: the exchange on SMs of its own (the scan on SM count - 4 or - 2 CTAs with a
     partition of its own) and next to the scan CTAs."""
-    for side in (4, 0, 2):
+    for side in (4, 0, 2, -1):
         sdb.set_side_sms(side)
         _pipelined_steps(sdb, counts, dbidx, n, qs, excl)
 
