@@ -836,7 +836,8 @@ struct XchgArgs {
   uint32_t epoch;              // strictly increasing per call, same on all ranks
   int nq;                      // queries of the step (the slim kernel's groups loop over them)
 #ifdef SSW_TRACE
-  unsigned long long* trace;   // development timeline (ssw_scan_stats block): %globaltimer at entry / exit of the first 8 blocks
+  unsigned long long* trace;   // development timeline (ssw_scan_stats block), first 8 blocks: %globaltimer at entry / exit
+                               // (CTA slot 160 + parity), end of the push phase and ns spent waiting for flags (slot 162 + parity)
 #endif
   int* timed_out;              // set to 1 when a peer's flag did not arrive within kXchgTimeoutNs
 };
@@ -1075,8 +1076,16 @@ __global__ void __launch_bounds__(kSlimThreads * GROUPS, GROUPS == 1 ? 10 : 1) e
     }
   }
   uint8_t* mine = static_cast<uint8_t*>(x.peers[x.rank]);
+#ifdef SSW_TRACE
+  if (tr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[32]));
+  unsigned long long waited = 0;
+#endif
   for (int q = first; q < nq; q += stride) {
     // ---- 3. wait until every rank's slot of THIS rank's buffer carries this epoch
+#ifdef SSW_TRACE
+    unsigned long long w0 = 0, w1 = 0;
+    if (tr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(w0));
+#endif
     if (tid < x.world) {
       const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine + flags_off) + (((size_t)par * x.world + tid) * x.nq_cap + q);
       uint32_t v;
@@ -1095,6 +1104,12 @@ __global__ void __launch_bounds__(kSlimThreads * GROUPS, GROUPS == 1 ? 10 : 1) e
       } while (v != x.epoch);
     }
     slim_sync(g);
+#ifdef SSW_TRACE
+    if (tr) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(w1));
+      waited += w1 - w0;
+    }
+#endif
     // ---- 4. merge the world's lists (read through L2: they were written by other GPUs)
     const size_t q0 = ((size_t)par * x.world) * x.nq_cap + q;
     const uint64_t* wk = reinterpret_cast<const uint64_t*>(mine) + q0 * x.k_cap;
@@ -1121,7 +1136,10 @@ __global__ void __launch_bounds__(kSlimThreads * GROUPS, GROUPS == 1 ? 10 : 1) e
     slim_sync(g);       // S is reused by the group's next query
   }
 #ifdef SSW_TRACE
-  if (tr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[1]));
+  if (tr) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr[1]));
+    tr[33] = waited;
+  }
 #endif
 }
 
