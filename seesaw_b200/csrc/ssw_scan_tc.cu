@@ -73,8 +73,21 @@ __device__ __forceinline__ long long ssw_trace_now() {
   do {                                                                                                            \
     if (a.stats && (cond)) reinterpret_cast<long long*>(a.stats)[16 + blockIdx.x * 16 + (slot)] = ssw_trace_now(); \
   } while (0)
+// ... and cycles spent inside a wait, summed into `acc` and stored by SSW_TRV: which of memory / MMA / epilogue a CTA waits for
+#define SSW_TW(acc, stmt)          \
+  do {                             \
+    const long long _t = clock64(); \
+    stmt;                          \
+    acc += clock64() - _t;         \
+  } while (0)
+#define SSW_TRV(slot, cond, val)                                                                          \
+  do {                                                                                                    \
+    if (a.stats && (cond)) reinterpret_cast<long long*>(a.stats)[16 + blockIdx.x * 16 + (slot)] = (val); \
+  } while (0)
 #else
 #define SSW_TR(slot, cond) do { } while (0)
+#define SSW_TW(acc, stmt) do { stmt; } while (0)
+#define SSW_TRV(slot, cond, val) do { } while (0)
 #endif
 
 constexpr int kTcMaxK = 64;   // per-query list length the batched epilogue keeps in shared memory
@@ -474,16 +487,17 @@ __global__ void __launch_bounds__(kScanTc8Threads, 1) scan_tc8_kernel(const __gr
     if (lane == 0) {
       TcPipe p(NS);
       SSW_TR(3, true);
+      [[maybe_unused]] long long w_ring = 0;        // trace build: cycles the producer waited for a free stage
       for (int t = 0; t < ntiles; ++t) {
         for (int kc = 0; kc < Cfg::KC; ++kc) {
-          mbar_wait_parked(S.empty + 8 * p.stage, p.phase ^ 1);
+          SSW_TW(w_ring, mbar_wait_parked(S.empty + 8 * p.stage, p.phase ^ 1));
           mbar_expect_tx(S.full + 8 * p.stage, Cfg::STAGE_BYTES);
           tma_load_2d(S.stages + p.stage * Cfg::STAGE_BYTES, &tmap, kc * kTcKChunk, (int)(r_begin + (int64_t)t * NT),
                       S.full + 8 * p.stage);
           p.advance();
         }
-        SSW_TR(4, t == 0);
       }
+      SSW_TRV(4, true, w_ring);
       SSW_TR(5, true);
     }
     __syncwarp();       // the idle lanes must not reach the closing __syncthreads ahead of lane 0
@@ -492,12 +506,13 @@ __global__ void __launch_bounds__(kScanTc8Threads, 1) scan_tc8_kernel(const __gr
     mbar_wait_parked(S.a_ready, 0);
     tc_fence_after();
     SSW_TR(6, lane == 0);
+    [[maybe_unused]] long long w_acc = 0, w_full = 0;   // trace build: cycles waited for a free accumulator / for a loaded stage
     for (int t = 0; t < ntiles; ++t) {
       const uint32_t as = NACC == 2 ? (t & 1) : 0;
-      mbar_wait_parked(S.tmem_empty + 8 * as, ((NACC == 2 ? (t >> 1) : t) & 1) ^ 1);
+      SSW_TW(w_acc, mbar_wait_parked(S.tmem_empty + 8 * as, ((NACC == 2 ? (t >> 1) : t) & 1) ^ 1));
       tc_fence_after();
       for (int kc = 0; kc < Cfg::KC; ++kc) {
-        mbar_wait_parked(S.full + 8 * p.stage, p.phase);
+        SSW_TW(w_full, mbar_wait_parked(S.full + 8 * p.stage, p.phase));
         tc_fence_after();
         if (lane == 0) {
           const uint64_t bdesc = make_bdesc_sw128(S.stages + p.stage * Cfg::STAGE_BYTES);
@@ -512,8 +527,9 @@ __global__ void __launch_bounds__(kScanTc8Threads, 1) scan_tc8_kernel(const __gr
       }
       if (lane == 0) tc_commit(S.tmem_full + 8 * as);
       __syncwarp();
-      SSW_TR(7, lane == 0 && t == 0);
     }
+    SSW_TRV(7, lane == 0, w_acc);
+    SSW_TRV(14, lane == 0, w_full);
     SSW_TR(8, lane == 0);
   } else if (warp == 10) {
     scan_tc_threshold_warp(Q, a, lane, 8);
@@ -601,6 +617,7 @@ __global__ void __launch_bounds__(kScanTc8Threads, 1) scan_tc8_kernel(const __gr
     };
     if (ntiles > 0) fetch_bits(0);
     const uint32_t half_addr = (uint32_t)(h * 16) << 16;
+    [[maybe_unused]] long long w_tile = 0;          // trace build: cycles this epilogue warp waited for a finished accumulator
     for (int t = 0; t < ntiles; ++t) {
       const uint32_t as = NACC == 2 ? (t & 1) : 0;
       const int64_t row0 = r_begin + (int64_t)t * NT;
@@ -615,7 +632,7 @@ __global__ void __launch_bounds__(kScanTc8Threads, 1) scan_tc8_kernel(const __gr
       }
       if (t + 1 < ntiles) fetch_bits(t + 1);
       st.thr = thr_to_acc(Q.thr[qA], cx.scale);
-      mbar_wait(S.tmem_full + 8 * as, (NACC == 2 ? (t >> 1) : t) & 1);
+      SSW_TW(w_tile, mbar_wait(S.tmem_full + 8 * as, (NACC == 2 ? (t >> 1) : t) & 1));
       tc_fence_after();
       SSW_TR(9, warp == 2 && lane == 0 && t == 0);
       SSW_TR(12, warp == 2 && lane == 0 && t == ntiles / 2);
@@ -658,6 +675,7 @@ __global__ void __launch_bounds__(kScanTc8Threads, 1) scan_tc8_kernel(const __gr
       }
     }
     __syncwarp();
+    SSW_TRV(15, warp == 2 && lane == 0, w_tile);
     SSW_TR(10, warp == 2 && lane == 0);
     if (lane == 0) atomicAdd(Q.done, 1);
     if (a.stats && lane < 8 && q4 * 16 + h * 8 + lane < a.nq) {
